@@ -1,0 +1,183 @@
+/*
+ * sp_nnue.h -- C-ABI of the B200-native batched NNUE evaluator (libsp_nnue.so).
+ *
+ * The reference engine (Stormphrax 8.0.2) has no plugin/FFI layer: its evaluation is the C++
+ * API of src/eval, one position per call, statically linked.  This header
+ * is the boundary a replacement plugs in at.  Every entry point names the reference interface it
+ * replaces (file:line, relative to the reference tree).  The C++ mirror of that API
+ * (stormphrax_b200/csrc/host/nnue_state.h: eval::init, NnueState::push/pop/evaluate, ...) is a
+ * thin host-side layer over these calls; INTEGRATION.md shows how an engine build binds to it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary
+ *   - every call returns an SpStatus (0 = ok); nothing throws; the message of the last failure
+ *     on a context is available from sp_nnue_last_error
+ *   - "host" pointers are ordinary process memory (pageable is fine); "device" pointers are CUDA
+ *     device memory on the context's GPU; `stream` is a cudaStream_t passed as void* (NULL = the
+ *     context's own stream)
+ *   - a context is thread-compatible, not thread-safe: like a reference NnueState
+ *     (src/eval/nnue_state.h:85-116) it must be driven by one host thread at a time
+ *   - evaluations are the reference's raw network output: int32, side-to-move relative, before
+ *     contempt / clamping / material scaling (src/eval/nnue_state.cpp:598-610)
+ *   - results are bit-exact with the reference CPU path by contract
+ */
+#ifndef SP_NNUE_H
+#define SP_NNUE_H
+
+#include "sp_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct SpNnue SpNnue; /* opaque; one per GPU; owns the device copy of the network */
+
+typedef enum SpStatus {
+    SP_OK = 0,
+    SP_ERR_INVALID = 1,     /* null pointer, bad size, slot out of range ... */
+    SP_ERR_BAD_NETWORK = 2, /* header validation failed (src/eval/nnue.cpp:85-185) */
+    SP_ERR_CUDA = 3,        /* a CUDA runtime call failed; see sp_nnue_last_error */
+    SP_ERR_NO_DEVICE = 4,   /* no usable CUDA device: there is NO CPU fallback on this path */
+    SP_ERR_BAD_BOARD = 5,   /* a position record is malformed (king count, piece codes, > 32 pieces) */
+    SP_ERR_CAPACITY = 6     /* a per-position feature list exceeded the reference's own bound (256) */
+} SpStatus;
+
+/* ---------------------------------------------------------------- lifecycle
+ * Replaces eval::init / eval::shutdown / eval::getNetwork / eval::isNetworkLoaded
+ * (src/eval/nnue.h:38-45, src/eval/nnue.cpp:200-321).  `net_image` is a LOGICAL (un-permuted)
+ * network file: 64-byte CBNF header (src/eval/header.h:38-52) + raw arrays
+ * (src/eval/nnue/input.h:359-361, src/eval/nnue/arch/multilayer.h:492-496).  The reference
+ * replicates the network per NUMA node (nnue.cpp:266-284); here it is one copy per GPU. */
+int sp_nnue_create(const void* net_image, size_t len, int device, SpNnue** out);
+void sp_nnue_destroy(SpNnue* ctx);
+const char* sp_nnue_last_error(const SpNnue* ctx); /* ctx may be NULL: error of the last failed create */
+int sp_nnue_device(const SpNnue* ctx);
+/* Wait for `stream` (NULL = the context's own) and report what the kernels flagged since the last
+ * check: SP_ERR_BAD_BOARD, SP_ERR_CAPACITY, SP_ERR_INVALID (slot out of range) or SP_OK.  The
+ * host-pointer entry points do this themselves; the *_device ones are asynchronous and do not. */
+int sp_nnue_sync(SpNnue* ctx, void* stream);
+
+/* ---------------------------------------------------------------- full refresh
+ * Replaces NnueState::evaluateOnce / eval::staticEvalOnce for a batch
+ * (src/eval/nnue_state.cpp:612-634, src/eval/eval.cpp:109-112): both accumulators are rebuilt
+ * from scratch for every position.  Side to move and output bucket are taken from the record.
+ * Host variant: copies boards H2D, runs, copies evals D2H, returns when `out` is filled. */
+int sp_nnue_eval_full(SpNnue* ctx, const SpPackedBoard* boards, size_t n, int32_t* out);
+int sp_nnue_eval_full_device(SpNnue* ctx, const SpPackedBoard* d_boards, size_t n, int32_t* d_out, void* stream);
+
+/* ---------------------------------------------------------------- accumulator slots
+ * Replaces the per-thread accumulator stack of NnueState (src/eval/nnue_state.h:68-116): a slot
+ * holds the two perspective accumulators (int16[2][1024], PSQ and threat parts summed -- only
+ * their wrapped sum reaches the network, src/eval/nnue/arch/multilayer.h:118-124) plus the board
+ * they describe.  Slots live in device memory and are addressed by index.
+ *
+ *   sp_nnue_refresh      NnueState::reset (nnue_state.cpp:539-560): rebuild slots from boards
+ *   sp_nnue_update       push + Position::applyMove<BoardObserver> + ensureUpToDate
+ *                        (nnue_state.cpp:562-570, 636-697; delta generation nnue.cpp:490-599,
+ *                        nnue_state.cpp:34-87, 163-307, 356-394): dst = src advanced to `after`.
+ *                        The library derives add/sub feature lists on the GPU from the board stored
+ *                        in src and the `after` record; when a king changes input bucket or board
+ *                        half (psq.h:264-283, nnue_state.h:118-128) that perspective is rebuilt.
+ *                        src == dst (in-place, the datagen applyImmediately form,
+ *                        nnue_state.cpp:572-591) is allowed.
+ *   sp_nnue_eval_slots   NnueState::evaluate (nnue_state.cpp:598-610).  stm[i] = 0 black, 1 white;
+ *                        NULL = side to move of the stored board (explicit stm exists because the
+ *                        engine evaluates null-move children on the parent's accumulators).
+ *   sp_nnue_update_eval  update followed by eval of the dst slots, one H2D and one D2H.
+ * All array arguments of the host variants are host pointers. */
+int sp_nnue_slots_reserve(SpNnue* ctx, size_t n_slots);
+int sp_nnue_refresh(SpNnue* ctx, const uint32_t* slots, const SpPackedBoard* boards, size_t n);
+int sp_nnue_update(
+    SpNnue* ctx, const uint32_t* src_slots, const uint32_t* dst_slots, const SpPackedBoard* after, size_t n);
+int sp_nnue_eval_slots(SpNnue* ctx, const uint32_t* slots, const uint8_t* stm, size_t n, int32_t* out);
+int sp_nnue_update_eval(
+    SpNnue* ctx,
+    const uint32_t* src_slots,
+    const uint32_t* dst_slots,
+    const SpPackedBoard* after,
+    size_t n,
+    int32_t* out);
+/* device-pointer variants (all arrays in device memory, asynchronous on `stream`) */
+int sp_nnue_refresh_device(SpNnue* ctx, const uint32_t* d_slots, const SpPackedBoard* d_boards, size_t n, void* stream);
+int sp_nnue_update_eval_device(
+    SpNnue* ctx,
+    const uint32_t* d_src_slots,
+    const uint32_t* d_dst_slots,
+    const SpPackedBoard* d_after,
+    size_t n,
+    int32_t* d_out, /* NULL = update only */
+    void* stream);
+
+/* ---------------------------------------------------------------- playout streams
+ * The incremental workload of BASELINE.json config 3 and of src/datagen/datagen.cpp:206-262: game g
+ * starts from starts[g] and plays moves[game_start[g] - g ... ) (one move fewer than positions);
+ * out[game_start[g] + i] receives the evaluation after i moves (i = 0 is the start position), for
+ * the side to move there.  Accumulators never leave the SM between plies of one game. */
+int sp_nnue_eval_playouts(
+    SpNnue* ctx,
+    const SpPackedBoard* boards, /* host; every position of every game, as sp_host_playouts writes them */
+    const uint32_t* game_start,  /* host; n_games + 1 offsets into boards/out */
+    uint32_t n_games,
+    int32_t* out);
+int sp_nnue_eval_playouts_device(
+    SpNnue* ctx, const SpPackedBoard* d_boards, const uint32_t* d_game_start, uint32_t n_games, size_t n_boards,
+    int32_t* d_out, void* stream);
+
+/* ---------------------------------------------------------------- dense head in isolation
+ * BASELINE.json config 4: L1 (int8 IMMA) -> L2 -> L3 from already-activated FT outputs.
+ * Replaces PairwiseMultilayerCReLUSCReLUCReLU::propagateL1/L2/L3
+ * (src/eval/nnue/arch/multilayer.h:154-490).  d_act is uint8[n][1024] (stm half first),
+ * d_bucket uint8[n]. */
+int sp_nnue_forward_device(
+    SpNnue* ctx, const uint8_t* d_act, const uint8_t* d_bucket, size_t n, int32_t* d_out, void* stream);
+/* FT only: boards -> activations + buckets (for tests and for feeding sp_nnue_forward_device) */
+int sp_nnue_activations_device(
+    SpNnue* ctx, const SpPackedBoard* d_boards, size_t n, uint8_t* d_act, uint8_t* d_bucket, void* stream);
+
+/* ---------------------------------------------------------------- introspection
+ * Counters since create (uint64 each): what the engine keeps per thread in SearchData
+ * (src/thread.h:35-79) and sums at report time.  Multi-GPU runs all-reduce these over NCCL. */
+enum {
+    SP_CTR_EVALS = 0,        /* positions evaluated */
+    SP_CTR_FULL_REFRESH = 1, /* perspective accumulators rebuilt from scratch */
+    SP_CTR_INCREMENTAL = 2,  /* perspective accumulators updated incrementally */
+    SP_CTR_LAUNCHES = 3,     /* kernels launched by this context */
+    SP_NUM_COUNTERS = 8
+};
+int sp_nnue_counters(SpNnue* ctx, uint64_t out[SP_NUM_COUNTERS]);
+/* Debug/test access: accumulators of a slot in LOGICAL order, int16[2][1024] (black, white). */
+int sp_nnue_read_slot(SpNnue* ctx, uint32_t slot, int16_t* out_acc, SpPackedBoard* out_board);
+
+/* ---------------------------------------------------------------- host utilities (no GPU)
+ * Workload generation and CPU execution of the shared feature code, for tests and benchmarks. */
+/* Random legal playouts from the standard start position: game g is seeded from (seed, g); all
+ * positions including the start are written; moves[i] is the move played from boards[i] (0 at
+ * the last position of a game); game_start has n_games + 1 entries.  boards/moves must hold
+ * n_games * (max_plies + 1) records.  Returns the number of positions written. */
+size_t sp_host_playouts(
+    uint64_t seed,
+    uint32_t n_games,
+    uint32_t max_plies,
+    int threads,
+    SpPackedBoard* boards,
+    SpMove* moves,
+    uint32_t* game_start);
+int sp_host_board_from_fen(const char* fen, SpPackedBoard* out);
+int sp_host_board_to_fen(const SpPackedBoard* board, char* out, size_t cap);
+int sp_host_legal_moves(const SpPackedBoard* board, SpMove* out /* [256] */);
+int sp_host_apply_move(const SpPackedBoard* board, SpMove move, SpPackedBoard* out);
+int sp_host_features(const SpPackedBoard* board, int perspective, int kind, uint32_t* out /* [512] */);
+int sp_host_feature_delta(
+    const SpPackedBoard* before,
+    const SpPackedBoard* after,
+    int perspective,
+    uint32_t* psq_add, int* n_psq_add,
+    uint32_t* psq_sub, int* n_psq_sub,
+    uint32_t* thr_add, int* n_thr_add,
+    uint32_t* thr_sub, int* n_thr_sub);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SP_NNUE_H */

@@ -194,3 +194,94 @@ def build_c_oracle() -> str:
     """Compile oracle/nnue_oracle.c (gcc only) and return the path of the shared library."""
     subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
     return os.path.join(HERE, "_build", "libsp_oracle.so")
+
+
+class COracle:
+    """The plain-C restatement (oracle/nnue_oracle.c)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(build_c_oracle())
+        L = self.lib
+        L.spo_load_net.argtypes = [_vp, C.c_size_t]
+        L.spo_eval_once.argtypes = [_vp, C.c_size_t, _vp]
+        L.spo_time_eval_once.argtypes = [_vp, C.c_size_t, C.c_int, C.c_int, _vp]
+        L.spo_time_eval_once.restype = C.c_double
+        L.spo_psq_features.argtypes = [_vp, C.c_int, _vp]
+        L.spo_threat_features.argtypes = [_vp, C.c_int, _vp]
+        L.spo_threat_index.argtypes = [C.c_int] * 6
+        L.spo_threat_index.restype = C.c_int32
+        L.spo_accumulators.argtypes = [_vp, _vp, _vp]
+        L.spo_ft_activations.argtypes = [_vp, _vp, _vp]
+        L.spo_forward.argtypes = [_vp, C.c_int]
+        L.spo_forward.restype = C.c_int32
+        L.spo_forward_acc.argtypes = [_vp, _vp, C.c_int, C.c_int]
+        L.spo_forward_acc.restype = C.c_int32
+
+    def load_net(self, image: np.ndarray) -> None:
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        rc = self.lib.spo_load_net(_ptr(image), image.size)
+        if rc:
+            raise RuntimeError(f"spo_load_net failed ({rc})")
+
+    def eval_once(self, boards: np.ndarray) -> np.ndarray:
+        boards = np.ascontiguousarray(boards, dtype=BOARD_DTYPE)
+        out = np.empty(boards.size, dtype=np.int32)
+        rc = self.lib.spo_eval_once(_ptr(boards), boards.size, _ptr(out))
+        if rc:
+            raise RuntimeError(f"spo_eval_once failed ({rc})")
+        return out
+
+    def time_eval_once(self, boards: np.ndarray, threads: int, reps: int = 1):
+        boards = np.ascontiguousarray(boards, dtype=BOARD_DTYPE)
+        out = np.empty(boards.size, dtype=np.int32)
+        secs = self.lib.spo_time_eval_once(_ptr(boards), boards.size, threads, reps, _ptr(out))
+        if secs < 0:
+            raise RuntimeError(f"spo_time_eval_once failed ({secs})")
+        return secs, out
+
+    def psq_features(self, board: np.ndarray, c: int) -> np.ndarray:
+        board = np.ascontiguousarray(board, dtype=BOARD_DTYPE).reshape(1)
+        out = np.empty(32, dtype=np.uint32)
+        n = self.lib.spo_psq_features(_ptr(board), c, _ptr(out))
+        if n < 0:
+            raise RuntimeError("spo_psq_features failed")
+        return out[:n].copy()
+
+    def threat_features(self, board: np.ndarray, c: int) -> np.ndarray:
+        board = np.ascontiguousarray(board, dtype=BOARD_DTYPE).reshape(1)
+        out = np.empty(512, dtype=np.uint32)
+        n = self.lib.spo_threat_features(_ptr(board), c, _ptr(out))
+        if n < 0:
+            raise RuntimeError("spo_threat_features failed")
+        return out[:n].copy()
+
+    def threat_index(self, c, king_sq, attacker, attacker_sq, attacked, attacked_sq) -> int:
+        return self.lib.spo_threat_index(c, king_sq, attacker, attacker_sq, attacked, attacked_sq)
+
+    def accumulators(self, board: np.ndarray):
+        board = np.ascontiguousarray(board, dtype=BOARD_DTYPE).reshape(1)
+        psq = np.empty((2, 1024), dtype=np.int16)
+        thr = np.empty((2, 1024), dtype=np.int16)
+        rc = self.lib.spo_accumulators(_ptr(board), _ptr(psq), _ptr(thr))
+        if rc:
+            raise RuntimeError("spo_accumulators failed")
+        return psq, thr
+
+    def ft_activations(self, board: np.ndarray):
+        board = np.ascontiguousarray(board, dtype=BOARD_DTYPE).reshape(1)
+        out = np.empty(1024, dtype=np.uint8)
+        bucket = C.c_int(0)
+        rc = self.lib.spo_ft_activations(_ptr(board), _ptr(out), C.byref(bucket))
+        if rc:
+            raise RuntimeError("spo_ft_activations failed")
+        return out, bucket.value
+
+    def forward(self, ft: np.ndarray, bucket: int) -> int:
+        ft = np.ascontiguousarray(ft, dtype=np.uint8)
+        assert ft.size == 1024
+        return self.lib.spo_forward(_ptr(ft), int(bucket))
+
+    def forward_acc(self, psq: np.ndarray, thr: np.ndarray, stm: int, bucket: int) -> int:
+        psq = np.ascontiguousarray(psq, dtype=np.int16)
+        thr = np.ascontiguousarray(thr, dtype=np.int16)
+        return self.lib.spo_forward_acc(_ptr(psq), _ptr(thr), int(stm), int(bucket))

@@ -1,0 +1,301 @@
+"""ctypes binding of libsp_nnue.so (include/sp_nnue.h) -- the product's Python face.
+
+Everything here calls the C-ABI; there is no Python or CPU implementation of the evaluation
+behind it.  If the shared library is missing, or no CUDA device is present, calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+BOARD_DTYPE = np.dtype(
+    [
+        ("occupancy", "<u8"),
+        ("pieces", "u1", (16,)),
+        ("stm_ep", "u1"),
+        ("halfmove", "u1"),
+        ("fullmove", "<u2"),
+        ("eval", "<i2"),
+        ("wdl", "u1"),
+        ("extra", "u1"),
+    ]
+)
+assert BOARD_DTYPE.itemsize == 32
+
+SP_OK, SP_ERR_INVALID, SP_ERR_BAD_NETWORK, SP_ERR_CUDA, SP_ERR_NO_DEVICE, SP_ERR_BAD_BOARD, SP_ERR_CAPACITY = range(7)
+STATUS_NAMES = ["SP_OK", "SP_ERR_INVALID", "SP_ERR_BAD_NETWORK", "SP_ERR_CUDA", "SP_ERR_NO_DEVICE", "SP_ERR_BAD_BOARD", "SP_ERR_CAPACITY"]
+NUM_COUNTERS = 8
+CTR_EVALS, CTR_FULL_REFRESH, CTR_INCREMENTAL, CTR_LAUNCHES = 0, 1, 2, 3
+
+_vp = C.c_void_p
+_sz = C.c_size_t
+
+# name -> (restype, argtypes): every symbol include/sp_nnue.h declares
+SIGNATURES = {
+    "sp_nnue_create": (C.c_int, [_vp, _sz, C.c_int, C.POINTER(_vp)]),
+    "sp_nnue_destroy": (None, [_vp]),
+    "sp_nnue_last_error": (C.c_char_p, [_vp]),
+    "sp_nnue_device": (C.c_int, [_vp]),
+    "sp_nnue_sync": (C.c_int, [_vp, _vp]),
+    "sp_nnue_eval_full": (C.c_int, [_vp, _vp, _sz, _vp]),
+    "sp_nnue_eval_full_device": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
+    "sp_nnue_slots_reserve": (C.c_int, [_vp, _sz]),
+    "sp_nnue_refresh": (C.c_int, [_vp, _vp, _vp, _sz]),
+    "sp_nnue_update": (C.c_int, [_vp, _vp, _vp, _vp, _sz]),
+    "sp_nnue_eval_slots": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "sp_nnue_update_eval": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "sp_nnue_refresh_device": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "sp_nnue_update_eval_device": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "sp_nnue_eval_playouts": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp]),
+    "sp_nnue_eval_playouts_device": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _sz, _vp, _vp]),
+    "sp_nnue_forward_device": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
+    "sp_nnue_activations_device": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "sp_nnue_counters": (C.c_int, [_vp, _vp]),
+    "sp_nnue_read_slot": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
+    "sp_host_playouts": (_sz, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp]),
+    "sp_host_board_from_fen": (C.c_int, [C.c_char_p, _vp]),
+    "sp_host_board_to_fen": (C.c_int, [_vp, C.c_char_p, _sz]),
+    "sp_host_legal_moves": (C.c_int, [_vp, _vp]),
+    "sp_host_apply_move": (C.c_int, [_vp, C.c_uint16, _vp]),
+    "sp_host_features": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "sp_host_feature_delta": (C.c_int, [_vp, _vp, C.c_int] + [_vp] * 8),
+}
+
+_lib = None
+
+
+class NnueError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS_NAMES[status] if 0 <= status < len(STATUS_NAMES) else status}: {message}")
+        self.status = status
+
+
+def lib() -> C.CDLL:
+    """Load (building first if the sources are newer) libsp_nnue.so and bind every export."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB_PATH
+        if os.path.exists(os.path.join(_build.CSRC, "kernels.cu")) and _build.shutil.which("nvcc"):
+            path = _build.build()
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing and cannot be built here: run `python -m stormphrax_b200.build`")
+        handle = C.CDLL(path)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError = the library does not export what the header declares
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def _ptr(a) -> int | None:
+    """Host numpy array, torch tensor (host or device) or raw int -> address."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return int(a)
+
+
+def _boards(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=BOARD_DTYPE)
+
+
+class Nnue:
+    """One evaluator context = one GPU holding one copy of the network (eval::init .. shutdown)."""
+
+    def __init__(self, net_image, device: int = 0):
+        self._lib = lib()
+        image = np.ascontiguousarray(np.frombuffer(net_image, dtype=np.uint8) if isinstance(net_image, (bytes, bytearray)) else net_image, dtype=np.uint8)
+        handle = _vp()
+        rc = self._lib.sp_nnue_create(image.ctypes.data, image.size, device, C.byref(handle))
+        if rc:
+            raise NnueError(rc, self._lib.sp_nnue_last_error(None).decode())
+        self._h = handle
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.sp_nnue_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc:
+            raise NnueError(rc, self._lib.sp_nnue_last_error(self._h).decode())
+
+    @property
+    def device(self) -> int:
+        return self._lib.sp_nnue_device(self._h)
+
+    def sync(self, stream: int | None = None) -> None:
+        self._check(self._lib.sp_nnue_sync(self._h, stream))
+
+    def counters(self) -> np.ndarray:
+        out = np.zeros(NUM_COUNTERS, dtype=np.uint64)
+        self._check(self._lib.sp_nnue_counters(self._h, out.ctypes.data))
+        return out
+
+    # ---- full refresh (NnueState::evaluateOnce for a batch)
+    def eval_full(self, boards, out: np.ndarray | None = None) -> np.ndarray:
+        boards = _boards(boards)
+        if out is None:
+            out = np.empty(boards.size, dtype=np.int32)
+        self._check(self._lib.sp_nnue_eval_full(self._h, boards.ctypes.data, boards.size, out.ctypes.data))
+        return out
+
+    def eval_full_device(self, d_boards, n: int, d_out, stream: int | None = None) -> None:
+        self._check(self._lib.sp_nnue_eval_full_device(self._h, _ptr(d_boards), n, _ptr(d_out), stream))
+
+    def activations_device(self, d_boards, n: int, d_act, d_bucket, stream: int | None = None) -> None:
+        self._check(self._lib.sp_nnue_activations_device(self._h, _ptr(d_boards), n, _ptr(d_act), _ptr(d_bucket), stream))
+
+    def forward_device(self, d_act, d_bucket, n: int, d_out, stream: int | None = None) -> None:
+        self._check(self._lib.sp_nnue_forward_device(self._h, _ptr(d_act), _ptr(d_bucket), n, _ptr(d_out), stream))
+
+    # ---- accumulator slots (the NnueState stack, device resident)
+    def slots_reserve(self, n_slots: int) -> None:
+        self._check(self._lib.sp_nnue_slots_reserve(self._h, n_slots))
+
+    def refresh(self, slots, boards) -> None:
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        boards = _boards(boards)
+        assert slots.size == boards.size
+        self._check(self._lib.sp_nnue_refresh(self._h, slots.ctypes.data, boards.ctypes.data, slots.size))
+
+    def update(self, src_slots, dst_slots, after) -> None:
+        src = np.ascontiguousarray(src_slots, dtype=np.uint32)
+        dst = np.ascontiguousarray(dst_slots, dtype=np.uint32)
+        after = _boards(after)
+        assert src.size == dst.size == after.size
+        self._check(self._lib.sp_nnue_update(self._h, src.ctypes.data, dst.ctypes.data, after.ctypes.data, src.size))
+
+    def eval_slots(self, slots, stm=None) -> np.ndarray:
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        stm_arr = None if stm is None else np.ascontiguousarray(stm, dtype=np.uint8)
+        out = np.empty(slots.size, dtype=np.int32)
+        self._check(self._lib.sp_nnue_eval_slots(self._h, slots.ctypes.data, _ptr(stm_arr), slots.size, out.ctypes.data))
+        return out
+
+    def update_eval(self, src_slots, dst_slots, after) -> np.ndarray:
+        src = np.ascontiguousarray(src_slots, dtype=np.uint32)
+        dst = np.ascontiguousarray(dst_slots, dtype=np.uint32)
+        after = _boards(after)
+        assert src.size == dst.size == after.size
+        out = np.empty(src.size, dtype=np.int32)
+        self._check(self._lib.sp_nnue_update_eval(self._h, src.ctypes.data, dst.ctypes.data, after.ctypes.data, src.size, out.ctypes.data))
+        return out
+
+    def refresh_device(self, d_slots, d_boards, n: int, stream: int | None = None) -> None:
+        self._check(self._lib.sp_nnue_refresh_device(self._h, _ptr(d_slots), _ptr(d_boards), n, stream))
+
+    def update_eval_device(self, d_src, d_dst, d_after, n: int, d_out, stream: int | None = None) -> None:
+        self._check(self._lib.sp_nnue_update_eval_device(self._h, _ptr(d_src), _ptr(d_dst), _ptr(d_after), n, _ptr(d_out), stream))
+
+    def read_slot(self, slot: int):
+        acc = np.empty((2, 1024), dtype=np.int16)
+        board = np.zeros(1, dtype=BOARD_DTYPE)
+        self._check(self._lib.sp_nnue_read_slot(self._h, slot, acc.ctypes.data, board.ctypes.data))
+        return acc, board
+
+    # ---- playout streams (datagen form: one accumulator chain per game)
+    def eval_playouts(self, boards, game_start) -> np.ndarray:
+        boards = _boards(boards)
+        game_start = np.ascontiguousarray(game_start, dtype=np.uint32)
+        assert game_start[-1] == boards.size
+        out = np.empty(boards.size, dtype=np.int32)
+        self._check(self._lib.sp_nnue_eval_playouts(self._h, boards.ctypes.data, game_start.ctypes.data, game_start.size - 1, out.ctypes.data))
+        return out
+
+    def eval_playouts_device(self, d_boards, d_game_start, n_games: int, n_boards: int, d_out, stream: int | None = None) -> None:
+        self._check(self._lib.sp_nnue_eval_playouts_device(self._h, _ptr(d_boards), _ptr(d_game_start), n_games, n_boards, _ptr(d_out), stream))
+
+
+# ------------------------------------------------------------------ host utilities (no GPU)
+
+def playouts(seed: int, n_games: int, max_plies: int, threads: int = 0):
+    """Random legal playouts from the start position: (boards, moves, game_start)."""
+    L = lib()
+    threads = threads or min(os.cpu_count() or 1, 32)
+    cap = n_games * (max_plies + 1)
+    boards = np.zeros(cap, dtype=BOARD_DTYPE)
+    moves = np.zeros(cap, dtype=np.uint16)
+    starts = np.zeros(n_games + 1, dtype=np.uint32)
+    n = L.sp_host_playouts(seed, n_games, max_plies, threads, boards.ctypes.data, moves.ctypes.data, starts.ctypes.data)
+    return boards[:n].copy(), moves[:n].copy(), starts
+
+
+def board_from_fen(fen: str) -> np.ndarray:
+    out = np.zeros(1, dtype=BOARD_DTYPE)
+    rc = lib().sp_host_board_from_fen(fen.encode(), out.ctypes.data)
+    if rc:
+        raise NnueError(rc, f"bad fen: {fen}")
+    return out
+
+
+def board_to_fen(board) -> str:
+    board = _boards(board).reshape(1)
+    buf = C.create_string_buffer(128)
+    rc = lib().sp_host_board_to_fen(board.ctypes.data, buf, 128)
+    if rc:
+        raise NnueError(rc, "bad board")
+    return buf.value.decode()
+
+
+def legal_moves(board) -> np.ndarray:
+    board = _boards(board).reshape(1)
+    out = np.zeros(256, dtype=np.uint16)
+    n = lib().sp_host_legal_moves(board.ctypes.data, out.ctypes.data)
+    if n < 0:
+        raise NnueError(SP_ERR_BAD_BOARD, "bad board")
+    return out[:n].copy()
+
+
+def apply_move(board, move: int) -> np.ndarray:
+    board = _boards(board).reshape(1)
+    out = np.zeros(1, dtype=BOARD_DTYPE)
+    rc = lib().sp_host_apply_move(board.ctypes.data, int(move), out.ctypes.data)
+    if rc:
+        raise NnueError(rc, "bad board")
+    return out
+
+
+def features(board, perspective: int, kind: int) -> np.ndarray:
+    """Feature indices from the shared host/device indexing code. kind 0 = PSQ, 1 = threat + pawn pair."""
+    board = _boards(board).reshape(1)
+    out = np.zeros(512, dtype=np.uint32)
+    n = lib().sp_host_features(board.ctypes.data, perspective, kind, out.ctypes.data)
+    if n < 0:
+        raise NnueError(SP_ERR_BAD_BOARD, "bad board")
+    return out[:n].copy()
+
+
+def feature_delta(before, after, perspective: int):
+    """(needs_refresh, psq_add, psq_sub, thr_add, thr_sub) from the shared delta generator."""
+    before = _boards(before).reshape(1)
+    after = _boards(after).reshape(1)
+    bufs = [np.zeros(512, dtype=np.uint32) for _ in range(4)]
+    counts = [C.c_int(0) for _ in range(4)]
+    args = []
+    for b, c in zip(bufs, counts):
+        args += [b.ctypes.data, C.cast(C.byref(c), _vp)]
+    rc = lib().sp_host_feature_delta(before.ctypes.data, after.ctypes.data, perspective, *args)
+    if rc < 0:
+        raise NnueError(SP_ERR_BAD_BOARD, "bad board")
+    return (rc == 1, *[b[: c.value].copy() for b, c in zip(bufs, counts)])

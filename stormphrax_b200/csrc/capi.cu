@@ -1,0 +1,350 @@
+/*
+ * capi.cu -- the extern "C" boundary of libsp_nnue.so (include/sp_nnue.h): network upload,
+ * device buffer management, batching, error reporting.  No evaluation arithmetic lives here
+ * and there is NO CPU fallback: without a CUDA device every entry point fails.
+ */
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sp_nnue.h"
+#include "kernels.cuh"
+
+using namespace sp;
+using namespace sp::gpu;
+
+struct SpNnue {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    DeviceNet net{};
+    uint8_t* d_net_blob = nullptr;
+    FeatureTables* d_tables = nullptr;
+    DeviceStatus* d_status = nullptr;
+    DeviceStatus* h_status = nullptr; /* pinned */
+
+    /* scratch for one chunk of positions */
+    size_t chunk = 32768;
+    uint8_t* d_act = nullptr;
+    uint8_t* d_bucket = nullptr;
+    /* staging for the host-pointer entry points */
+    SpPackedBoard* d_boards = nullptr;
+    int32_t* d_out = nullptr;
+    uint32_t* d_ids = nullptr; /* [3][cap]: src slots, dst slots, game starts */
+    uint8_t* d_stm = nullptr;
+    size_t cap = 0;
+
+    SlotStore slots{};
+    uint64_t counters[SP_NUM_COUNTERS] = {};
+    std::string error;
+};
+
+namespace {
+
+std::string g_create_error;
+
+int fail(SpNnue* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    (ctx ? ctx->error : g_create_error) = buf;
+    return code;
+}
+
+#define SP_CUDA(ctx, call)                                                                              \
+    do {                                                                                                \
+        const cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return fail(ctx, SP_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+/* Header checks in the order of `validate`, src/eval/nnue.cpp:85-185 (header layout header.h:38-52). */
+const char* validate_header(const uint8_t* h) {
+    static thread_local char msg[160];
+    if (std::memcmp(h, "CBNF", 4) != 0) return "invalid magic bytes in network header";
+    const unsigned version = h[4] | h[5] << 8, flags = h[6] | h[7] << 8;
+    const unsigned arch = h[9], activation = h[10], hidden = h[11] | h[12] << 8, in_b = h[13], out_b = h[14];
+    auto fmt = [&](const char* f, unsigned a, unsigned b) { snprintf(msg, sizeof(msg), f, a, b); return msg; };
+    if (version != 1) return fmt("unsupported network format version %u (expected: %u)", version, 1);
+    if (arch != 5) return fmt("wrong network architecture %u (expected: %u)", arch, 5);
+    if (!(flags & 0x0002)) return "unmirrored network, expected horizontally mirrored";
+    if (!(flags & 0x0004)) return "network does not have merged king planes, expected merged";
+    if (!(flags & 0x0008)) return "network L1 does not require pairwise multiplication, expected paired";
+    if (activation != 0) return fmt("wrong l1 activation function %u (expected: %u = crelu)", activation, 0);
+    if (hidden != SP_L1_SIZE) return fmt("wrong number of l1 neurons %u (expected: %u)", hidden, SP_L1_SIZE);
+    if (!(in_b & 0x80)) return "network does not have the expected threat inputs";
+    if ((in_b & 0x7F) != SP_INPUT_BUCKETS) return fmt("wrong number of input buckets %u (expected: %u)", in_b & 0x7F, SP_INPUT_BUCKETS);
+    if (out_b != SP_OUTPUT_BUCKETS) return fmt("wrong number of output buckets %u (expected: %u)", out_b, SP_OUTPUT_BUCKETS);
+    if (flags & 0x0001) return "zstd-compressed network: decompress before upload";
+    return nullptr;
+}
+
+constexpr size_t align256(size_t x) { return (x + 255) & ~size_t{255}; }
+
+/* Device layout of the network. Offsets into one allocation. */
+struct NetLayout {
+    size_t psq, thr, l1_w, l1_b, l2_w, l2_b, l3_w, l3_b, total;
+    NetLayout() {
+        size_t o = 0;
+        psq = o;  o = align256(o + size_t{kPsqRows} * SP_L1_SIZE * 2);
+        thr = o;  o = align256(o + size_t{kThrRows} * SP_L1_SIZE);
+        l1_w = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * SP_L1_SIZE * SP_L2_SIZE);
+        l1_b = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * SP_L2_SIZE * 4);
+        l2_w = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * 2 * SP_L2_SIZE * SP_L3_SIZE * 4);
+        l2_b = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * SP_L3_SIZE * 4);
+        l3_w = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * SP_L3_SIZE * 4);
+        l3_b = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * 4);
+        total = o;
+    }
+};
+
+/* logical file image -> device image (host side) */
+void build_device_image(const uint8_t* payload, const NetLayout& L, uint8_t* img) {
+    const int16_t* psq_w = reinterpret_cast<const int16_t*>(payload);
+    const uint8_t* thr_w = payload + size_t{SP_PSQ_FEATURES} * SP_L1_SIZE * 2;
+    const uint8_t* rest = thr_w + size_t{SP_THREAT_FEATURES} * SP_L1_SIZE;
+    const int16_t* ft_b = reinterpret_cast<const int16_t*>(rest);
+    rest += SP_L1_SIZE * 2;
+
+    int16_t* psq = reinterpret_cast<int16_t*>(img + L.psq);
+    auto permute_row = [&](const int16_t* src, int16_t* dst) {
+        for (int k = 0; k < 4; ++k)
+            for (int lane = 0; lane < 32; ++lane)
+                std::memcpy(dst + (k * 32 + lane) * 8, src + lane_order_element(k, lane, 0), 16);
+    };
+    for (int r = 0; r < SP_PSQ_FEATURES; ++r) permute_row(psq_w + size_t(r) * SP_L1_SIZE, psq + size_t(r) * SP_L1_SIZE);
+    permute_row(ft_b, psq + size_t{kPsqBiasRow} * SP_L1_SIZE);
+    std::memset(psq + size_t{kPsqZeroRow} * SP_L1_SIZE, 0, SP_L1_SIZE * 2);
+
+    uint8_t* thr = img + L.thr;
+    const size_t thr_bytes = size_t{SP_THREAT_FEATURES} * SP_L1_SIZE;
+    for (size_t i = 0; i < thr_bytes; ++i) thr[i] = static_cast<uint8_t>(thr_w[i] ^ 0x80); /* int8 + 128 */
+    std::memset(thr + thr_bytes, 0x80, SP_L1_SIZE);
+
+    auto take = [&](size_t off, size_t bytes) {
+        std::memcpy(img + off, rest, bytes);
+        rest += bytes;
+    };
+    take(L.l1_w, size_t{SP_OUTPUT_BUCKETS} * SP_L1_SIZE * SP_L2_SIZE);
+    take(L.l1_b, size_t{SP_OUTPUT_BUCKETS} * SP_L2_SIZE * 4);
+    take(L.l2_w, size_t{SP_OUTPUT_BUCKETS} * 2 * SP_L2_SIZE * SP_L3_SIZE * 4);
+    take(L.l2_b, size_t{SP_OUTPUT_BUCKETS} * SP_L3_SIZE * 4);
+    take(L.l3_w, size_t{SP_OUTPUT_BUCKETS} * SP_L3_SIZE * 4);
+    take(L.l3_b, size_t{SP_OUTPUT_BUCKETS} * 4);
+}
+
+int ensure_staging(SpNnue* ctx, size_t n) {
+    if (n <= ctx->cap) return SP_OK;
+    const size_t cap = std::max(n, ctx->cap * 2);
+    cudaFree(ctx->d_boards);
+    cudaFree(ctx->d_out);
+    cudaFree(ctx->d_ids);
+    cudaFree(ctx->d_stm);
+    ctx->d_boards = nullptr, ctx->d_out = nullptr, ctx->d_ids = nullptr, ctx->d_stm = nullptr;
+    ctx->cap = 0;
+    SP_CUDA(ctx, cudaMalloc(&ctx->d_boards, cap * sizeof(SpPackedBoard)));
+    SP_CUDA(ctx, cudaMalloc(&ctx->d_out, cap * sizeof(int32_t)));
+    SP_CUDA(ctx, cudaMalloc(&ctx->d_ids, 3 * (cap + 1) * sizeof(uint32_t)));
+    SP_CUDA(ctx, cudaMalloc(&ctx->d_stm, cap));
+    ctx->cap = cap;
+    return SP_OK;
+}
+
+/* Wait for `stream`, then translate the device status word. */
+int finish(SpNnue* ctx, cudaStream_t stream) {
+    SP_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    SP_CUDA(ctx, cudaStreamSynchronize(stream));
+    const int err = ctx->h_status->error;
+    if (!err) return SP_OK;
+    SP_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(int), stream));
+    if (err & kErrBadSlot) return fail(ctx, SP_ERR_INVALID, "slot index out of range");
+    if (err & kErrBadBoard) return fail(ctx, SP_ERR_BAD_BOARD, "malformed position record (affected outputs are INT32_MIN)");
+    return fail(ctx, SP_ERR_CAPACITY, "threat feature list exceeded %d entries", SP_MAX_THREAT_INDICES);
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+cudaStream_t pick(SpNnue* ctx, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : ctx->stream; }
+
+/* boards (device) -> out (device), in chunks that keep the activation scratch L2-sized */
+int eval_full_device(SpNnue* ctx, const SpPackedBoard* d_boards, size_t n, int32_t* d_out, cudaStream_t stream) {
+    for (size_t off = 0; off < n; off += ctx->chunk) {
+        const size_t m = std::min(ctx->chunk, n - off);
+        launch_ft_full(ctx->net, d_boards + off, m, ctx->d_act, ctx->d_bucket, ctx->d_status, ctx->sm_count, stream);
+        launch_head(ctx->net, ctx->d_act, ctx->d_bucket, m, d_out + off, ctx->d_status, ctx->sm_count, stream);
+        ctx->counters[SP_CTR_LAUNCHES] += 2;
+    }
+    ctx->counters[SP_CTR_EVALS] += n;
+    ctx->counters[SP_CTR_FULL_REFRESH] += 2 * n;
+    SP_CUDA(ctx, cudaGetLastError());
+    return SP_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sp_nnue_create(const void* net_image, size_t len, int device, SpNnue** out) {
+    if (!out) return fail(nullptr, SP_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!net_image || len < SP_NET_HEADER_BYTES) return fail(nullptr, SP_ERR_BAD_NETWORK, "missing network header");
+    const uint8_t* bytes = static_cast<const uint8_t*>(net_image);
+    if (const char* why = validate_header(bytes)) return fail(nullptr, SP_ERR_BAD_NETWORK, "%s", why);
+    if (len < size_t{SP_NET_HEADER_BYTES} + SP_NET_PAYLOAD_BYTES)
+        return fail(nullptr, SP_ERR_BAD_NETWORK, "network too small? %zu < %zu", len - SP_NET_HEADER_BYTES, size_t{SP_NET_PAYLOAD_BYTES});
+
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, SP_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, SP_ERR_NO_DEVICE, "device %d out of range (%d present)", device, count);
+
+    std::unique_ptr<SpNnue> ctx{new (std::nothrow) SpNnue};
+    if (!ctx) return fail(nullptr, SP_ERR_INVALID, "out of host memory");
+    ctx->device = device;
+    DeviceGuard guard{device};
+    cudaDeviceProp prop{};
+    SP_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(nullptr, SP_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (const char* env = std::getenv("SP_NNUE_CHUNK")) {
+        const long v = std::atol(env);
+        if (v >= 16) ctx->chunk = static_cast<size_t>(v);
+    }
+    SP_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+
+    const NetLayout L;
+    std::vector<uint8_t> img(L.total);
+    build_device_image(bytes + SP_NET_HEADER_BYTES, L, img.data());
+    SP_CUDA(nullptr, cudaMalloc(&ctx->d_net_blob, L.total));
+    SP_CUDA(nullptr, cudaMemcpy(ctx->d_net_blob, img.data(), L.total, cudaMemcpyHostToDevice));
+    FeatureTables tables;
+    build_feature_tables(tables);
+    SP_CUDA(nullptr, cudaMalloc(&ctx->d_tables, sizeof(FeatureTables)));
+    SP_CUDA(nullptr, cudaMemcpy(ctx->d_tables, &tables, sizeof(FeatureTables), cudaMemcpyHostToDevice));
+    SP_CUDA(nullptr, cudaMalloc(&ctx->d_status, sizeof(DeviceStatus)));
+    SP_CUDA(nullptr, cudaMemset(ctx->d_status, 0, sizeof(DeviceStatus)));
+    SP_CUDA(nullptr, cudaMallocHost(&ctx->h_status, sizeof(DeviceStatus)));
+    SP_CUDA(nullptr, cudaMalloc(&ctx->d_act, ctx->chunk * SP_L1_SIZE));
+    SP_CUDA(nullptr, cudaMalloc(&ctx->d_bucket, ctx->chunk));
+
+    uint8_t* b = ctx->d_net_blob;
+    ctx->net.psq = reinterpret_cast<const uint4*>(b + L.psq);
+    ctx->net.thr = reinterpret_cast<const uint4*>(b + L.thr);
+    ctx->net.l1_w = reinterpret_cast<const int8_t*>(b + L.l1_w);
+    ctx->net.l1_b = reinterpret_cast<const int32_t*>(b + L.l1_b);
+    ctx->net.l2_w = reinterpret_cast<const int32_t*>(b + L.l2_w);
+    ctx->net.l2_b = reinterpret_cast<const int32_t*>(b + L.l2_b);
+    ctx->net.l3_w = reinterpret_cast<const int32_t*>(b + L.l3_w);
+    ctx->net.l3_b = reinterpret_cast<const int32_t*>(b + L.l3_b);
+    ctx->net.tables = ctx->d_tables;
+    *out = ctx.release();
+    return SP_OK;
+}
+
+void sp_nnue_destroy(SpNnue* ctx) {
+    if (!ctx) return;
+    DeviceGuard guard{ctx->device};
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_net_blob);
+    cudaFree(ctx->d_tables);
+    cudaFree(ctx->d_status);
+    cudaFreeHost(ctx->h_status);
+    cudaFree(ctx->d_act);
+    cudaFree(ctx->d_bucket);
+    cudaFree(ctx->d_boards);
+    cudaFree(ctx->d_out);
+    cudaFree(ctx->d_ids);
+    cudaFree(ctx->d_stm);
+    cudaFree(ctx->slots.acc);
+    cudaFree(ctx->slots.boards);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* sp_nnue_last_error(const SpNnue* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int sp_nnue_device(const SpNnue* ctx) { return ctx ? ctx->device : -1; }
+
+int sp_nnue_sync(SpNnue* ctx, void* stream) {
+    if (!ctx) return SP_ERR_INVALID;
+    DeviceGuard guard{ctx->device};
+    return finish(ctx, pick(ctx, stream));
+}
+
+int sp_nnue_eval_full(SpNnue* ctx, const SpPackedBoard* boards, size_t n, int32_t* out) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!n) return SP_OK;
+    if (!boards || !out) return fail(ctx, SP_ERR_INVALID, "null argument");
+    DeviceGuard guard{ctx->device};
+    if (const int rc = ensure_staging(ctx, n)) return rc;
+    SP_CUDA(ctx, cudaMemcpyAsync(ctx->d_boards, boards, n * sizeof(SpPackedBoard), cudaMemcpyHostToDevice, ctx->stream));
+    if (const int rc = eval_full_device(ctx, ctx->d_boards, n, ctx->d_out, ctx->stream)) return rc;
+    SP_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx, ctx->stream);
+}
+
+int sp_nnue_eval_full_device(SpNnue* ctx, const SpPackedBoard* d_boards, size_t n, int32_t* d_out, void* stream) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!n) return SP_OK;
+    if (!d_boards || !d_out) return fail(ctx, SP_ERR_INVALID, "null argument");
+    if (reinterpret_cast<uintptr_t>(d_boards) & 15) return fail(ctx, SP_ERR_INVALID, "d_boards must be 16-byte aligned");
+    DeviceGuard guard{ctx->device};
+    return eval_full_device(ctx, d_boards, n, d_out, pick(ctx, stream));
+}
+
+int sp_nnue_activations_device(SpNnue* ctx, const SpPackedBoard* d_boards, size_t n, uint8_t* d_act, uint8_t* d_bucket, void* stream) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!n) return SP_OK;
+    if (!d_boards || !d_act || !d_bucket) return fail(ctx, SP_ERR_INVALID, "null argument");
+    if ((reinterpret_cast<uintptr_t>(d_boards) | reinterpret_cast<uintptr_t>(d_act)) & 15)
+        return fail(ctx, SP_ERR_INVALID, "d_boards and d_act must be 16-byte aligned");
+    DeviceGuard guard{ctx->device};
+    launch_ft_full(ctx->net, d_boards, n, d_act, d_bucket, ctx->d_status, ctx->sm_count, pick(ctx, stream));
+    ctx->counters[SP_CTR_LAUNCHES] += 1;
+    ctx->counters[SP_CTR_FULL_REFRESH] += 2 * n;
+    SP_CUDA(ctx, cudaGetLastError());
+    return SP_OK;
+}
+
+int sp_nnue_forward_device(SpNnue* ctx, const uint8_t* d_act, const uint8_t* d_bucket, size_t n, int32_t* d_out, void* stream) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!n) return SP_OK;
+    if (!d_act || !d_bucket || !d_out) return fail(ctx, SP_ERR_INVALID, "null argument");
+    if (reinterpret_cast<uintptr_t>(d_act) & 15) return fail(ctx, SP_ERR_INVALID, "d_act must be 16-byte aligned");
+    DeviceGuard guard{ctx->device};
+    launch_head(ctx->net, d_act, d_bucket, n, d_out, ctx->d_status, ctx->sm_count, pick(ctx, stream));
+    ctx->counters[SP_CTR_LAUNCHES] += 1;
+    ctx->counters[SP_CTR_EVALS] += n;
+    SP_CUDA(ctx, cudaGetLastError());
+    return SP_OK;
+}
+
+int sp_nnue_counters(SpNnue* ctx, uint64_t out[SP_NUM_COUNTERS]) {
+    if (!ctx || !out) return SP_ERR_INVALID;
+    std::memcpy(out, ctx->counters, sizeof(ctx->counters));
+    return SP_OK;
+}
+
+} // extern "C"
+
+/* ------------------------------------------------------------------ accumulator slots / playouts */
+#include "capi_slots.inc"

@@ -1,0 +1,218 @@
+/*
+ * host_capi.cpp -- extern "C" exports of the host-side helpers (no GPU involved):
+ * board conversion, legal move generation, random legal playouts (the synthetic workload of
+ * BASELINE.json configs 2 and 3) and CPU evaluation of the shared feature-index code
+ * (sp_features.h) so that it can be unit-tested without a GPU.
+ * Declared in include/sp_nnue.h ("host utilities").
+ */
+#include <algorithm>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../../include/sp_nnue.h"
+#include "../sp_delta.h"
+#include "../sp_features.h"
+#include "position.h"
+
+using namespace sp;
+using namespace sp::host;
+
+namespace {
+
+/* splitmix64 seeding + JSF64 stream + Lemire's bounded draw: public-domain generators, the same
+ * family the reference uses for datagen (src/util/rng.h), re-stated so playouts are reproducible
+ * from a (seed, game index) pair on any machine. */
+struct SplitMix64 {
+    uint64_t s;
+    uint64_t next() {
+        s += 0x9E3779B97F4A7C15ULL;
+        uint64_t z = s;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    }
+};
+
+struct Jsf64 {
+    uint64_t a{0xF1EA5EED}, b, c, d;
+    explicit Jsf64(uint64_t seed) : b{seed}, c{seed}, d{seed} {
+        for (int i = 0; i < 20; ++i) next();
+    }
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    uint64_t next() {
+        const uint64_t e = a - rotl(b, 7);
+        a = b ^ rotl(c, 13);
+        b = c + rotl(d, 37);
+        c = d + e;
+        d = e + a;
+        return d;
+    }
+    uint32_t below(uint32_t bound) {
+        if (!bound) return 0;
+        uint32_t x = static_cast<uint32_t>(next() >> 32);
+        uint64_t m = static_cast<uint64_t>(x) * bound;
+        uint32_t l = static_cast<uint32_t>(m);
+        if (l < bound) {
+            const uint32_t t = (0u - bound) % bound;
+            while (l < t) {
+                x = static_cast<uint32_t>(next() >> 32);
+                m = static_cast<uint64_t>(x) * bound;
+                l = static_cast<uint32_t>(m);
+            }
+        }
+        return static_cast<uint32_t>(m >> 32);
+    }
+};
+
+const FeatureTables& tables() {
+    static const FeatureTables t = [] {
+        FeatureTables x;
+        build_feature_tables(x);
+        return x;
+    }();
+    return t;
+}
+
+/* One game: emits every position including the start; moves[i] is the move played from boards[i]. */
+size_t play_game(uint64_t seed, uint32_t max_plies, SpPackedBoard* boards, SpMove* moves) {
+    Jsf64 rng{seed};
+    Position pos = Position::startpos();
+    size_t n = 0;
+    for (uint32_t ply = 0;; ++ply) {
+        boards[n] = pos.pack();
+        moves[n] = 0;
+        ++n;
+        if (ply >= max_plies || popcount64(pos.occ()) <= 2) break;
+        Move legal[256];
+        const int count = pos.generateLegal(legal);
+        if (!count) break;
+        const Move m = legal[rng.below(static_cast<uint32_t>(count))];
+        moves[n - 1] = m.raw;
+        pos = pos.applyMove(m);
+    }
+    return n;
+}
+
+} // namespace
+
+extern "C" {
+
+/* see include/sp_nnue.h */
+size_t sp_host_playouts(
+    uint64_t seed,
+    uint32_t n_games,
+    uint32_t max_plies,
+    int threads,
+    SpPackedBoard* boards,
+    SpMove* moves,
+    uint32_t* game_start
+) {
+    if (threads < 1) threads = 1;
+    const size_t stride = static_cast<size_t>(max_plies) + 1;
+    std::vector<uint64_t> seeds(n_games);
+    SplitMix64 sm{seed};
+    for (auto& s : seeds) s = sm.next();
+    std::vector<uint32_t> len(n_games);
+    /* every game writes into its own fixed-stride window, then the windows are compacted in order,
+     * so the result does not depend on the thread count */
+    std::vector<SpPackedBoard> tmpBoards(static_cast<size_t>(n_games) * stride);
+    std::vector<SpMove> tmpMoves(static_cast<size_t>(n_games) * stride);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        pool.emplace_back([&, t] {
+            for (uint32_t g = static_cast<uint32_t>(t); g < n_games; g += static_cast<uint32_t>(threads))
+                len[g] = static_cast<uint32_t>(play_game(seeds[g], max_plies, &tmpBoards[g * stride], &tmpMoves[g * stride]));
+        });
+    }
+    for (auto& th : pool) th.join();
+    size_t n = 0;
+    for (uint32_t g = 0; g < n_games; ++g) {
+        game_start[g] = static_cast<uint32_t>(n);
+        std::memcpy(&boards[n], &tmpBoards[g * stride], len[g] * sizeof(SpPackedBoard));
+        std::memcpy(&moves[n], &tmpMoves[g * stride], len[g] * sizeof(SpMove));
+        n += len[g];
+    }
+    game_start[n_games] = static_cast<uint32_t>(n);
+    return n;
+}
+
+int sp_host_board_from_fen(const char* fen, SpPackedBoard* out) {
+    Position p;
+    if (!Position::fromFen(fen, p)) return SP_ERR_BAD_BOARD;
+    *out = p.pack();
+    return SP_OK;
+}
+
+int sp_host_board_to_fen(const SpPackedBoard* board, char* out, size_t cap) {
+    Position p;
+    if (!Position::fromPacked(*board, p)) return SP_ERR_BAD_BOARD;
+    const std::string fen = p.toFen();
+    if (fen.size() + 1 > cap) return SP_ERR_INVALID;
+    std::memcpy(out, fen.c_str(), fen.size() + 1);
+    return SP_OK;
+}
+
+int sp_host_legal_moves(const SpPackedBoard* board, SpMove* out) {
+    Position p;
+    if (!Position::fromPacked(*board, p)) return -1;
+    Move legal[256];
+    const int n = p.generateLegal(legal);
+    for (int i = 0; i < n; ++i) out[i] = legal[i].raw;
+    return n;
+}
+
+int sp_host_apply_move(const SpPackedBoard* board, SpMove move, SpPackedBoard* out) {
+    Position p;
+    if (!Position::fromPacked(*board, p)) return SP_ERR_BAD_BOARD;
+    *out = p.applyMove(Move{move}).pack();
+    return SP_OK;
+}
+
+/* Feature index lists of perspective c computed by the SAME code the kernels run
+ * (sp_features.h), on the CPU. kind 0 = PSQ, 1 = threats + pawn pairs. Returns the count. */
+int sp_host_features(const SpPackedBoard* board, int c, int kind, uint32_t* out) {
+    Board b;
+    if (unpack_board(*board, b)) return -1;
+    int n = 0;
+    auto emit = [&](int persp, uint32_t idx) {
+        if (persp == c) out[n++] = idx;
+    };
+    for (int sq = 0; sq < 64; ++sq) {
+        if (kind == 0)
+            square_psq_features(tables(), b, sq, emit);
+        else
+            square_threat_features(tables(), b, sq, emit);
+    }
+    return n;
+}
+
+/* Feature deltas between two boards for perspective c, computed by the shared delta generator
+ * (sp_delta.h) on the CPU. Returns 0, or 1 if the perspective needs a full refresh. */
+int sp_host_feature_delta(
+    const SpPackedBoard* before,
+    const SpPackedBoard* after,
+    int c,
+    uint32_t* psq_add, int* n_psq_add,
+    uint32_t* psq_sub, int* n_psq_sub,
+    uint32_t* thr_add, int* n_thr_add,
+    uint32_t* thr_sub, int* n_thr_sub
+) {
+    Board bb, ba;
+    if (unpack_board(*before, bb) || unpack_board(*after, ba)) return -1;
+    *n_psq_add = *n_psq_sub = *n_thr_add = *n_thr_sub = 0;
+    if (needs_refresh(tables(), bb, ba, c)) return 1;
+    const uint64_t changed = changed_squares(bb, ba);
+    auto emit = [&](int persp, int kind, int sign, uint32_t idx) {
+        if (persp != c) return;
+        if (kind == 0) {
+            if (sign > 0) psq_add[(*n_psq_add)++] = idx; else psq_sub[(*n_psq_sub)++] = idx;
+        } else {
+            if (sign > 0) thr_add[(*n_thr_add)++] = idx; else thr_sub[(*n_thr_sub)++] = idx;
+        }
+    };
+    for (int item = 0; item < kDeltaItems; ++item) delta_item(tables(), bb, ba, changed, item, emit);
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,90 @@
+/*
+ * kernels.cuh -- launch interface between the C-ABI layer (capi.cu) and the sm_100a kernels
+ * (kernels.cu).  Device memory layouts are documented in DESIGN.md section 3.
+ */
+#ifndef SP_KERNELS_CUH
+#define SP_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sp_features.h"
+
+namespace sp::gpu {
+
+/* Row counts of the device feature-transformer tables (extra rows are synthetic). */
+constexpr int kPsqBiasRow = SP_PSQ_FEATURES;        /* FT bias stored as one more PSQ row */
+constexpr int kPsqZeroRow = SP_PSQ_FEATURES + 1;    /* all-zero row: pads index lists to x4 */
+constexpr int kPsqRows = SP_PSQ_FEATURES + 2;
+constexpr int kThrZeroRow = SP_THREAT_FEATURES;     /* "zero" row (0x80 bytes in the biased table) */
+constexpr int kThrRows = SP_THREAT_FEATURES + 1;
+
+constexpr int kSlotBytes = 2 * SP_L1_SIZE * 2;      /* two perspectives of int16[1024] */
+constexpr int kSlotVec = kSlotBytes / 16;           /* uint4 per slot */
+
+struct DeviceNet {
+    const uint4* psq;   /* [kPsqRows][128]: int16 rows in lane order (see lane_order_element) */
+    const uint4* thr;   /* [kThrRows][64] : int8 rows + 128 (stored unsigned), natural order */
+    const int8_t* l1_w; /* [8][256][32][4] reference order (multilayer.h:180-196) */
+    const int32_t* l1_b;
+    const int32_t* l2_w; /* [8][64][64] */
+    const int32_t* l2_b;
+    const int32_t* l3_w; /* [8][64] */
+    const int32_t* l3_b;
+    const FeatureTables* tables;
+};
+
+struct SlotStore {
+    uint4* acc;            /* [n_slots][2][4][32] uint4 : lane-order accumulators (psq + threat, wrapped) */
+    SpPackedBoard* boards; /* [n_slots] */
+    uint32_t n_slots;
+};
+
+enum : int {
+    kErrBadBoard = 1,
+    kErrCapacity = 2,
+    kErrBadSlot = 4,
+};
+
+/* Device-resident status block. */
+struct DeviceStatus {
+    int error; /* OR of kErr* bits */
+    int pad;
+    unsigned long long counters[8];
+};
+
+/* Logical element index held at (chunk k, lane l, element e) of a device PSQ row / accumulator:
+ * lane l owns logical elements [16 l, 16 l + 16) and [512 + 16 l, 512 + 16 l + 16), i.e. both
+ * members of the 16 activation pairs (i, i + 512) it will multiply (multilayer.h:118-135). */
+inline int lane_order_element(int k, int lane, int e) { return (k >= 2 ? 512 : 0) + lane * 16 + (k & 1) * 8 + e; }
+
+/* boards[i] -> act[i][1024], bucket[i]; every position rebuilt from scratch */
+void launch_ft_full(
+    const DeviceNet& net, const SpPackedBoard* boards, size_t n, uint8_t* act, uint8_t* bucket, DeviceStatus* status,
+    int sm_count, cudaStream_t stream);
+
+/* slot refresh / update. src == nullptr: every dst slot is rebuilt from boards[i].
+ * act may be nullptr (no evaluation wanted). */
+void launch_ft_slots(
+    const DeviceNet& net, SlotStore slots, const uint32_t* src, const uint32_t* dst, const SpPackedBoard* boards,
+    size_t n, uint8_t* act, uint8_t* bucket, DeviceStatus* status, int sm_count, cudaStream_t stream);
+
+/* one warp walks one game; act/bucket rows are indexed like boards */
+void launch_ft_games(
+    const DeviceNet& net, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, uint8_t* act,
+    uint8_t* bucket, DeviceStatus* status, int sm_count, cudaStream_t stream);
+
+/* slots[i] -> act[i], bucket[i]; stm may be nullptr (use the stored board's side to move) */
+void launch_slot_activate(
+    SlotStore slots, const uint32_t* slot_ids, const uint8_t* stm, size_t n, uint8_t* act, uint8_t* bucket,
+    DeviceStatus* status, int sm_count, cudaStream_t stream);
+
+/* act[i], bucket[i] -> out[i] : L1 (int8 IMMA) + L2 + L3 + scale.  bucket[i] > 7 marks a
+ * position whose board was rejected: out[i] = INT32_MIN. */
+void launch_head(
+    const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, DeviceStatus* status,
+    int sm_count, cudaStream_t stream);
+
+} // namespace sp::gpu
+
+#endif
