@@ -56,6 +56,10 @@ int sp_nnue_device(const SpNnue* ctx);
  * check: SP_ERR_BAD_BOARD, SP_ERR_CAPACITY, SP_ERR_INVALID (slot out of range) or SP_OK.  The
  * host-pointer entry points do this themselves; the *_device ones are asynchronous and do not. */
 int sp_nnue_sync(SpNnue* ctx, void* stream);
+/* Run the host-pointer entry points on the caller's stream (a cudaStream_t as void*) instead of
+ * the context's private one, so that a caller can bracket them with its own events.
+ * NULL restores a private stream. */
+int sp_nnue_set_stream(SpNnue* ctx, void* stream);
 
 /* ---------------------------------------------------------------- full refresh
  * Replaces NnueState::evaluateOnce / eval::staticEvalOnce for a batch
@@ -145,6 +149,18 @@ enum {
     SP_NUM_COUNTERS = 8
 };
 int sp_nnue_counters(SpNnue* ctx, uint64_t out[SP_NUM_COUNTERS]);
+/* Per-kernel device time: when enabled, every launch made by this context is bracketed with CUDA
+ * events on its stream; sp_nnue_profile_read waits for them, returns summed milliseconds and launch
+ * counts per kernel class since the previous read, and resets the sums. */
+enum {
+    SP_KERNEL_FT_FULL = 0,  /* boards -> activations, both accumulators rebuilt */
+    SP_KERNEL_HEAD = 1,     /* activations -> evals (L1 IMMA, L2, L3) */
+    SP_KERNEL_FT_SLOTS = 2, /* slot refresh / incremental update */
+    SP_KERNEL_FT_GAMES = 3, /* playout walker */
+    SP_NUM_KERNEL_CLASSES = 4
+};
+int sp_nnue_profile(SpNnue* ctx, int enable);
+int sp_nnue_profile_read(SpNnue* ctx, double ms[SP_NUM_KERNEL_CLASSES], uint64_t launches[SP_NUM_KERNEL_CLASSES]);
 /* Debug/test access: accumulators of a slot in LOGICAL order, int16[2][1024] (black, white). */
 int sp_nnue_read_slot(SpNnue* ctx, uint32_t slot, int16_t* out_acc, SpPackedBoard* out_board);
 
@@ -167,6 +183,9 @@ int sp_host_board_to_fen(const SpPackedBoard* board, char* out, size_t cap);
 int sp_host_legal_moves(const SpPackedBoard* board, SpMove* out /* [256] */);
 int sp_host_apply_move(const SpPackedBoard* board, SpMove move, SpPackedBoard* out);
 int sp_host_features(const SpPackedBoard* board, int perspective, int kind, uint32_t* out /* [512] */);
+/* Workload statistics for the roofline: out[0] = PSQ rows, out[1] = threat rows, out[2] = pawn-pair
+ * rows, summed over both perspectives of all n boards (what a full refresh must read). */
+int sp_host_feature_counts(const SpPackedBoard* boards, size_t n, int threads, uint64_t out[3]);
 int sp_host_feature_delta(
     const SpPackedBoard* before,
     const SpPackedBoard* after,

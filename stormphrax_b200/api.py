@@ -30,6 +30,8 @@ SP_OK, SP_ERR_INVALID, SP_ERR_BAD_NETWORK, SP_ERR_CUDA, SP_ERR_NO_DEVICE, SP_ERR
 STATUS_NAMES = ["SP_OK", "SP_ERR_INVALID", "SP_ERR_BAD_NETWORK", "SP_ERR_CUDA", "SP_ERR_NO_DEVICE", "SP_ERR_BAD_BOARD", "SP_ERR_CAPACITY"]
 NUM_COUNTERS = 8
 CTR_EVALS, CTR_FULL_REFRESH, CTR_INCREMENTAL, CTR_LAUNCHES = 0, 1, 2, 3
+KERNEL_CLASSES = ["ft_full", "head", "ft_slots", "ft_games"]
+NUM_KERNEL_CLASSES = len(KERNEL_CLASSES)
 
 _vp = C.c_void_p
 _sz = C.c_size_t
@@ -41,6 +43,10 @@ SIGNATURES = {
     "sp_nnue_last_error": (C.c_char_p, [_vp]),
     "sp_nnue_device": (C.c_int, [_vp]),
     "sp_nnue_sync": (C.c_int, [_vp, _vp]),
+    "sp_nnue_set_stream": (C.c_int, [_vp, _vp]),
+    "sp_nnue_profile": (C.c_int, [_vp, C.c_int]),
+    "sp_nnue_profile_read": (C.c_int, [_vp, _vp, _vp]),
+    "sp_host_feature_counts": (C.c_int, [_vp, _sz, C.c_int, _vp]),
     "sp_nnue_eval_full": (C.c_int, [_vp, _vp, _sz, _vp]),
     "sp_nnue_eval_full_device": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
     "sp_nnue_slots_reserve": (C.c_int, [_vp, _sz]),
@@ -146,6 +152,19 @@ class Nnue:
 
     def sync(self, stream: int | None = None) -> None:
         self._check(self._lib.sp_nnue_sync(self._h, stream))
+
+    def set_stream(self, stream: int | None) -> None:
+        self._check(self._lib.sp_nnue_set_stream(self._h, stream))
+
+    def profile(self, enable: bool) -> None:
+        self._check(self._lib.sp_nnue_profile(self._h, int(enable)))
+
+    def profile_read(self) -> dict:
+        """{kernel class: (milliseconds, launches)} since the previous read."""
+        ms = np.zeros(NUM_KERNEL_CLASSES, dtype=np.float64)
+        launches = np.zeros(NUM_KERNEL_CLASSES, dtype=np.uint64)
+        self._check(self._lib.sp_nnue_profile_read(self._h, ms.ctypes.data, launches.ctypes.data))
+        return {name: (float(ms[i]), int(launches[i])) for i, name in enumerate(KERNEL_CLASSES)}
 
     def counters(self) -> np.ndarray:
         out = np.zeros(NUM_COUNTERS, dtype=np.uint64)
@@ -284,6 +303,16 @@ def features(board, perspective: int, kind: int) -> np.ndarray:
     if n < 0:
         raise NnueError(SP_ERR_BAD_BOARD, "bad board")
     return out[:n].copy()
+
+
+def feature_counts(boards, threads: int = 0) -> dict:
+    """Rows a full refresh of `boards` must read, summed over both perspectives."""
+    boards = _boards(boards)
+    out = np.zeros(3, dtype=np.uint64)
+    rc = lib().sp_host_feature_counts(boards.ctypes.data, boards.size, threads or min(os.cpu_count() or 1, 32), out.ctypes.data)
+    if rc:
+        raise NnueError(rc, "bad board")
+    return {"psq_rows": int(out[0]), "threat_rows": int(out[1]), "pawn_pair_rows": int(out[2])}
 
 
 def feature_delta(before, after, perspective: int):

@@ -23,6 +23,7 @@ struct SpNnue {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    bool owns_stream = true;
     DeviceNet net{};
     uint8_t* d_net_blob = nullptr;
     FeatureTables* d_tables = nullptr;
@@ -33,6 +34,10 @@ struct SpNnue {
     size_t chunk = 32768;
     uint8_t* d_act = nullptr;
     uint8_t* d_bucket = nullptr;
+    /* whole-stream scratch of the playout walker (one activation row per board) */
+    uint8_t* d_act_big = nullptr;
+    uint8_t* d_bucket_big = nullptr;
+    size_t act_cap = 0;
     /* staging for the host-pointer entry points */
     SpPackedBoard* d_boards = nullptr;
     int32_t* d_out = nullptr;
@@ -43,6 +48,14 @@ struct SpNnue {
     SlotStore slots{};
     uint64_t counters[SP_NUM_COUNTERS] = {};
     std::string error;
+
+    /* optional per-kernel timing (sp_nnue_profile): event pairs around launches, by kernel class */
+    bool profiling = false;
+    struct Span { cudaEvent_t a, b; int kind; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    double prof_ms[SP_NUM_KERNEL_CLASSES] = {};
+    uint64_t prof_launches[SP_NUM_KERNEL_CLASSES] = {};
 };
 
 namespace {
@@ -183,12 +196,46 @@ struct DeviceGuard {
 
 cudaStream_t pick(SpNnue* ctx, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : ctx->stream; }
 
+cudaEvent_t take_event(SpNnue* ctx) {
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+/* RAII: brackets one kernel launch with events when profiling is on */
+struct Timed {
+    SpNnue* ctx;
+    cudaStream_t stream;
+    SpNnue::Span span{};
+    Timed(SpNnue* c, cudaStream_t s, int kind) : ctx{c}, stream{s} {
+        if (!ctx->profiling) return;
+        span = {take_event(ctx), take_event(ctx), kind};
+        cudaEventRecord(span.a, stream);
+    }
+    ~Timed() {
+        if (!ctx->profiling) return;
+        cudaEventRecord(span.b, stream);
+        ctx->spans.push_back(span);
+    }
+};
+
 /* boards (device) -> out (device), in chunks that keep the activation scratch L2-sized */
 int eval_full_device(SpNnue* ctx, const SpPackedBoard* d_boards, size_t n, int32_t* d_out, cudaStream_t stream) {
     for (size_t off = 0; off < n; off += ctx->chunk) {
         const size_t m = std::min(ctx->chunk, n - off);
-        launch_ft_full(ctx->net, d_boards + off, m, ctx->d_act, ctx->d_bucket, ctx->d_status, ctx->sm_count, stream);
-        launch_head(ctx->net, ctx->d_act, ctx->d_bucket, m, d_out + off, ctx->d_status, ctx->sm_count, stream);
+        {
+            Timed timed{ctx, stream, SP_KERNEL_FT_FULL};
+            launch_ft_full(ctx->net, d_boards + off, m, ctx->d_act, ctx->d_bucket, ctx->d_status, ctx->sm_count, stream);
+        }
+        {
+            Timed timed{ctx, stream, SP_KERNEL_HEAD};
+            launch_head(ctx->net, ctx->d_act, ctx->d_bucket, m, d_out + off, ctx->d_status, ctx->sm_count, stream);
+        }
         ctx->counters[SP_CTR_LAUNCHES] += 2;
     }
     ctx->counters[SP_CTR_EVALS] += n;
@@ -270,19 +317,65 @@ void sp_nnue_destroy(SpNnue* ctx) {
     cudaFreeHost(ctx->h_status);
     cudaFree(ctx->d_act);
     cudaFree(ctx->d_bucket);
+    cudaFree(ctx->d_act_big);
+    cudaFree(ctx->d_bucket_big);
     cudaFree(ctx->d_boards);
     cudaFree(ctx->d_out);
     cudaFree(ctx->d_ids);
     cudaFree(ctx->d_stm);
     cudaFree(ctx->slots.acc);
     cudaFree(ctx->slots.boards);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (const auto& span : ctx->spans) cudaEventDestroy(span.a), cudaEventDestroy(span.b);
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->stream && ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 const char* sp_nnue_last_error(const SpNnue* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
 int sp_nnue_device(const SpNnue* ctx) { return ctx ? ctx->device : -1; }
+
+int sp_nnue_set_stream(SpNnue* ctx, void* stream) {
+    if (!ctx) return SP_ERR_INVALID;
+    DeviceGuard guard{ctx->device};
+    SP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    ctx->owns_stream = stream == nullptr;
+    if (stream) {
+        ctx->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        SP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    }
+    return SP_OK;
+}
+
+int sp_nnue_profile(SpNnue* ctx, int enable) {
+    if (!ctx) return SP_ERR_INVALID;
+    ctx->profiling = enable != 0;
+    return SP_OK;
+}
+
+int sp_nnue_profile_read(SpNnue* ctx, double ms[SP_NUM_KERNEL_CLASSES], uint64_t launches[SP_NUM_KERNEL_CLASSES]) {
+    if (!ctx || !ms || !launches) return SP_ERR_INVALID;
+    DeviceGuard guard{ctx->device};
+    for (const auto& span : ctx->spans) {
+        SP_CUDA(ctx, cudaEventSynchronize(span.b));
+        float t = 0;
+        SP_CUDA(ctx, cudaEventElapsedTime(&t, span.a, span.b));
+        ctx->prof_ms[span.kind] += t;
+        ctx->prof_launches[span.kind] += 1;
+        ctx->event_pool.push_back(span.a);
+        ctx->event_pool.push_back(span.b);
+    }
+    ctx->spans.clear();
+    for (int k = 0; k < SP_NUM_KERNEL_CLASSES; ++k) {
+        ms[k] = ctx->prof_ms[k];
+        launches[k] = ctx->prof_launches[k];
+        ctx->prof_ms[k] = 0;
+        ctx->prof_launches[k] = 0;
+    }
+    return SP_OK;
+}
 
 int sp_nnue_sync(SpNnue* ctx, void* stream) {
     if (!ctx) return SP_ERR_INVALID;

@@ -6,6 +6,7 @@
  * Declared in include/sp_nnue.h ("host utilities").
  */
 #include <algorithm>
+#include <array>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -185,6 +186,36 @@ int sp_host_features(const SpPackedBoard* board, int c, int kind, uint32_t* out)
             square_threat_features(tables(), b, sq, emit);
     }
     return n;
+}
+
+int sp_host_feature_counts(const SpPackedBoard* boards, size_t n, int threads, uint64_t out[3]) {
+    if (threads < 1) threads = 1;
+    std::vector<std::array<uint64_t, 4>> part(static_cast<size_t>(threads), {0, 0, 0, 0});
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        pool.emplace_back([&, t] {
+            auto& p = part[static_cast<size_t>(t)];
+            for (size_t i = n * t / threads; i < n * (t + 1) / threads; ++i) {
+                Board b;
+                if (unpack_board(boards[i], b)) {
+                    p[3] = 1;
+                    continue;
+                }
+                for (int sq = 0; sq < 64; ++sq) {
+                    square_psq_features(tables(), b, sq, [&](int, uint32_t) { ++p[0]; });
+                    square_threat_features(tables(), b, sq, [&](int, uint32_t idx) { ++p[idx < SP_PP_FEATURES ? 2 : 1]; });
+                }
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    out[0] = out[1] = out[2] = 0;
+    bool bad = false;
+    for (const auto& p : part) {
+        out[0] += p[0], out[1] += p[1], out[2] += p[2];
+        bad |= p[3] != 0;
+    }
+    return bad ? SP_ERR_BAD_BOARD : SP_OK;
 }
 
 /* Feature deltas between two boards for perspective c, computed by the shared delta generator

@@ -27,16 +27,21 @@ namespace {
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kPsqGroup = 4;      /* PSQ rows fetched per batch of loads (16 x LDG.128 in flight per lane) */
-constexpr int kThrGroup = 8;      /* threat rows per batch (16 x LDG.128 in flight per lane) */
-constexpr int kPsqListCap = 40;   /* 32 pieces + bias row, padded to a multiple of kPsqGroup */
+constexpr int kThrGroupFull = 8;  /* threat rows per batch on the rebuild path (16 x LDG.128 in flight) */
+constexpr int kThrGroupDelta = 4; /* per sign on the incremental path (4 adds + 4 subs = 16 x LDG.128) */
+constexpr int kPsqListCap = 40;   /* 32 pieces + bias row */
 constexpr int kThrListCap = SP_MAX_THREAT_INDICES;
+constexpr uint32_t kSubFlag = 0x8000u; /* PSQ list entries: bit 15 = subtract this row */
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
+/* Per-warp shared memory. */
 struct WarpScratch {
-    uint16_t thr[2][kThrListCap];
+    uint16_t thr_add[2][kThrListCap];
+    uint16_t thr_sub[2][kThrListCap];
     uint16_t psq[2][kPsqListCap];
-    uint8_t mailbox[64];
-    int n_thr[2];
+    uint8_t mailbox[2][64]; /* two boards: the one being evaluated and its predecessor */
+    int n_thr_add[2];
+    int n_thr_sub[2];
     int n_psq[2];
 };
 
@@ -83,6 +88,7 @@ __device__ __forceinline__ Decoded decode_board(const SpPackedBoard* board, int 
     d.ok = d.n_pieces <= 32 && d.n_pieces >= 2;
     d.piece = kNoPiece;
     d.sq = 0;
+    __syncwarp();
     reinterpret_cast<uint16_t*>(mailbox)[lane] = static_cast<uint16_t>(kNoPiece | kNoPiece << 8);
     __syncwarp();
     if (lane < d.n_pieces && d.ok) {
@@ -110,54 +116,80 @@ __device__ __forceinline__ Decoded decode_board(const SpPackedBoard* board, int 
     return d;
 }
 
-/* Build both perspectives' full feature lists (nnue_state.cpp:309-354, 440-449).  Returns false
- * if a threat list would exceed the reference's own bound of 256 entries. */
-__device__ __forceinline__ bool build_full_lists(const FeatureTables& t, const Decoded& d, int lane, WarpScratch& ws) {
-    if (lane < 2) ws.n_thr[lane] = 0;
-    __syncwarp();
-    if (d.piece != kNoPiece) {
-        ws.psq[kBlack][lane] = static_cast<uint16_t>(psq_index(t, kBlack, d.piece, d.sq, d.view.king[kBlack]));
-        ws.psq[kWhite][lane] = static_cast<uint16_t>(psq_index(t, kWhite, d.piece, d.sq, d.view.king[kWhite]));
-        square_threat_features(t, d.view, d.sq, [&](int c, uint32_t idx) {
-            const int at = atomicAdd(&ws.n_thr[c], 1);
-            if (at < kThrListCap) ws.thr[c][at] = static_cast<uint16_t>(idx);
-        });
+__device__ __forceinline__ void push(uint16_t* list, int* count, uint32_t value) {
+    const int at = atomicAdd(count, 1);
+    if (at < kThrListCap) list[at] = static_cast<uint16_t>(value);
+}
+
+/*
+ * Fill the warp's feature lists for the step `before` -> `d` (before == nullptr: no predecessor).
+ *   perspectives in the returned mask are rebuilt from scratch: psq list = all pieces + bias row,
+ *     thr_add = every threat / pawn-pair feature of the board (nnue_state.cpp:309-354, 440-449)
+ *   the others are updated: psq list = signed delta rows, thr_add / thr_sub = delta rows (sp_delta.h;
+ *     replaces nnue.cpp:490-599, nnue_state.cpp:163-307)
+ * A perspective is rebuilt when its king changes input bucket or board half (psq.h:264-283,
+ * nnue_state.h:118-128), when more than kMaxChanged squares differ, or when a delta list overflows.
+ * Returns -1 if a full list exceeds the reference's bound of 256 entries.
+ */
+__device__ __forceinline__ int build_lists(
+    const FeatureTables& t, const BoardView* before, const Decoded& d, int lane, WarpScratch& ws) {
+    int rebuild = 3;
+    uint64_t changed = 0;
+    if (before) {
+        const unsigned lo = __ballot_sync(kFull, before->mailbox[lane] != d.view.mailbox[lane]);
+        const unsigned hi = __ballot_sync(kFull, before->mailbox[32 + lane] != d.view.mailbox[32 + lane]);
+        changed = static_cast<uint64_t>(hi) << 32 | lo;
+        rebuild = (needs_refresh(t, *before, d.view, kBlack) ? 1 : 0) | (needs_refresh(t, *before, d.view, kWhite) ? 2 : 0);
+        if (__popcll(changed) > kMaxChanged) rebuild = 3;
     }
-    __syncwarp();
-    const int n0 = ws.n_thr[0], n1 = ws.n_thr[1];
-    if (n0 > kThrListCap || n1 > kThrListCap) return false;
-    /* bias row + zero-row padding so the row loops run in whole batches */
-    const int np = d.n_pieces;
-    const int np_pad = (np + 1 + kPsqGroup - 1) / kPsqGroup * kPsqGroup;
-    if (lane < 2) {
-        ws.psq[lane][np] = kPsqBiasRow;
-        for (int i = np + 1; i < np_pad; ++i) ws.psq[lane][i] = kPsqZeroRow;
-        ws.n_psq[lane] = np_pad;
-        const int n = lane == 0 ? n0 : n1;
-        const int n_pad = (n + kThrGroup - 1) / kThrGroup * kThrGroup;
-        for (int i = n; i < n_pad; ++i) ws.thr[lane][i] = static_cast<uint16_t>(kThrZeroRow);
-        ws.n_thr[lane] = n_pad;
+    for (;;) {
+        if (lane < 2) ws.n_thr_add[lane] = ws.n_thr_sub[lane] = ws.n_psq[lane] = 0;
+        __syncwarp();
+        if (rebuild != 3) {
+            const int n_items = __popcll(changed) * 2 * kItemsPerSquareBoard;
+            for (int item = lane; item < n_items; item += 32) {
+                delta_item(t, *before, d.view, changed, item, [&](int c, int kind, int sign, uint32_t idx) {
+                    if ((rebuild >> c) & 1) return;
+                    if (kind == 0) push(ws.psq[c], &ws.n_psq[c], sign > 0 ? idx : idx | kSubFlag);
+                    else if (sign > 0) push(ws.thr_add[c], &ws.n_thr_add[c], idx);
+                    else push(ws.thr_sub[c], &ws.n_thr_sub[c], idx);
+                });
+            }
+        }
+        if (rebuild && d.piece != kNoPiece) {
+            if (rebuild & 1) ws.psq[kBlack][lane] = static_cast<uint16_t>(psq_index(t, kBlack, d.piece, d.sq, d.view.king[kBlack]));
+            if (rebuild & 2) ws.psq[kWhite][lane] = static_cast<uint16_t>(psq_index(t, kWhite, d.piece, d.sq, d.view.king[kWhite]));
+            square_threat_features(t, d.view, d.sq, [&](int c, uint32_t idx) {
+                if ((rebuild >> c) & 1) push(ws.thr_add[c], &ws.n_thr_add[c], idx);
+            });
+        }
+        __syncwarp();
+        if (lane < 2 && ((rebuild >> lane) & 1)) {
+            ws.psq[lane][d.n_pieces] = kPsqBiasRow;
+            ws.n_psq[lane] = d.n_pieces + 1;
+        }
+        __syncwarp();
+        int overflow = 0;
+        for (int c = 0; c < 2; ++c)
+            if (ws.n_thr_add[c] > kThrListCap || ws.n_thr_sub[c] > kThrListCap || ws.n_psq[c] > kPsqListCap) overflow |= 1 << c;
+        if (!overflow) return rebuild;
+        if (overflow & rebuild) return -1; /* a from-scratch list does not fit: the reference's own limit */
+        rebuild = 3;                       /* an over-long delta: fall back to rebuilding */
+        __syncwarp();
     }
-    __syncwarp();
-    return true;
 }
 
 /* ------------------------------------------------------------------ accumulators in registers */
 
 /* One perspective, one lane: 32 logical elements.
- *   plo/phi  int16 PSQ sums, one 32-bit register per element; only the low 16 bits are meaningful
+ *   plo/phi  int16 sums, one 32-bit register per element; only the low 16 bits are meaningful
  *            (plo += word leaves garbage above bit 15, phi += word >> 16 likewise)
- *   te/to    sums of BIASED (+128) threat bytes, two 16-bit fields per register: even bytes of a
- *            word in te, odd bytes in to.  <= 256 rows x 255 < 2^16, so fields never carry. */
+ *   ae/ao    sums of BIASED (+128) threat bytes of added rows, two 16-bit fields per register: even
+ *            bytes of a word in ae, odd bytes in ao.  <= 256 rows x 255 < 2^16: fields never carry.
+ *   se/so    the same for subtracted rows */
 struct LaneAcc {
     uint32_t plo[16], phi[16];
-    uint32_t te[8], to[8];
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) plo[i] = phi[i] = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) te[i] = to[i] = 0;
-    }
+    uint32_t ae[8], ao[8], se[8], so[8];
 };
 
 template <int kSign>
@@ -202,38 +234,77 @@ __device__ __forceinline__ void load_thr_row(const DeviceNet& net, uint32_t row,
     c[1] = __ldg(r + 32);
 }
 
-/* Sum `n_psq` PSQ rows and `n_thr` threat rows (both multiples of their batch size). */
-__device__ __forceinline__ void accumulate_lists(
-    const DeviceNet& net, const uint16_t* psq_list, int n_psq, const uint16_t* thr_list, int n_thr, int lane, LaneAcc& a) {
-    for (int i = 0; i < n_psq; i += kPsqGroup) {
+/* Apply a PSQ row list (entries may carry kSubFlag); short batches are topped up with the zero row. */
+__device__ __forceinline__ void accumulate_psq(const DeviceNet& net, const uint16_t* list, int n, int lane, LaneAcc& a) {
+    for (int i = 0; i < n; i += kPsqGroup) {
         uint4 c[kPsqGroup][4];
+        uint32_t e[kPsqGroup];
 #pragma unroll
-        for (int j = 0; j < kPsqGroup; ++j) load_psq_row(net, psq_list[i + j], lane, c[j]);
+        for (int j = 0; j < kPsqGroup; ++j) {
+            e[j] = i + j < n ? list[i + j] : static_cast<uint32_t>(kPsqZeroRow);
+            load_psq_row(net, e[j] & (kSubFlag - 1), lane, c[j]);
+        }
 #pragma unroll
-        for (int j = 0; j < kPsqGroup; ++j) add_psq_chunks<1>(a, c[j]);
-    }
-    for (int i = 0; i < n_thr; i += kThrGroup) {
-        uint4 c[kThrGroup][2];
-#pragma unroll
-        for (int j = 0; j < kThrGroup; ++j) load_thr_row(net, thr_list[i + j], lane, c[j]);
-#pragma unroll
-        for (int j = 0; j < kThrGroup; ++j) add_thr_chunks(a.te, a.to, c[j]);
+        for (int j = 0; j < kPsqGroup; ++j) {
+            if (e[j] & kSubFlag) add_psq_chunks<-1>(a, c[j]);
+            else add_psq_chunks<1>(a, c[j]);
+        }
     }
 }
 
-/* Collapse a LaneAcc into 32 wrapped int16 values: v[0..15] = first-half elements 16l + j,
- * v[16..31] = second-half elements 512 + 16l + j.  `n_thr` rows contributed a +128 bias each. */
-__device__ __forceinline__ void finalize(const LaneAcc& a, int n_thr, int (&v)[32]) {
-    const uint32_t corr = static_cast<uint32_t>(n_thr) * 128u;
+/* Sum threat rows; returns how many rows (including zero-row top-ups, each worth +128) went in. */
+template <int kGroup>
+__device__ __forceinline__ int accumulate_thr(
+    const DeviceNet& net, const uint16_t* list, int n, int lane, uint32_t (&te)[8], uint32_t (&to)[8]) {
+    int rows = 0;
+    for (int i = 0; i < n; i += kGroup) {
+        uint4 c[kGroup][2];
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) load_thr_row(net, i + j < n ? list[i + j] : static_cast<uint32_t>(kThrZeroRow), lane, c[j]);
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) add_thr_chunks(te, to, c[j]);
+        rows += kGroup;
+    }
+    return rows;
+}
+
+/* Added and subtracted rows in lock-step, so both signs' loads are in flight together. */
+__device__ __forceinline__ int accumulate_thr_delta(
+    const DeviceNet& net, const uint16_t* add, int n_add, const uint16_t* sub, int n_sub, int lane, LaneAcc& a) {
+    int rows = 0;
+    const int n = max(n_add, n_sub);
+    for (int i = 0; i < n; i += kThrGroupDelta) {
+        uint4 ca[kThrGroupDelta][2], cs[kThrGroupDelta][2];
+#pragma unroll
+        for (int j = 0; j < kThrGroupDelta; ++j) {
+            load_thr_row(net, i + j < n_add ? add[i + j] : static_cast<uint32_t>(kThrZeroRow), lane, ca[j]);
+            load_thr_row(net, i + j < n_sub ? sub[i + j] : static_cast<uint32_t>(kThrZeroRow), lane, cs[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kThrGroupDelta; ++j) {
+            add_thr_chunks(a.ae, a.ao, ca[j]);
+            add_thr_chunks(a.se, a.so, cs[j]);
+        }
+        rows += kThrGroupDelta;
+    }
+    return rows; /* the same number of rows on both sides: their +128 biases cancel */
+}
+
+/* Collapse into 32 wrapped int16 values: v[0..15] = first-half elements 16l + j, v[16..31] =
+ * second-half elements 512 + 16l + j.  `bias_rows` = added-minus-subtracted threat rows (x128). */
+template <bool kHasSub>
+__device__ __forceinline__ void finalize(const LaneAcc& a, int bias_rows, int (&v)[32]) {
+    const uint32_t corr = static_cast<uint32_t>(bias_rows) * 128u;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int pi = (h * 2 + (j >> 3)) * 4 + ((j & 7) >> 1);
-            const uint32_t psq = (j & 1) ? a.phi[pi] : a.plo[pi];
-            const uint32_t field = (j & 1) ? a.to[h * 4 + (j >> 2)] : a.te[h * 4 + (j >> 2)];
-            const uint32_t thr = field >> (((j & 3) >> 1) * 16);
-            v[h * 16 + j] = static_cast<int16_t>(static_cast<uint16_t>(psq + thr - corr));
+            const int ti = h * 4 + (j >> 2), shift = ((j & 3) >> 1) * 16;
+            uint32_t x = (j & 1) ? a.phi[pi] : a.plo[pi];
+            x += ((j & 1) ? a.ao[ti] : a.ae[ti]) >> shift;
+            if (kHasSub) x -= ((j & 1) ? a.so[ti] : a.se[ti]) >> shift;
+            v[h * 16 + j] = static_cast<int16_t>(static_cast<uint16_t>(x - corr));
         }
     }
 }
@@ -253,6 +324,7 @@ __device__ __forceinline__ uint4 activate(const int (&v)[32]) {
     return make_uint4(out[0], out[1], out[2], out[3]);
 }
 
+/* 32 int16 values <-> 4 uint4 (the slot / register-resident form: q[0..1] first half, q[2..3] second) */
 __device__ __forceinline__ void pack_acc(const int (&v)[32], uint4 (&q)[4]) {
     uint32_t w[16];
 #pragma unroll
@@ -274,6 +346,48 @@ __device__ __forceinline__ void unpack_acc(const uint4 (&q)[4], int (&v)[32]) {
     }
 }
 
+/* Seed a LaneAcc from a stored accumulator: word i of q holds elements (2i, 2i+1) in exactly the
+ * order of the device PSQ rows, so plo = word and phi = word >> 16. */
+__device__ __forceinline__ void seed_acc(LaneAcc& a, const uint4 (&q)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t w[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            a.plo[k * 4 + t] = w[t];
+            a.phi[k * 4 + t] = w[t] >> 16;
+        }
+    }
+}
+
+__device__ __forceinline__ void clear_acc(LaneAcc& a, bool psq_too) {
+    if (psq_too) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a.plo[i] = a.phi[i] = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a.ae[i] = a.ao[i] = a.se[i] = a.so[i] = 0;
+}
+
+/* Bring perspective c up to date with the lists in `ws`: rebuilt from zero, or `q` (+/- delta rows).
+ * On return q holds the new accumulator and v its 32 values. */
+__device__ __forceinline__ void advance_perspective(
+    const DeviceNet& net, const WarpScratch& ws, int c, bool rebuild, int lane, uint4 (&q)[4], int (&v)[32]) {
+    LaneAcc a;
+    clear_acc(a, rebuild);
+    if (!rebuild) seed_acc(a, q);
+    accumulate_psq(net, ws.psq[c], ws.n_psq[c], lane, a);
+    int bias_rows;
+    if (rebuild) {
+        bias_rows = accumulate_thr<kThrGroupFull>(net, ws.thr_add[c], ws.n_thr_add[c], lane, a.ae, a.ao);
+        finalize<false>(a, bias_rows, v);
+    } else {
+        accumulate_thr_delta(net, ws.thr_add[c], ws.n_thr_add[c], ws.thr_sub[c], ws.n_thr_sub[c], lane, a);
+        finalize<true>(a, 0, v);
+    }
+    pack_acc(v, q);
+}
+
 __device__ __forceinline__ void flag_error(DeviceStatus* status, int bits) { atomicOr(&status->error, bits); }
 
 /* ------------------------------------------------------------------ full refresh: boards -> activations */
@@ -287,32 +401,187 @@ ft_full_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, size_t n
     const FeatureTables& t = *net.tables;
     const size_t stride = static_cast<size_t>(gridDim.x) * kWarpsPerCta;
     for (size_t pos = static_cast<size_t>(blockIdx.x) * kWarpsPerCta + warp; pos < n; pos += stride) {
-        const Decoded d = decode_board(boards + pos, lane, ws.mailbox);
-        bool ok = d.ok;
-        if (!ok) {
-            if (lane == 0) flag_error(status, kErrBadBoard);
-        } else if (!build_full_lists(t, d, lane, ws)) {
-            ok = false;
-            if (lane == 0) flag_error(status, kErrCapacity);
-        }
-        if (!ok) {
-            if (lane == 0) bucket[pos] = 0xFF;
-            __syncwarp();
+        const Decoded d = decode_board(boards + pos, lane, ws.mailbox[0]);
+        int err = d.ok ? 0 : kErrBadBoard;
+        if (!err && build_lists(t, nullptr, d, lane, ws) < 0) err = kErrCapacity;
+        if (err) {
+            if (lane == 0) {
+                flag_error(status, err);
+                bucket[pos] = 0xFF;
+            }
             continue;
         }
         uint4* row = reinterpret_cast<uint4*>(act + pos * SP_L1_SIZE);
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
             LaneAcc a;
-            a.clear();
-            accumulate_lists(net, ws.psq[c], ws.n_psq[c], ws.thr[c], ws.n_thr[c], lane, a);
+            clear_acc(a, true);
+            accumulate_psq(net, ws.psq[c], ws.n_psq[c], lane, a);
+            const int rows = accumulate_thr<kThrGroupFull>(net, ws.thr_add[c], ws.n_thr_add[c], lane, a.ae, a.ao);
             int v[32];
-            finalize(a, ws.n_thr[c], v);
+            finalize<false>(a, rows, v);
             const int half = c == d.view.stm ? 0 : 1; /* side to move first, nnue_state.cpp:405-419 */
             row[half * 32 + lane] = activate(v);
         }
         if (lane == 0) bucket[pos] = static_cast<uint8_t>(output_bucket(d.view.occ));
-        __syncwarp();
+    }
+}
+
+/* ------------------------------------------------------------------ accumulator slots */
+
+__device__ __forceinline__ void load_slot_acc(const SlotStore& s, uint32_t slot, int c, int lane, uint4 (&q)[4]) {
+    const uint4* p = s.acc + (static_cast<size_t>(slot) * 2 + c) * 128 + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = p[32 * k];
+}
+
+__device__ __forceinline__ void store_slot_acc(const SlotStore& s, uint32_t slot, int c, int lane, const uint4 (&q)[4]) {
+    uint4* p = s.acc + (static_cast<size_t>(slot) * 2 + c) * 128 + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p[32 * k] = q[k];
+}
+
+/* dst[i] = (src ? src[i] advanced to boards[i] : rebuilt from boards[i]); optional activation output.
+ * Replaces NnueState::reset / push + applyMove<BoardObserver> + ensureUpToDate
+ * (nnue_state.cpp:539-570, 636-697). */
+__global__ void __launch_bounds__(kThreads)
+ft_slots_kernel(DeviceNet net, SlotStore slots, const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
+                const SpPackedBoard* __restrict__ boards, size_t n, uint8_t* __restrict__ act, uint8_t* __restrict__ bucket,
+                DeviceStatus* status) {
+    __shared__ WarpScratch scratch[kWarpsPerCta];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratch& ws = scratch[warp];
+    const FeatureTables& t = *net.tables;
+    const size_t stride = static_cast<size_t>(gridDim.x) * kWarpsPerCta;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * kWarpsPerCta + warp; i < n; i += stride) {
+        const uint32_t to = dst[i];
+        const uint32_t from = src ? src[i] : to;
+        int err = (to >= slots.n_slots || from >= slots.n_slots) ? kErrBadSlot : 0;
+        Decoded d{};
+        Decoded prev{};
+        int rebuild = 3;
+        if (!err) {
+            d = decode_board(boards + i, lane, ws.mailbox[0]);
+            if (!d.ok) err = kErrBadBoard;
+        }
+        if (!err && src) {
+            prev = decode_board(slots.boards + from, lane, ws.mailbox[1]);
+            if (!prev.ok) err = kErrBadBoard; /* the source slot was never filled */
+        }
+        if (!err) {
+            rebuild = build_lists(t, src ? &prev.view : nullptr, d, lane, ws);
+            if (rebuild < 0) err = kErrCapacity;
+        }
+        if (err) {
+            if (lane == 0) {
+                flag_error(status, err);
+                if (bucket) bucket[i] = 0xFF;
+            }
+            continue;
+        }
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            const bool fresh = (rebuild >> c) & 1;
+            uint4 q[4];
+            if (!fresh) load_slot_acc(slots, from, c, lane, q);
+            int v[32];
+            advance_perspective(net, ws, c, fresh, lane, q, v);
+            store_slot_acc(slots, to, c, lane, q);
+            if (act) {
+                const int half = c == d.view.stm ? 0 : 1;
+                reinterpret_cast<uint4*>(act + i * SP_L1_SIZE)[half * 32 + lane] = activate(v);
+            }
+        }
+        if (lane < 2) reinterpret_cast<uint4*>(slots.boards + to)[lane] = __ldg(reinterpret_cast<const uint4*>(boards + i) + lane);
+        if (act && lane == 0) bucket[i] = static_cast<uint8_t>(output_bucket(d.view.occ));
+    }
+}
+
+/* slots -> activations for an explicit side to move (NnueState::evaluate, nnue_state.cpp:598-610) */
+__global__ void __launch_bounds__(kThreads)
+slot_activate_kernel(SlotStore slots, const uint32_t* __restrict__ ids, const uint8_t* __restrict__ stm, size_t n,
+                     uint8_t* __restrict__ act, uint8_t* __restrict__ bucket, DeviceStatus* status) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t stride = static_cast<size_t>(gridDim.x) * kWarpsPerCta;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * kWarpsPerCta + warp; i < n; i += stride) {
+        const uint32_t slot = ids[i];
+        if (slot >= slots.n_slots) {
+            if (lane == 0) {
+                flag_error(status, kErrBadSlot);
+                bucket[i] = 0xFF;
+            }
+            continue;
+        }
+        const uint4* rec = reinterpret_cast<const uint4*>(slots.boards + slot);
+        const uint4 lo = rec[0], hi = rec[1];
+        const uint64_t occ = static_cast<uint64_t>(lo.y) << 32 | lo.x;
+        const int n_pieces = __popcll(occ);
+        if (n_pieces < 2 || n_pieces > 32) {
+            if (lane == 0) {
+                flag_error(status, kErrBadBoard);
+                bucket[i] = 0xFF;
+            }
+            continue;
+        }
+        const int side = stm ? (stm[i] & 1) : ((hi.z & 0x80) ? kBlack : kWhite);
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint4 q[4];
+            load_slot_acc(slots, slot, c, lane, q);
+            int v[32];
+            unpack_acc(q, v);
+            const int half = c == side ? 0 : 1;
+            reinterpret_cast<uint4*>(act + i * SP_L1_SIZE)[half * 32 + lane] = activate(v);
+        }
+        if (lane == 0) bucket[i] = static_cast<uint8_t>(output_bucket(occ));
+    }
+}
+
+/* ------------------------------------------------------------------ playout walker */
+
+/* One warp plays through one game: both accumulators stay in registers from ply to ply
+ * (datagen form, src/datagen/datagen.cpp:257-262: applyMove + applyImmediately + evaluate). */
+__global__ void __launch_bounds__(kThreads)
+ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const uint32_t* __restrict__ game_start,
+                uint32_t n_games, uint8_t* __restrict__ act, uint8_t* __restrict__ bucket, DeviceStatus* status) {
+    __shared__ WarpScratch scratch[kWarpsPerCta];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratch& ws = scratch[warp];
+    const FeatureTables& t = *net.tables;
+    const uint32_t stride = gridDim.x * kWarpsPerCta;
+    for (uint32_t g = blockIdx.x * kWarpsPerCta + warp; g < n_games; g += stride) {
+        const size_t first = game_start[g], last = game_start[g + 1];
+        uint4 q[2][4];
+        BoardView prev{};
+        bool have_prev = false;
+        for (size_t pos = first; pos < last; ++pos) {
+            const int buf = static_cast<int>(pos - first) & 1;
+            const Decoded d = decode_board(boards + pos, lane, ws.mailbox[buf]);
+            int err = d.ok ? 0 : kErrBadBoard;
+            int rebuild = 3;
+            if (!err) {
+                rebuild = build_lists(t, have_prev ? &prev : nullptr, d, lane, ws);
+                if (rebuild < 0) err = kErrCapacity;
+            }
+            if (err) {
+                if (lane == 0) {
+                    flag_error(status, err);
+                    bucket[pos] = 0xFF;
+                }
+                have_prev = false; /* the next good board restarts the chain */
+                continue;
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                int v[32];
+                advance_perspective(net, ws, c, (rebuild >> c) & 1, lane, q[c], v);
+                const int half = c == d.view.stm ? 0 : 1;
+                reinterpret_cast<uint4*>(act + pos * SP_L1_SIZE)[half * 32 + lane] = activate(v);
+            }
+            if (lane == 0) bucket[pos] = static_cast<uint8_t>(output_bucket(d.view.occ));
+            prev = d.view;
+            have_prev = true;
+        }
     }
 }
 
@@ -466,6 +735,27 @@ void launch_ft_full(
     int sm_count, cudaStream_t stream) {
     if (!n) return;
     ft_full_kernel<<<grid_for(n, kWarpsPerCta, sm_count, 2), kThreads, 0, stream>>>(net, boards, n, act, bucket, status);
+}
+
+void launch_ft_slots(
+    const DeviceNet& net, SlotStore slots, const uint32_t* src, const uint32_t* dst, const SpPackedBoard* boards,
+    size_t n, uint8_t* act, uint8_t* bucket, DeviceStatus* status, int sm_count, cudaStream_t stream) {
+    if (!n) return;
+    ft_slots_kernel<<<grid_for(n, kWarpsPerCta, sm_count, 2), kThreads, 0, stream>>>(net, slots, src, dst, boards, n, act, bucket, status);
+}
+
+void launch_ft_games(
+    const DeviceNet& net, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, uint8_t* act,
+    uint8_t* bucket, DeviceStatus* status, int sm_count, cudaStream_t stream) {
+    if (!n_games) return;
+    ft_games_kernel<<<grid_for(n_games, kWarpsPerCta, sm_count, 2), kThreads, 0, stream>>>(net, boards, game_start, n_games, act, bucket, status);
+}
+
+void launch_slot_activate(
+    SlotStore slots, const uint32_t* slot_ids, const uint8_t* stm, size_t n, uint8_t* act, uint8_t* bucket,
+    DeviceStatus* status, int sm_count, cudaStream_t stream) {
+    if (!n) return;
+    slot_activate_kernel<<<grid_for(n, kWarpsPerCta, sm_count, 4), kThreads, 0, stream>>>(slots, slot_ids, stm, n, act, bucket, status);
 }
 
 void launch_head(

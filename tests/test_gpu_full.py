@@ -1,0 +1,158 @@
+"""GPU parity, full-refresh path (BASELINE.json config 2): every call goes through the C-ABI.
+
+Bar: bit-exact.  Checked against (i) golden vectors produced by the reference's own code and
+(ii) the pinned C oracle on seeded inputs, plus size-independent properties at the full 1M size.
+"""
+import numpy as np
+import pytest
+
+from stormphrax_b200 import api
+from stormphrax_b200 import net as N
+
+pytestmark = pytest.mark.gpu
+
+INT32_MIN = np.iinfo(np.int32).min
+
+
+def _dev(a: np.ndarray):
+    import torch
+
+    _stream()
+    t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
+    torch.cuda.synchronize()
+    return t
+
+
+_STREAM = None
+
+
+def _stream() -> int:
+    """A non-default torch stream (the library maps a NULL stream to the context's own)."""
+    import torch
+
+    global _STREAM
+    if _STREAM is None:
+        _STREAM = torch.cuda.Stream()
+        torch.cuda.set_stream(_STREAM)
+    return _STREAM.cuda_stream
+
+
+def test_golden_playouts_bit_exact(gpu_ctx, golden):
+    assert (gpu_ctx.eval_full(golden["boards"]) == golden["evals"]).all()
+
+
+def test_golden_dfrc_and_special_fens_bit_exact(gpu_ctx, golden):
+    assert (gpu_ctx.eval_full(golden["dfrc_boards"]) == golden["dfrc_evals"]).all()
+    assert (gpu_ctx.eval_full(golden["fen_boards"]) == golden["fen_evals"]).all()
+
+
+def test_stress_network_bit_exact(golden):
+    """Full-range weights: every int16 / int32 wrap-around path is taken."""
+    import os
+
+    stress = np.load(os.path.join(os.path.dirname(__file__), "golden", "stress_seed99.npz"))
+    with api.Nnue(N.synthetic(99, stress=True).image, 0) as ctx:
+        assert (ctx.eval_full(golden["boards"]) == stress["evals"]).all()
+        assert (ctx.eval_full(golden["fen_boards"]) == stress["fen_evals"]).all()
+
+
+def test_ft_activations_match_oracle(gpu_ctx, c_oracle, small_playouts):
+    import torch
+
+    boards = small_playouts[0][::9]
+    n = len(boards)
+    d_boards = _dev(boards)
+    d_act = torch.empty(n * 1024, dtype=torch.uint8, device="cuda")
+    d_bucket = torch.empty(n, dtype=torch.uint8, device="cuda")
+    s = _stream()
+    gpu_ctx.activations_device(d_boards, n, d_act, d_bucket, s)
+    gpu_ctx.sync(s)
+    act = d_act.cpu().numpy().reshape(n, 1024)
+    bucket = d_bucket.cpu().numpy()
+    for i in range(n):
+        want, b = c_oracle.ft_activations(boards[i])
+        assert bucket[i] == b
+        assert (act[i] == want).all(), i
+
+
+def test_dense_head_matches_oracle_on_arbitrary_activations(gpu_ctx, c_oracle):
+    """Config 4's isolated head: full u8 range (the FT only produces 0..127), all buckets, ragged n."""
+    import torch
+
+    rng = np.random.default_rng(3)
+    for n in (1, 15, 16, 17, 333):
+        act = rng.integers(0, 256, (n, 1024), dtype=np.uint8)
+        act[0] = 0
+        if n > 1:
+            act[1] = 255
+        bucket = rng.integers(0, 8, n, dtype=np.uint8)
+        d_out = torch.empty(n, dtype=torch.int32, device="cuda")
+        s = _stream()
+        gpu_ctx.forward_device(_dev(act), _dev(bucket), n, d_out, s)
+        gpu_ctx.sync(s)
+        got = d_out.cpu().numpy()
+        want = np.array([c_oracle.forward(act[i], int(bucket[i])) for i in range(n)], dtype=np.int32)
+        assert (got == want).all(), n
+
+
+def test_matches_oracle_on_seeded_playouts(gpu_ctx, c_oracle, small_playouts):
+    boards = small_playouts[0]
+    assert (gpu_ctx.eval_full(boards) == c_oracle.eval_once(boards)).all()
+
+
+def test_empty_and_ragged_batches(gpu_ctx, golden):
+    assert gpu_ctx.eval_full(golden["boards"][:0]).size == 0
+    for n in (1, 2, 7, 16, 17, 31, 33, 257):
+        assert (gpu_ctx.eval_full(golden["boards"][:n]) == golden["evals"][:n]).all(), n
+
+
+def test_malformed_boards_are_reported_not_evaluated(gpu_ctx, golden):
+    boards = golden["boards"][:40].copy()
+    boards["occupancy"][5] = 0  # no kings at all
+    boards["pieces"][9] = 0x77  # piece code 7 does not exist
+    out = np.zeros(40, dtype=np.int32)
+    with pytest.raises(api.NnueError) as e:
+        gpu_ctx.eval_full(boards, out)
+    assert e.value.status == api.SP_ERR_BAD_BOARD
+    good = np.ones(40, dtype=bool)
+    good[[5, 9]] = False
+    assert (out[good] == golden["evals"][:40][good]).all()
+    assert (out[~good] == INT32_MIN).all()
+    # the context stays usable and the error does not stick
+    assert (gpu_ctx.eval_full(golden["boards"][:40]) == golden["evals"][:40]).all()
+
+
+def test_device_pointer_entry_point(gpu_ctx, golden):
+    import torch
+
+    boards = golden["boards"]
+    d_out = torch.empty(len(boards), dtype=torch.int32, device="cuda")
+    s = _stream()
+    gpu_ctx.eval_full_device(_dev(boards), len(boards), d_out, s)
+    gpu_ctx.sync(s)
+    assert (d_out.cpu().numpy() == golden["evals"]).all()
+
+
+def test_counters(net, golden):
+    with api.Nnue(net.image, 0) as ctx:
+        ctx.eval_full(golden["boards"][:100])
+        c = ctx.counters()
+        assert c[api.CTR_EVALS] == 100 and c[api.CTR_FULL_REFRESH] == 200 and c[api.CTR_LAUNCHES] >= 2
+
+
+def test_full_size_properties(gpu_ctx, c_oracle):
+    """BASELINE config 2 size (1,048,576 positions): permutation equivariance, duplicate
+    consistency, and a random sample against the oracle."""
+    boards, _, _ = api.playouts(42, 13200, 80)
+    assert len(boards) >= 1 << 20
+    boards = boards[: 1 << 20]
+    out = gpu_ctx.eval_full(boards)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(len(boards))
+    assert (gpu_ctx.eval_full(boards[perm]) == out[perm]).all()
+    sample = rng.choice(len(boards), 3000, replace=False)
+    assert (c_oracle.eval_once(boards[sample]) == out[sample]).all()
+    # identical records evaluate identically wherever they sit in the batch
+    start = boards[0].tobytes()
+    same = np.array([b.tobytes() == start for b in boards[:: 81][:200]])
+    assert same.sum() > 1 and len(set(out[::81][:200][same].tolist())) == 1

@@ -1,0 +1,128 @@
+"""GPU parity, incremental path (BASELINE.json config 3): accumulator slots and playout streams.
+
+The reference's own invariant is `evaluate after any push/pop/apply sequence == evaluateOnce`
+(src/datagen/datagen.cpp:262); golden `evals` are evaluateOnce results which the reference's
+incremental code was checked against when the fixtures were generated (make_golden.py).
+"""
+import numpy as np
+import pytest
+
+from stormphrax_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+INT32_MIN = np.iinfo(np.int32).min
+
+
+def test_playout_walker_matches_golden(gpu_ctx, golden):
+    assert (gpu_ctx.eval_playouts(golden["boards"], golden["starts"]) == golden["evals"]).all()
+
+
+def test_playout_walker_dfrc_castling(gpu_ctx, golden):
+    """Chess960 castling moves king and rook at once, sometimes onto each other's squares."""
+    assert (gpu_ctx.eval_playouts(golden["dfrc_boards"], golden["dfrc_starts"]) == golden["dfrc_evals"]).all()
+
+
+def test_playout_walker_stress_network(golden):
+    import os
+
+    from stormphrax_b200 import net as N
+
+    stress = np.load(os.path.join(os.path.dirname(__file__), "golden", "stress_seed99.npz"))
+    with api.Nnue(N.synthetic(99, stress=True).image, 0) as ctx:
+        assert (ctx.eval_playouts(golden["boards"], golden["starts"]) == stress["evals"]).all()
+
+
+def test_playout_walker_ragged_games(gpu_ctx, golden):
+    """Empty games, single-board games and games cut mid-way."""
+    boards, evals = golden["boards"], golden["evals"]
+    starts = np.array([0, 0, 1, 1, 30, 81, 81, 100], dtype=np.uint32)
+    # a cut game is still a legal chain as long as consecutive boards follow from each other
+    out = gpu_ctx.eval_playouts(boards[:100], starts)
+    assert (out == evals[:100]).all()
+
+
+def test_walker_jump_between_unrelated_boards_falls_back_to_rebuild(gpu_ctx, golden):
+    """A 'game' whose consecutive boards are unrelated (> 8 changed squares, or any king jump)."""
+    idx = np.array([0, 500, 37, 2100, 36, 1200, 1201, 5, 3000], dtype=np.int64)
+    boards = golden["boards"][idx]
+    out = gpu_ctx.eval_playouts(boards, np.array([0, len(idx)], dtype=np.uint32))
+    assert (out == golden["evals"][idx]).all()
+
+
+def test_slots_refresh_update_eval(gpu_ctx, golden):
+    boards, starts, evals = golden["boards"], golden["starts"], golden["evals"]
+    n_games = len(starts) - 1
+    gpu_ctx.slots_reserve(2 * n_games)
+    slots = np.arange(n_games, dtype=np.uint32)
+    gpu_ctx.refresh(slots, boards[starts[:-1]])
+    assert (gpu_ctx.eval_slots(slots) == evals[starts[:-1]]).all()
+    lengths = np.diff(starts)
+    for ply in range(1, int(lengths.max())):
+        live = np.nonzero(lengths > ply)[0]
+        idx = starts[:-1][live] + ply
+        # in-place update (datagen's applyImmediately form) fused with evaluation
+        out = gpu_ctx.update_eval(slots[live], slots[live], boards[idx])
+        assert (out == evals[idx]).all(), ply
+
+
+def test_slots_push_pop_semantics(gpu_ctx, golden):
+    """Search form: children are written to fresh slots, the parent slot stays valid (pop = reuse it)."""
+    boards, starts, evals = golden["boards"], golden["starts"], golden["evals"]
+    g = 3
+    lo = int(starts[g])
+    gpu_ctx.slots_reserve(64)
+    gpu_ctx.refresh([0], boards[lo : lo + 1])
+    # parent -> three different descendants in three slots, one call
+    out = gpu_ctx.update_eval([0, 0, 0], [1, 2, 3], boards[[lo + 1, lo + 1, lo + 1]])
+    assert (out == evals[lo + 1]).all()
+    gpu_ctx.update([1], [4], boards[lo + 2 : lo + 3])
+    assert gpu_ctx.eval_slots([4, 0, 1])[0] == evals[lo + 2]
+    assert (gpu_ctx.eval_slots([0, 1]) == evals[[lo, lo + 1]]).all()  # parents untouched
+    # explicit side to move (null-move children are evaluated on the parent's accumulators)
+    stm_board = 0 if boards[lo]["stm_ep"] & 0x80 else 1
+    flipped = gpu_ctx.eval_slots([0], stm=[1 - stm_board])
+    same = gpu_ctx.eval_slots([0], stm=[stm_board])
+    assert same[0] == evals[lo] and flipped[0] != INT32_MIN
+
+
+def test_flipped_stm_matches_oracle(gpu_ctx, c_oracle, golden):
+    board = golden["boards"][40:41].copy()
+    gpu_ctx.slots_reserve(8)
+    gpu_ctx.refresh([5], board)
+    psq, thr = c_oracle.accumulators(board)
+    bucket = (bin(int(board["occupancy"][0])).count("1") - 2) // 4
+    for stm in (0, 1):
+        assert gpu_ctx.eval_slots([5], stm=[stm])[0] == c_oracle.forward_acc(psq, thr, stm, bucket)
+
+
+def test_read_slot_returns_logical_accumulators(gpu_ctx, c_oracle, golden):
+    board = golden["boards"][123:124]
+    gpu_ctx.slots_reserve(8)
+    gpu_ctx.refresh([7], board)
+    acc, stored = gpu_ctx.read_slot(7)
+    psq, thr = c_oracle.accumulators(board)
+    want = (psq.astype(np.int32) + thr.astype(np.int32)).astype(np.int16)  # only the wrapped sum reaches the net
+    assert (acc == want).all()
+    assert stored.tobytes() == board.tobytes()
+
+
+def test_slot_errors(gpu_ctx, golden):
+    gpu_ctx.slots_reserve(8)
+    with pytest.raises(api.NnueError) as e:
+        gpu_ctx.refresh([1 << 20], golden["boards"][:1])
+    assert e.value.status == api.SP_ERR_INVALID
+    with pytest.raises(api.NnueError) as e:
+        # updating from a slot that was never filled is a malformed-board error, not garbage
+        gpu_ctx.slots_reserve(4096)
+        gpu_ctx.update([4095], [4094], golden["boards"][:1])
+    assert e.value.status == api.SP_ERR_BAD_BOARD
+
+
+def test_full_size_playouts_equal_full_refresh(gpu_ctx):
+    """Config 3 size: 65,536 games.  Property: the incremental walker equals the from-scratch
+    evaluator on every position (the reference's datagen assertion, at scale)."""
+    boards, _, starts = api.playouts(4242, 65536, 80)
+    full = gpu_ctx.eval_full(boards)
+    inc = gpu_ctx.eval_playouts(boards, starts)
+    assert (full == inc).all()
