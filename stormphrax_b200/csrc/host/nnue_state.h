@@ -1,0 +1,163 @@
+/*
+ * nnue_state.h -- host-side mirror of the reference's eval API, implemented over the C-ABI
+ * (include/sp_nnue.h).  Same names, argument meaning and call protocol as
+ *   eval::init / shutdown / isNetworkLoaded / getNetwork        src/eval/nnue.h:38-45
+ *   eval::NnueState::{reset,push,pop,applyImmediately,evaluate,evaluateOnce}
+ *                                                               src/eval/nnue_state.h:85-116
+ *   eval::BoardObserver / UpdateContext                         src/eval/nnue_state.h:28-45
+ *   eval::staticEval / staticEvalOnce / adjustStatic            src/eval/eval.{h,cpp}
+ * so that search / datagen code written against the reference compiles against this header
+ * with `Position` being anything that offers `SpPackedBoard pack() const` and `stm()`.
+ *
+ * What differs underneath: the accumulator stack lives in device memory (one slot per stack
+ * level), and the observer records nothing -- the GPU derives add/sub feature lists from the
+ * (stored predecessor board, new board) pair, however many plies apart they are
+ * (csrc/sp_delta.h).  Laziness is preserved: push() is O(1) and touches no device memory;
+ * work happens in evaluate(), from the nearest up-to-date ancestor (nnue_state.cpp:636-697).
+ *
+ * One NnueState per host thread, like the reference (thread.h:147).  For throughput, many
+ * states share one EvalBatch: evaluateAsync() queues, flush() runs ONE device batch.
+ */
+#ifndef SP_HOST_NNUE_STATE_H
+#define SP_HOST_NNUE_STATE_H
+
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../../include/sp_nnue.h"
+#include "position.h"
+
+namespace sp::host::eval {
+
+using i32 = int32_t;
+using Color = int;
+
+constexpr i32 kScoreWin = 25000; /* src/core.h:708 */
+
+/* ---- lifecycle (src/eval/nnue.cpp:200-321).  One network copy per GPU instead of per NUMA node. */
+bool init(const void* networkImage, size_t len, int device = 0);
+bool initFromFile(const std::string& path, int device = 0);
+void shutdown();
+[[nodiscard]] bool isNetworkLoaded();
+[[nodiscard]] SpNnue* getNetwork(int device = -1); /* -1: the device passed to init */
+[[nodiscard]] const char* lastError();
+
+/* The reference's UpdateContext carries the add/sub lists the observer collected
+ * (nnue_state.h:28-31).  Here the device derives them from boards, so it is empty. */
+struct UpdateContext {};
+
+/* Same callback surface as eval::BoardObserver (nnue_state.h:33-45); every callback is a no-op. */
+struct BoardObserver {
+    UpdateContext& ctx;
+    void prepareKingMove(Color, Square, Square) {}
+    template <typename P> void pieceAdded(const P&, Piece, Square) {}
+    template <typename P> void pieceRemoved(const P&, Piece, Square) {}
+    template <typename P> void pieceMutated(const P&, Piece, Piece, Square) {}
+    template <typename P> void pieceMoved(const P&, Piece, Square, Square) {}
+    template <typename P> void piecePromoted(const P&, Piece, Square, Piece, Square) {}
+    template <typename P> void finalize(const P&, const P&) {}
+};
+
+class NnueState;
+
+/* Collects evaluations from many NnueStates (many concurrent games / search threads) and runs
+ * them as one device batch.  enqueue is mutex-protected (MPSC), flush is called by one thread. */
+class EvalBatch {
+public:
+    static constexpr uint32_t kNoUpdate = 0xFFFFFFFFu; /* srcSlot value: dstSlot is already up to date */
+
+    explicit EvalBatch(SpNnue* network) : m_network{network} {}
+
+    /* result is written to *out by flush().  A state may have ONE evaluation pending per flush. */
+    void enqueue(uint32_t srcSlot, uint32_t dstSlot, bool rebuild, const SpPackedBoard& board, Color stm, i32* out);
+    [[nodiscard]] size_t pending() const { return m_out.size(); }
+    /* Runs everything queued; returns an SpStatus. */
+    int flush();
+
+private:
+    SpNnue* m_network;
+    std::mutex m_mutex;
+    std::vector<uint32_t> m_src, m_dst, m_refreshSlots;
+    std::vector<SpPackedBoard> m_boards, m_refreshBoards;
+    std::vector<uint8_t> m_stm;
+    std::vector<i32*> m_out;
+    std::vector<uint32_t> m_evalSlots;
+    std::vector<i32> m_results;
+};
+
+class NnueState {
+public:
+    static constexpr uint32_t kStackDepth = 256; /* nnue_state.h:88 */
+
+    /* Slots [slotBase, slotBase + kStackDepth) of `network` belong to this state. */
+    NnueState() = default;
+    explicit NnueState(SpNnue* network, uint32_t slotBase = 0) { setNetwork(network, slotBase); }
+
+    void setNetwork(SpNnue* network, uint32_t slotBase = 0);
+
+    template <typename Position> void reset(const Position& pos) { resetPacked(pos.pack()); }
+
+    BoardObserver push(); /* O(1): bumps the stack pointer and marks the level dirty */
+    void pop();
+
+    /* datagen form (datagen.cpp:257-260): the current level itself moves on to `pos` */
+    template <typename Position> void applyImmediately(const UpdateContext&, const Position& pos) {
+        applyPacked(pos.pack());
+    }
+
+    template <typename Position> [[nodiscard]] i32 evaluate(const Position& pos, Color stm) {
+        return evaluatePacked(pos.pack(), stm);
+    }
+    /* queue instead of running: the result lands in *out when batch.flush() is called */
+    template <typename Position> void evaluateAsync(EvalBatch& batch, const Position& pos, Color stm, i32* out) {
+        evaluateAsyncPacked(batch, pos.pack(), stm, out);
+    }
+
+    template <typename Position> [[nodiscard]] static i32 evaluateOnce(const Position& pos, Color stm) {
+        return evaluateOncePacked(pos.pack(), stm);
+    }
+
+    void resetPacked(const SpPackedBoard& board);
+    void applyPacked(const SpPackedBoard& board);
+    [[nodiscard]] i32 evaluatePacked(const SpPackedBoard& board, Color stm);
+    void evaluateAsyncPacked(EvalBatch& batch, const SpPackedBoard& board, Color stm, i32* out);
+    [[nodiscard]] static i32 evaluateOncePacked(const SpPackedBoard& board, Color stm);
+
+    [[nodiscard]] uint32_t depth() const { return m_top; }
+
+private:
+    [[nodiscard]] uint32_t slot(uint32_t level) const { return m_slotBase + level; }
+    /* nearest level <= m_top whose slot is up to date, or -1 */
+    [[nodiscard]] int cleanAncestor() const;
+
+    SpNnue* m_network{nullptr};
+    uint32_t m_slotBase{0};
+    uint32_t m_top{0};
+    UpdateContext m_ctx{};
+    std::vector<uint8_t> m_clean = std::vector<uint8_t>(kStackDepth, 0);
+};
+
+/* ---- eval.h wrappers (src/eval/eval.cpp:25-28, 74-77, 109-112) */
+struct Contempt {
+    i32 value[2]{0, 0};
+    i32 operator[](Color c) const { return value[c]; }
+};
+
+inline i32 adjustStatic(i32 eval, Color stm, const Contempt& contempt) {
+    eval += contempt[stm];
+    return eval < -kScoreWin + 1 ? -kScoreWin + 1 : (eval > kScoreWin - 1 ? kScoreWin - 1 : eval);
+}
+
+template <typename Position> i32 staticEval(const Position& pos, NnueState& state, const Contempt& contempt = {}) {
+    return adjustStatic(state.evaluate(pos, pos.stm()), pos.stm(), contempt);
+}
+
+template <typename Position> i32 staticEvalOnce(const Position& pos, const Contempt& contempt = {}) {
+    return adjustStatic(NnueState::evaluateOnce(pos, pos.stm()), pos.stm(), contempt);
+}
+
+} // namespace sp::host::eval
+
+#endif
