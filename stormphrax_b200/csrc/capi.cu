@@ -130,7 +130,7 @@ void build_device_image(const uint8_t* payload, const NetLayout& L, uint8_t* img
     auto permute_row = [&](const int16_t* src, int16_t* dst) {
         for (int k = 0; k < 4; ++k)
             for (int lane = 0; lane < 32; ++lane)
-                std::memcpy(dst + (k * 32 + lane) * 8, src + lane_order_element(k, lane, 0), 16);
+                for (int e = 0; e < 8; ++e) dst[(k * 32 + lane) * 8 + e] = src[lane_order_element(k, lane, e)];
     };
     for (int r = 0; r < SP_PSQ_FEATURES; ++r) permute_row(psq_w + size_t(r) * SP_L1_SIZE, psq + size_t(r) * SP_L1_SIZE);
     permute_row(ft_b, psq + size_t{kPsqBiasRow} * SP_L1_SIZE);

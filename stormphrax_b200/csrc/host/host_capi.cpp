@@ -242,7 +242,8 @@ int sp_host_feature_delta(
             if (sign > 0) thr_add[(*n_thr_add)++] = idx; else thr_sub[(*n_thr_sub)++] = idx;
         }
     };
-    for (int item = 0; item < kDeltaItems; ++item) delta_item(tables(), bb, ba, changed, item, emit);
+    if (popcount64(changed) > kMaxChanged) return 1;
+    delta_all(tables(), bb, ba, changed, emit);
     return 0;
 }
 

@@ -26,23 +26,26 @@ namespace {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kPsqGroup = 4;      /* PSQ rows fetched per batch of loads (16 x LDG.128 in flight per lane) */
-constexpr int kThrGroupFull = 8;  /* threat rows per batch on the rebuild path (16 x LDG.128 in flight) */
-constexpr int kThrGroupDelta = 4; /* per sign on the incremental path (4 adds + 4 subs = 16 x LDG.128) */
-constexpr int kPsqListCap = 40;   /* 32 pieces + bias row */
+constexpr int kPsqGroup = 4;       /* PSQ rows fetched per batch on the rebuild path (16 x LDG.128 in flight per lane) */
+constexpr int kThrGroupFull = 8;   /* threat rows per batch on the rebuild path (16 x LDG.128) */
+constexpr int kPsqGroupDelta = 2;  /* per sign on the incremental path (2 adds + 2 subs = 16 x LDG.128) */
+constexpr int kThrGroupDelta = 4;  /* per sign on the incremental path (4 adds + 4 subs = 16 x LDG.128) */
+constexpr int kPsqListCap = 40;    /* 32 pieces + bias row */
+constexpr int kPsqDeltaCap = 16;
 constexpr int kThrListCap = SP_MAX_THREAT_INDICES;
-constexpr uint32_t kSubFlag = 0x8000u; /* PSQ list entries: bit 15 = subtract this row */
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 /* Per-warp shared memory. */
 struct WarpScratch {
     uint16_t thr_add[2][kThrListCap];
     uint16_t thr_sub[2][kThrListCap];
-    uint16_t psq[2][kPsqListCap];
+    uint16_t psq_add[2][kPsqListCap];
+    uint16_t psq_sub[2][kPsqDeltaCap];
     uint8_t mailbox[2][64]; /* two boards: the one being evaluated and its predecessor */
     int n_thr_add[2];
     int n_thr_sub[2];
-    int n_psq[2];
+    int n_psq_add[2];
+    int n_psq_sub[2];
 };
 
 /* Board as the shared feature code (sp_features.h, sp_delta.h) wants to see it. */
@@ -77,9 +80,7 @@ __device__ __forceinline__ uint64_t warp_or64(uint64_t v) {
 
 /* Decode one marlinformat record (src/datagen/marlinformat.h:43-77) cooperatively.
  * The mailbox is written to shared memory; everything else stays in registers. */
-__device__ __forceinline__ Decoded decode_board(const SpPackedBoard* board, int lane, uint8_t* mailbox) {
-    const uint4* p = reinterpret_cast<const uint4*>(board);
-    const uint4 lo = __ldg(p), hi = __ldg(p + 1);
+__device__ __forceinline__ Decoded decode_board(uint4 lo, uint4 hi, int lane, uint8_t* mailbox) {
     Decoded d;
     d.view.mailbox = mailbox;
     d.view.occ = static_cast<uint64_t>(lo.y) << 32 | lo.x;
@@ -116,17 +117,22 @@ __device__ __forceinline__ Decoded decode_board(const SpPackedBoard* board, int 
     return d;
 }
 
-__device__ __forceinline__ void push(uint16_t* list, int* count, uint32_t value) {
+__device__ __forceinline__ Decoded decode_board(const SpPackedBoard* board, int lane, uint8_t* mailbox) {
+    const uint4* p = reinterpret_cast<const uint4*>(board);
+    return decode_board(__ldg(p), __ldg(p + 1), lane, mailbox);
+}
+
+__device__ __forceinline__ void push(uint16_t* list, int* count, int cap, uint32_t value) {
     const int at = atomicAdd(count, 1);
-    if (at < kThrListCap) list[at] = static_cast<uint16_t>(value);
+    if (at < cap) list[at] = static_cast<uint16_t>(value);
 }
 
 /*
  * Fill the warp's feature lists for the step `before` -> `d` (before == nullptr: no predecessor).
- *   perspectives in the returned mask are rebuilt from scratch: psq list = all pieces + bias row,
+ *   perspectives in the returned mask are rebuilt from scratch: psq_add = all pieces + bias row,
  *     thr_add = every threat / pawn-pair feature of the board (nnue_state.cpp:309-354, 440-449)
- *   the others are updated: psq list = signed delta rows, thr_add / thr_sub = delta rows (sp_delta.h;
- *     replaces nnue.cpp:490-599, nnue_state.cpp:163-307)
+ *   the others are updated: psq_add / psq_sub / thr_add / thr_sub = delta rows (sp_delta.h;
+ *     replaces nnue.cpp:490-599, nnue_state.cpp:34-87, 163-307)
  * A perspective is rebuilt when its king changes input bucket or board half (psq.h:264-283,
  * nnue_state.h:118-128), when more than kMaxChanged squares differ, or when a delta list overflows.
  * Returns -1 if a full list exceeds the reference's bound of 256 entries.
@@ -143,35 +149,49 @@ __device__ __forceinline__ int build_lists(
         if (__popcll(changed) > kMaxChanged) rebuild = 3;
     }
     for (;;) {
-        if (lane < 2) ws.n_thr_add[lane] = ws.n_thr_sub[lane] = ws.n_psq[lane] = 0;
+        if (lane < 2) ws.n_thr_add[lane] = ws.n_thr_sub[lane] = ws.n_psq_add[lane] = ws.n_psq_sub[lane] = 0;
         __syncwarp();
         if (rebuild != 3) {
-            const int n_items = __popcll(changed) * 2 * kItemsPerSquareBoard;
-            for (int item = lane; item < n_items; item += 32) {
-                delta_item(t, *before, d.view, changed, item, [&](int c, int kind, int sign, uint32_t idx) {
-                    if ((rebuild >> c) & 1) return;
-                    if (kind == 0) push(ws.psq[c], &ws.n_psq[c], sign > 0 ? idx : idx | kSubFlag);
-                    else if (sign > 0) push(ws.thr_add[c], &ws.n_thr_add[c], idx);
-                    else push(ws.thr_sub[c], &ws.n_thr_sub[c], idx);
-                });
+            auto emit = [&](int c, int kind, int sign, uint32_t idx) {
+                if ((rebuild >> c) & 1) return;
+                if (kind == 0) {
+                    if (sign > 0) push(ws.psq_add[c], &ws.n_psq_add[c], kPsqDeltaCap, idx);
+                    else push(ws.psq_sub[c], &ws.n_psq_sub[c], kPsqDeltaCap, idx);
+                } else if (sign > 0) {
+                    push(ws.thr_add[c], &ws.n_thr_add[c], kThrListCap, idx);
+                } else {
+                    push(ws.thr_sub[c], &ws.n_thr_sub[c], kThrListCap, idx);
+                }
+            };
+            /* line items: lane = unit * 8 + k, uniform code in every lane */
+            const int units = 2 * __popcll(changed);
+            for (int item = lane; item < units * kLineItemsPerUnit; item += 32) {
+                const int u = item >> 3;
+                delta_line_item(t, (u & 1) ? d.view : *before, (u & 1) ? 1 : -1, changed, unit_square(changed, u), item & 7, emit);
             }
+            if (lane < units)
+                delta_square_item(t, (lane & 1) ? d.view : *before, (lane & 1) ? 1 : -1, changed, unit_square(changed, lane), emit);
         }
         if (rebuild && d.piece != kNoPiece) {
-            if (rebuild & 1) ws.psq[kBlack][lane] = static_cast<uint16_t>(psq_index(t, kBlack, d.piece, d.sq, d.view.king[kBlack]));
-            if (rebuild & 2) ws.psq[kWhite][lane] = static_cast<uint16_t>(psq_index(t, kWhite, d.piece, d.sq, d.view.king[kWhite]));
+            if (rebuild & 1) ws.psq_add[kBlack][lane] = static_cast<uint16_t>(psq_index(t, kBlack, d.piece, d.sq, d.view.king[kBlack]));
+            if (rebuild & 2) ws.psq_add[kWhite][lane] = static_cast<uint16_t>(psq_index(t, kWhite, d.piece, d.sq, d.view.king[kWhite]));
             square_threat_features(t, d.view, d.sq, [&](int c, uint32_t idx) {
-                if ((rebuild >> c) & 1) push(ws.thr_add[c], &ws.n_thr_add[c], idx);
+                if ((rebuild >> c) & 1) push(ws.thr_add[c], &ws.n_thr_add[c], kThrListCap, idx);
             });
         }
         __syncwarp();
         if (lane < 2 && ((rebuild >> lane) & 1)) {
-            ws.psq[lane][d.n_pieces] = kPsqBiasRow;
-            ws.n_psq[lane] = d.n_pieces + 1;
+            ws.psq_add[lane][d.n_pieces] = kPsqBiasRow;
+            ws.n_psq_add[lane] = d.n_pieces + 1;
         }
         __syncwarp();
         int overflow = 0;
-        for (int c = 0; c < 2; ++c)
-            if (ws.n_thr_add[c] > kThrListCap || ws.n_thr_sub[c] > kThrListCap || ws.n_psq[c] > kPsqListCap) overflow |= 1 << c;
+        for (int c = 0; c < 2; ++c) {
+            const int psq_cap = ((rebuild >> c) & 1) ? kPsqListCap : kPsqDeltaCap;
+            if (ws.n_thr_add[c] > kThrListCap || ws.n_thr_sub[c] > kThrListCap || ws.n_psq_add[c] > psq_cap
+                || ws.n_psq_sub[c] > kPsqDeltaCap)
+                overflow |= 1 << c;
+        }
         if (!overflow) return rebuild;
         if (overflow & rebuild) return -1; /* a from-scratch list does not fit: the reference's own limit */
         rebuild = 3;                       /* an over-long delta: fall back to rebuilding */
@@ -179,48 +199,17 @@ __device__ __forceinline__ int build_lists(
     }
 }
 
-/* ------------------------------------------------------------------ accumulators in registers */
+/* ------------------------------------------------------------------ accumulators in registers
+ *
+ * One perspective, one lane: 32 int16 elements packed two per register, V[k * 4 + t]:
+ *   k = 0: A-half elements (4t, 4t+2)   k = 1: A-half (4t+1, 4t+3)      A-half element j = 16 l + j
+ *   k = 2: D-half elements (4t, 4t+2)   k = 3: D-half (4t+1, 4t+3)      D-half element j = 512 + 16 l + j
+ * (low 16 bits first).  This is the order in which the even / odd bytes of word t of a threat row
+ * fall out of one AND / one PRMT, and the device PSQ rows are stored in the same order, so both
+ * kinds of row are added with VIADD.16x2 (__vadd2: wrapping, no carry between the halves). */
 
-/* One perspective, one lane: 32 logical elements.
- *   plo/phi  int16 sums, one 32-bit register per element; only the low 16 bits are meaningful
- *            (plo += word leaves garbage above bit 15, phi += word >> 16 likewise)
- *   ae/ao    sums of BIASED (+128) threat bytes of added rows, two 16-bit fields per register: even
- *            bytes of a word in ae, odd bytes in ao.  <= 256 rows x 255 < 2^16: fields never carry.
- *   se/so    the same for subtracted rows */
-struct LaneAcc {
-    uint32_t plo[16], phi[16];
-    uint32_t ae[8], ao[8], se[8], so[8];
-};
-
-template <int kSign>
-__device__ __forceinline__ void add_psq_chunks(LaneAcc& a, const uint4 (&c)[4]) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t w[4] = {c[k].x, c[k].y, c[k].z, c[k].w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            if (kSign > 0) {
-                a.plo[k * 4 + t] += w[t];
-                a.phi[k * 4 + t] += w[t] >> 16;
-            } else {
-                a.plo[k * 4 + t] -= w[t];
-                a.phi[k * 4 + t] -= w[t] >> 16;
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ void add_thr_chunks(uint32_t (&te)[8], uint32_t (&to)[8], const uint4 (&c)[2]) {
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const uint32_t w[4] = {c[u].x, c[u].y, c[u].z, c[u].w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            te[u * 4 + t] += w[t] & 0x00FF00FFu;
-            to[u * 4 + t] += __byte_perm(w[t], 0, 0x4341); /* bytes 1 and 3 into the two 16-bit fields */
-        }
-    }
-}
+__device__ __forceinline__ uint32_t even_bytes(uint32_t w) { return w & 0x00FF00FFu; }
+__device__ __forceinline__ uint32_t odd_bytes(uint32_t w) { return __byte_perm(w, 0, 0x4341); }
 
 __device__ __forceinline__ void load_psq_row(const DeviceNet& net, uint32_t row, int lane, uint4 (&c)[4]) {
     const uint4* r = net.psq + static_cast<size_t>(row) * 128 + lane;
@@ -234,165 +223,145 @@ __device__ __forceinline__ void load_thr_row(const DeviceNet& net, uint32_t row,
     c[1] = __ldg(r + 32);
 }
 
-/* Apply a PSQ row list (entries may carry kSubFlag); short batches are topped up with the zero row. */
-__device__ __forceinline__ void accumulate_psq(const DeviceNet& net, const uint16_t* list, int n, int lane, LaneAcc& a) {
-    for (int i = 0; i < n; i += kPsqGroup) {
+__device__ __forceinline__ void add_psq(uint32_t (&v)[16], const uint4 (&c)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k * 4 + 0] = __vadd2(v[k * 4 + 0], c[k].x);
+        v[k * 4 + 1] = __vadd2(v[k * 4 + 1], c[k].y);
+        v[k * 4 + 2] = __vadd2(v[k * 4 + 2], c[k].z);
+        v[k * 4 + 3] = __vadd2(v[k * 4 + 3], c[k].w);
+    }
+}
+
+/* threat row (biased bytes) straight into packed int16 registers: used for the few delta rows */
+__device__ __forceinline__ void add_thr_packed(uint32_t (&v)[16], const uint4 (&c)[2]) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const uint32_t w[4] = {c[u].x, c[u].y, c[u].z, c[u].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            v[(2 * u) * 4 + t] = __vadd2(v[(2 * u) * 4 + t], even_bytes(w[t]));
+            v[(2 * u + 1) * 4 + t] = __vadd2(v[(2 * u + 1) * 4 + t], odd_bytes(w[t]));
+        }
+    }
+}
+
+/* Many threat rows (rebuild path): plain 32-bit sums.  s += word accumulates all four bytes with
+ * weights 1, 2^8, 2^16, 2^24 (mod 2^32); o += odd bytes as two 16-bit fields.  <= 256 rows x 255
+ * < 2^16, so the fields of o never carry and s - (o << 8) leaves exactly the even-byte fields. */
+__device__ __forceinline__ void add_thr_wide(uint32_t (&s)[8], uint32_t (&o)[8], const uint4 (&c)[2]) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const uint32_t w[4] = {c[u].x, c[u].y, c[u].z, c[u].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            s[u * 4 + t] += w[t];
+            o[u * 4 + t] += odd_bytes(w[t]);
+        }
+    }
+}
+
+/* Rebuild one perspective from its full lists: v = bias + sum(PSQ rows) + sum(threat rows). */
+__device__ __forceinline__ void rebuild_perspective(
+    const DeviceNet& net, const uint16_t* psq_list, int n_psq, const uint16_t* thr_list, int n_thr, int lane, uint32_t (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0;
+    for (int i = 0; i < n_psq; i += kPsqGroup) {
         uint4 c[kPsqGroup][4];
-        uint32_t e[kPsqGroup];
 #pragma unroll
-        for (int j = 0; j < kPsqGroup; ++j) {
-            e[j] = i + j < n ? list[i + j] : static_cast<uint32_t>(kPsqZeroRow);
-            load_psq_row(net, e[j] & (kSubFlag - 1), lane, c[j]);
-        }
+        for (int j = 0; j < kPsqGroup; ++j) load_psq_row(net, i + j < n_psq ? psq_list[i + j] : static_cast<uint32_t>(kPsqZeroRow), lane, c[j]);
 #pragma unroll
-        for (int j = 0; j < kPsqGroup; ++j) {
-            if (e[j] & kSubFlag) add_psq_chunks<-1>(a, c[j]);
-            else add_psq_chunks<1>(a, c[j]);
-        }
+        for (int j = 0; j < kPsqGroup; ++j) add_psq(v, c[j]);
     }
+    uint32_t s[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = o[i] = 0;
+    int rows = 0;
+    for (int i = 0; i < n_thr; i += kThrGroupFull) {
+        uint4 c[kThrGroupFull][2];
+#pragma unroll
+        for (int j = 0; j < kThrGroupFull; ++j) load_thr_row(net, i + j < n_thr ? thr_list[i + j] : static_cast<uint32_t>(kThrZeroRow), lane, c[j]);
+#pragma unroll
+        for (int j = 0; j < kThrGroupFull; ++j) add_thr_wide(s, o, c[j]);
+        rows += kThrGroupFull;
+    }
+    /* every row (zero-row top-ups included) carried +128 per element */
+    const uint32_t corr = (static_cast<uint32_t>(-128 * rows) & 0xFFFFu) * 0x10001u;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint32_t even = s[u * 4 + t] - (o[u * 4 + t] << 8);
+            v[(2 * u) * 4 + t] = __vadd2(__vadd2(v[(2 * u) * 4 + t], even), corr);
+            v[(2 * u + 1) * 4 + t] = __vadd2(__vadd2(v[(2 * u + 1) * 4 + t], o[u * 4 + t]), corr);
+        }
 }
 
-/* Sum threat rows; returns how many rows (including zero-row top-ups, each worth +128) went in. */
-template <int kGroup>
-__device__ __forceinline__ int accumulate_thr(
-    const DeviceNet& net, const uint16_t* list, int n, int lane, uint32_t (&te)[8], uint32_t (&to)[8]) {
-    int rows = 0;
-    for (int i = 0; i < n; i += kGroup) {
-        uint4 c[kGroup][2];
+/* Advance one perspective by its delta lists: v += adds - subs.  Added and subtracted rows are
+ * fetched in lock-step (equal row counts on both sides, so the +128 biases cancel). */
+__device__ __forceinline__ void update_perspective(const DeviceNet& net, const WarpScratch& ws, int c, int lane, uint32_t (&v)[16]) {
+    uint32_t neg[16];
 #pragma unroll
-        for (int j = 0; j < kGroup; ++j) load_thr_row(net, i + j < n ? list[i + j] : static_cast<uint32_t>(kThrZeroRow), lane, c[j]);
+    for (int i = 0; i < 16; ++i) neg[i] = 0;
+    const int n_pa = ws.n_psq_add[c], n_ps = ws.n_psq_sub[c];
+    for (int i = 0; i < max(n_pa, n_ps); i += kPsqGroupDelta) {
+        uint4 ca[kPsqGroupDelta][4], cs[kPsqGroupDelta][4];
 #pragma unroll
-        for (int j = 0; j < kGroup; ++j) add_thr_chunks(te, to, c[j]);
-        rows += kGroup;
+        for (int j = 0; j < kPsqGroupDelta; ++j) {
+            load_psq_row(net, i + j < n_pa ? ws.psq_add[c][i + j] : static_cast<uint32_t>(kPsqZeroRow), lane, ca[j]);
+            load_psq_row(net, i + j < n_ps ? ws.psq_sub[c][i + j] : static_cast<uint32_t>(kPsqZeroRow), lane, cs[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kPsqGroupDelta; ++j) {
+            add_psq(v, ca[j]);
+            add_psq(neg, cs[j]);
+        }
     }
-    return rows;
-}
-
-/* Added and subtracted rows in lock-step, so both signs' loads are in flight together. */
-__device__ __forceinline__ int accumulate_thr_delta(
-    const DeviceNet& net, const uint16_t* add, int n_add, const uint16_t* sub, int n_sub, int lane, LaneAcc& a) {
-    int rows = 0;
-    const int n = max(n_add, n_sub);
-    for (int i = 0; i < n; i += kThrGroupDelta) {
+    const int n_ta = ws.n_thr_add[c], n_ts = ws.n_thr_sub[c];
+    for (int i = 0; i < max(n_ta, n_ts); i += kThrGroupDelta) {
         uint4 ca[kThrGroupDelta][2], cs[kThrGroupDelta][2];
 #pragma unroll
         for (int j = 0; j < kThrGroupDelta; ++j) {
-            load_thr_row(net, i + j < n_add ? add[i + j] : static_cast<uint32_t>(kThrZeroRow), lane, ca[j]);
-            load_thr_row(net, i + j < n_sub ? sub[i + j] : static_cast<uint32_t>(kThrZeroRow), lane, cs[j]);
+            load_thr_row(net, i + j < n_ta ? ws.thr_add[c][i + j] : static_cast<uint32_t>(kThrZeroRow), lane, ca[j]);
+            load_thr_row(net, i + j < n_ts ? ws.thr_sub[c][i + j] : static_cast<uint32_t>(kThrZeroRow), lane, cs[j]);
         }
 #pragma unroll
         for (int j = 0; j < kThrGroupDelta; ++j) {
-            add_thr_chunks(a.ae, a.ao, ca[j]);
-            add_thr_chunks(a.se, a.so, cs[j]);
-        }
-        rows += kThrGroupDelta;
-    }
-    return rows; /* the same number of rows on both sides: their +128 biases cancel */
-}
-
-/* Collapse into 32 wrapped int16 values: v[0..15] = first-half elements 16l + j, v[16..31] =
- * second-half elements 512 + 16l + j.  `bias_rows` = added-minus-subtracted threat rows (x128). */
-template <bool kHasSub>
-__device__ __forceinline__ void finalize(const LaneAcc& a, int bias_rows, int (&v)[32]) {
-    const uint32_t corr = static_cast<uint32_t>(bias_rows) * 128u;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int pi = (h * 2 + (j >> 3)) * 4 + ((j & 7) >> 1);
-            const int ti = h * 4 + (j >> 2), shift = ((j & 3) >> 1) * 16;
-            uint32_t x = (j & 1) ? a.phi[pi] : a.plo[pi];
-            x += ((j & 1) ? a.ao[ti] : a.ae[ti]) >> shift;
-            if (kHasSub) x -= ((j & 1) ? a.so[ti] : a.se[ti]) >> shift;
-            v[h * 16 + j] = static_cast<int16_t>(static_cast<uint16_t>(x - corr));
+            add_thr_packed(v, ca[j]);
+            add_thr_packed(neg, cs[j]);
         }
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __vsub2(v[i], neg[i]);
 }
 
-/* activateFt, multilayer.h:92-152: 16 outputs of this lane for one perspective, packed little-endian. */
-__device__ __forceinline__ uint4 activate(const int (&v)[32]) {
-    uint32_t out[4] = {0, 0, 0, 0};
+/* activateFt, multilayer.h:92-152, on packed pairs: out = (clamp(a,0,255) * clamp(d,0,255)) >> 9.
+ * Equal to the reference's sat_u8(((clamp(a,0,255) << 7) * min(d,255)) >> 16): for d < 0 the
+ * product is <= 0 and saturates to 0, for d >= 0 it is (a * d) >> 9 <= 127.
+ * Returns this lane's 16 output bytes (elements 16 l .. 16 l + 15 of the perspective's half). */
+__device__ __forceinline__ uint4 activate(const uint32_t (&v)[16]) {
+    uint32_t out[4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        int a = v[j], d = v[16 + j];
-        a = min(max(a, 0), 255);
-        d = min(d, 255);
-        int p = ((a << 7) * d) >> 16; /* signed mulhi: arithmetic shift floors */
-        p = min(max(p, 0), 255);      /* packus */
-        out[j >> 2] |= static_cast<uint32_t>(p) << ((j & 3) * 8);
+    for (int t = 0; t < 4; ++t) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+            const uint32_t a = __vmins2(__vmaxs2(v[par * 4 + t], 0u), 0x00FF00FFu);
+            const uint32_t d = __vmins2(__vmaxs2(v[(2 + par) * 4 + t], 0u), 0x00FF00FFu);
+            const uint32_t lo = ((a & 0xFFFFu) * (d & 0xFFFFu)) >> 9; /* element 4t + par     -> byte par     */
+            const uint32_t hi = ((a >> 16) * (d >> 16)) >> 9;         /* element 4t + par + 2 -> byte par + 2 */
+            word |= lo << (8 * par) | hi << (8 * par + 16);
+        }
+        out[t] = word;
     }
     return make_uint4(out[0], out[1], out[2], out[3]);
-}
-
-/* 32 int16 values <-> 4 uint4 (the slot / register-resident form: q[0..1] first half, q[2..3] second) */
-__device__ __forceinline__ void pack_acc(const int (&v)[32], uint4 (&q)[4]) {
-    uint32_t w[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-        w[i] = (static_cast<uint32_t>(v[2 * i]) & 0xFFFFu) | (static_cast<uint32_t>(v[2 * i + 1]) << 16);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) q[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-}
-
-__device__ __forceinline__ void unpack_acc(const uint4 (&q)[4], int (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t w[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            v[(i * 4 + t) * 2] = static_cast<int16_t>(w[t] & 0xFFFFu);
-            v[(i * 4 + t) * 2 + 1] = static_cast<int16_t>(w[t] >> 16);
-        }
-    }
-}
-
-/* Seed a LaneAcc from a stored accumulator: word i of q holds elements (2i, 2i+1) in exactly the
- * order of the device PSQ rows, so plo = word and phi = word >> 16. */
-__device__ __forceinline__ void seed_acc(LaneAcc& a, const uint4 (&q)[4]) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t w[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            a.plo[k * 4 + t] = w[t];
-            a.phi[k * 4 + t] = w[t] >> 16;
-        }
-    }
-}
-
-__device__ __forceinline__ void clear_acc(LaneAcc& a, bool psq_too) {
-    if (psq_too) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a.plo[i] = a.phi[i] = 0;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a.ae[i] = a.ao[i] = a.se[i] = a.so[i] = 0;
-}
-
-/* Bring perspective c up to date with the lists in `ws`: rebuilt from zero, or `q` (+/- delta rows).
- * On return q holds the new accumulator and v its 32 values. */
-__device__ __forceinline__ void advance_perspective(
-    const DeviceNet& net, const WarpScratch& ws, int c, bool rebuild, int lane, uint4 (&q)[4], int (&v)[32]) {
-    LaneAcc a;
-    clear_acc(a, rebuild);
-    if (!rebuild) seed_acc(a, q);
-    accumulate_psq(net, ws.psq[c], ws.n_psq[c], lane, a);
-    int bias_rows;
-    if (rebuild) {
-        bias_rows = accumulate_thr<kThrGroupFull>(net, ws.thr_add[c], ws.n_thr_add[c], lane, a.ae, a.ao);
-        finalize<false>(a, bias_rows, v);
-    } else {
-        accumulate_thr_delta(net, ws.thr_add[c], ws.n_thr_add[c], ws.thr_sub[c], ws.n_thr_sub[c], lane, a);
-        finalize<true>(a, 0, v);
-    }
-    pack_acc(v, q);
 }
 
 __device__ __forceinline__ void flag_error(DeviceStatus* status, int bits) { atomicOr(&status->error, bits); }
 
 /* ------------------------------------------------------------------ full refresh: boards -> activations */
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 ft_full_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, size_t n, uint8_t* __restrict__ act,
                uint8_t* __restrict__ bucket, DeviceStatus* status) {
     __shared__ WarpScratch scratch[kWarpsPerCta];
@@ -414,12 +383,8 @@ ft_full_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, size_t n
         uint4* row = reinterpret_cast<uint4*>(act + pos * SP_L1_SIZE);
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
-            LaneAcc a;
-            clear_acc(a, true);
-            accumulate_psq(net, ws.psq[c], ws.n_psq[c], lane, a);
-            const int rows = accumulate_thr<kThrGroupFull>(net, ws.thr_add[c], ws.n_thr_add[c], lane, a.ae, a.ao);
-            int v[32];
-            finalize<false>(a, rows, v);
+            uint32_t v[16];
+            rebuild_perspective(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, v);
             const int half = c == d.view.stm ? 0 : 1; /* side to move first, nnue_state.cpp:405-419 */
             row[half * 32 + lane] = activate(v);
         }
@@ -429,22 +394,25 @@ ft_full_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, size_t n
 
 /* ------------------------------------------------------------------ accumulator slots */
 
-__device__ __forceinline__ void load_slot_acc(const SlotStore& s, uint32_t slot, int c, int lane, uint4 (&q)[4]) {
+__device__ __forceinline__ void load_slot_acc(const SlotStore& s, uint32_t slot, int c, int lane, uint32_t (&v)[16]) {
     const uint4* p = s.acc + (static_cast<size_t>(slot) * 2 + c) * 128 + lane;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) q[k] = p[32 * k];
+    for (int k = 0; k < 4; ++k) {
+        const uint4 q = p[32 * k];
+        v[k * 4 + 0] = q.x, v[k * 4 + 1] = q.y, v[k * 4 + 2] = q.z, v[k * 4 + 3] = q.w;
+    }
 }
 
-__device__ __forceinline__ void store_slot_acc(const SlotStore& s, uint32_t slot, int c, int lane, const uint4 (&q)[4]) {
+__device__ __forceinline__ void store_slot_acc(const SlotStore& s, uint32_t slot, int c, int lane, const uint32_t (&v)[16]) {
     uint4* p = s.acc + (static_cast<size_t>(slot) * 2 + c) * 128 + lane;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) p[32 * k] = q[k];
+    for (int k = 0; k < 4; ++k) p[32 * k] = make_uint4(v[k * 4 + 0], v[k * 4 + 1], v[k * 4 + 2], v[k * 4 + 3]);
 }
 
 /* dst[i] = (src ? src[i] advanced to boards[i] : rebuilt from boards[i]); optional activation output.
  * Replaces NnueState::reset / push + applyMove<BoardObserver> + ensureUpToDate
  * (nnue_state.cpp:539-570, 636-697). */
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 ft_slots_kernel(DeviceNet net, SlotStore slots, const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
                 const SpPackedBoard* __restrict__ boards, size_t n, uint8_t* __restrict__ act, uint8_t* __restrict__ bucket,
                 DeviceStatus* status) {
@@ -465,7 +433,8 @@ ft_slots_kernel(DeviceNet net, SlotStore slots, const uint32_t* __restrict__ src
             if (!d.ok) err = kErrBadBoard;
         }
         if (!err && src) {
-            prev = decode_board(slots.boards + from, lane, ws.mailbox[1]);
+            const uint4* rec = reinterpret_cast<const uint4*>(slots.boards + from); /* written by earlier launches: plain loads */
+            prev = decode_board(rec[0], rec[1], lane, ws.mailbox[1]);
             if (!prev.ok) err = kErrBadBoard; /* the source slot was never filled */
         }
         if (!err) {
@@ -481,12 +450,14 @@ ft_slots_kernel(DeviceNet net, SlotStore slots, const uint32_t* __restrict__ src
         }
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
-            const bool fresh = (rebuild >> c) & 1;
-            uint4 q[4];
-            if (!fresh) load_slot_acc(slots, from, c, lane, q);
-            int v[32];
-            advance_perspective(net, ws, c, fresh, lane, q, v);
-            store_slot_acc(slots, to, c, lane, q);
+            uint32_t v[16];
+            if ((rebuild >> c) & 1) {
+                rebuild_perspective(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, v);
+            } else {
+                load_slot_acc(slots, from, c, lane, v);
+                update_perspective(net, ws, c, lane, v);
+            }
+            store_slot_acc(slots, to, c, lane, v);
             if (act) {
                 const int half = c == d.view.stm ? 0 : 1;
                 reinterpret_cast<uint4*>(act + i * SP_L1_SIZE)[half * 32 + lane] = activate(v);
@@ -526,10 +497,8 @@ slot_activate_kernel(SlotStore slots, const uint32_t* __restrict__ ids, const ui
         const int side = stm ? (stm[i] & 1) : ((hi.z & 0x80) ? kBlack : kWhite);
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
-            uint4 q[4];
-            load_slot_acc(slots, slot, c, lane, q);
-            int v[32];
-            unpack_acc(q, v);
+            uint32_t v[16];
+            load_slot_acc(slots, slot, c, lane, v);
             const int half = c == side ? 0 : 1;
             reinterpret_cast<uint4*>(act + i * SP_L1_SIZE)[half * 32 + lane] = activate(v);
         }
@@ -541,7 +510,7 @@ slot_activate_kernel(SlotStore slots, const uint32_t* __restrict__ ids, const ui
 
 /* One warp plays through one game: both accumulators stay in registers from ply to ply
  * (datagen form, src/datagen/datagen.cpp:257-262: applyMove + applyImmediately + evaluate). */
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const uint32_t* __restrict__ game_start,
                 uint32_t n_games, uint8_t* __restrict__ act, uint8_t* __restrict__ bucket, DeviceStatus* status) {
     __shared__ WarpScratch scratch[kWarpsPerCta];
@@ -551,12 +520,22 @@ ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const u
     const uint32_t stride = gridDim.x * kWarpsPerCta;
     for (uint32_t g = blockIdx.x * kWarpsPerCta + warp; g < n_games; g += stride) {
         const size_t first = game_start[g], last = game_start[g + 1];
-        uint4 q[2][4];
+        uint32_t v[2][16];
         BoardView prev{};
         bool have_prev = false;
+        /* the next record is fetched one ply ahead so its latency hides behind this ply's work */
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (first < last) {
+            const uint4* p = reinterpret_cast<const uint4*>(boards + first);
+            lo = __ldg(p), hi = __ldg(p + 1);
+        }
         for (size_t pos = first; pos < last; ++pos) {
             const int buf = static_cast<int>(pos - first) & 1;
-            const Decoded d = decode_board(boards + pos, lane, ws.mailbox[buf]);
+            const Decoded d = decode_board(lo, hi, lane, ws.mailbox[buf]);
+            if (pos + 1 < last) {
+                const uint4* p = reinterpret_cast<const uint4*>(boards + pos + 1);
+                lo = __ldg(p), hi = __ldg(p + 1);
+            }
             int err = d.ok ? 0 : kErrBadBoard;
             int rebuild = 3;
             if (!err) {
@@ -573,10 +552,10 @@ ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const u
             }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                int v[32];
-                advance_perspective(net, ws, c, (rebuild >> c) & 1, lane, q[c], v);
+                if ((rebuild >> c) & 1) rebuild_perspective(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, v[c]);
+                else update_perspective(net, ws, c, lane, v[c]);
                 const int half = c == d.view.stm ? 0 : 1;
-                reinterpret_cast<uint4*>(act + pos * SP_L1_SIZE)[half * 32 + lane] = activate(v);
+                reinterpret_cast<uint4*>(act + pos * SP_L1_SIZE)[half * 32 + lane] = activate(v[c]);
             }
             if (lane == 0) bucket[pos] = static_cast<uint8_t>(output_bucket(d.view.occ));
             prev = d.view;

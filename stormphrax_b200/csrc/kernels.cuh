@@ -53,10 +53,15 @@ struct DeviceStatus {
     unsigned long long counters[8];
 };
 
-/* Logical element index held at (chunk k, lane l, element e) of a device PSQ row / accumulator:
- * lane l owns logical elements [16 l, 16 l + 16) and [512 + 16 l, 512 + 16 l + 16), i.e. both
- * members of the 16 activation pairs (i, i + 512) it will multiply (multilayer.h:118-135). */
-inline int lane_order_element(int k, int lane, int e) { return (k >= 2 ? 512 : 0) + lane * 16 + (k & 1) * 8 + e; }
+/* Logical element index held at (chunk k, lane l, int16 slot e) of a device PSQ row / stored
+ * accumulator.  Lane l owns logical elements [16 l, 16 l + 16) ("A half") and
+ * [512 + 16 l, 512 + 16 l + 16) ("D half"): both members of the 16 activation pairs (i, i + 512) it
+ * multiplies (multilayer.h:118-135).  Inside a lane the int16 are paired the way the even / odd
+ * bytes of a 4-byte threat-row word unpack: chunk k = 0: A even, 1: A odd, 2: D even, 3: D odd;
+ * word t = e / 2 of the chunk holds elements 4t + (k & 1) (low half) and 4t + (k & 1) + 2 (high). */
+inline int lane_order_element(int k, int lane, int e) {
+    return (k >= 2 ? 512 : 0) + lane * 16 + 4 * (e >> 1) + (k & 1) + 2 * (e & 1);
+}
 
 /* boards[i] -> act[i][1024], bucket[i]; every position rebuilt from scratch */
 void launch_ft_full(

@@ -12,18 +12,19 @@
  * know which move was played, so captures, castling (incl. Chess960), en passant, promotions
  * and even several plies at once are all the same code path.
  *
- * Work decomposition.  D = squares whose content differs.  For every square s in D, for each of
- * the two boards X (before: rows are subtracted, after: rows are added), 17 independent items:
- *     0..7   one ray direction from s   (the reference's 8 rays)
- *     8..15  one knight offset from s   (slot 0 of each reference ray)
- *     16     PSQ row of the piece on s, and the pawn pairs of a pawn on s
- * A GPU lane takes items round-robin; the CPU tests run them in a loop.  Rules that make every
- * (attacker, victim) pair of X that touches D appear exactly once:
- *     - attacker on a D square           -> emitted by the attacker's item (ray or knight)
+ * Work decomposition.  D = squares whose content differs.  A UNIT is (square s in D, board X):
+ * X = before emits rows to subtract, X = after rows to add.  Per unit there are
+ *     8 LINE items   k = 0..7: ray direction k from s AND knight offset k from s
+ *                    (the reference's 8 rays, whose slot 0 is the knight square)
+ *     1 SQUARE item  PSQ row of the piece on s, and the pawn pairs of a pawn on s
+ * Line items are uniform code for every (unit, k), so a GPU warp runs 32 of them in lock-step:
+ * lane = unit * 8 + k.  Rules that make every (attacker, victim) pair of X that touches D
+ * appear exactly once:
+ *     - attacker on a D square           -> emitted by the attacker's item
  *     - victim on D, attacker not on D   -> emitted by the victim's item
  *     - both off D, but a D square that is EMPTY in X lies strictly between them on the line
  *       (x-ray through the vacated / newly blocked square: the reference's "discovered"
- *       threats, nnue.cpp:424-484) -> emitted by the ray item of the D square closest to the
+ *       threats, nnue.cpp:424-484) -> emitted by the item of the D square closest to the
  *       attacker.
  */
 #ifndef SP_DELTA_H
@@ -33,9 +34,8 @@
 
 namespace sp {
 
-constexpr int kMaxChanged = 8;         /* more changed squares than this -> full refresh */
-constexpr int kItemsPerSquareBoard = 17;
-constexpr int kDeltaItems = kMaxChanged * 2 * kItemsPerSquareBoard;
+constexpr int kMaxChanged = 8; /* more changed squares than this -> full rebuild */
+constexpr int kLineItemsPerUnit = 8;
 
 SP_HD uint64_t changed_squares(const Board& before, const Board& after) {
     uint64_t d = 0;
@@ -53,43 +53,52 @@ SP_HD bool needs_refresh(const FeatureTables& t, const B& before, const B& after
     return ((kb & 7) >= 4) != ((ka & 7) >= 4) || king_bucket(t, c, kb) != king_bucket(t, c, ka);
 }
 
-SP_HD bool slides_along(int piece, int dir) { /* dir 0..7 = N,NE,E,SE,S,SW,W,NW; odd = diagonal */
+/* Directions 0..7 = N, NE, E, SE, S, SW, W, NW; k ^ 4 is the opposite; odd = diagonal.
+ * N, NE, E and NW lead to higher square numbers. */
+SP_HD bool dir_is_up(int k) { return k < 3 || k == 7; }
+
+SP_HD bool slides_along(int piece, int dir) {
     const int type = piece >> 1;
     return type == kQueen || (type == kBishop && (dir & 1)) || (type == kRook && !(dir & 1));
 }
 
-/* Does `piece` standing `dist` steps away attack along direction `dir` (pointing from the piece
- * towards the target)?  Kings never count (threats.cpp:42-54 maps them to -1 anyway). */
-SP_HD bool attacks_along(int piece, int dir, int dist) {
+/* Does `piece` attack along direction `dir` (pointing from the piece towards the target)?
+ * `adjacent`: the target is the very next square.  Kings never count (threats.cpp:42-54 maps
+ * them to -1 anyway). */
+SP_HD bool attacks_along(int piece, int dir, bool adjacent) {
     if (piece == kNoPiece) return false;
     if (slides_along(piece, dir)) return true;
-    if ((piece >> 1) == kPawn && dist == 1) {
+    if ((piece >> 1) == kPawn && adjacent) {
         /* white pawns capture NE / NW, black pawns SE / SW (attacks.h:37-48) */
         return (piece & 1) == kWhite ? (dir == 1 || dir == 7) : (dir == 3 || dir == 5);
     }
     return false;
 }
 
-/* First occupied square from s along dir (exclusive of s); kNoSquare if the ray leaves the board.
- * `between` receives the empty squares walked over. */
-template <typename B>
-SP_HD int ray_first(const B& b, int s, int dir, uint64_t& between, int& dist) {
-    const int dx = (dir >= 1 && dir <= 3) ? 1 : ((dir >= 5) ? -1 : 0);
-    const int dy = (dir == 0 || dir == 1 || dir == 7) ? 1 : ((dir >= 3 && dir <= 5) ? -1 : 0);
-    int f = (s & 7) + dx, r = (s >> 3) + dy;
-    between = 0;
-    dist = 1;
-    while (f >= 0 && f < 8 && r >= 0 && r < 8) {
-        const int sq = r * 8 + f;
-        if ((b.occ >> sq) & 1) return sq;
-        between |= bit(sq);
-        f += dx;
-        r += dy;
-        ++dist;
+SP_HD uint64_t squares_above(int s) { return ~((uint64_t{2} << s) - 1); }
+SP_HD uint64_t squares_below(int s) { return bit(s) - 1; }
+
+/* First occupied square from s along k (exclusive of s), or kNoSquare; `between` receives the
+ * empty squares passed over (the whole ray if it runs off the board). */
+SP_HD int ray_first(const FeatureTables& t, uint64_t occ, int s, int k, uint64_t& between) {
+    const uint64_t ray = t.rays[k][s];
+    const uint64_t hits = ray & occ;
+    between = ray;
+    if (!hits) return kNoSquare;
+    int first;
+    if (dir_is_up(k)) {
+        first = lsb64(hits);
+        between = ray & squares_below(first);
+    } else {
+        first = msb64(hits);
+        between = ray & squares_above(first);
     }
-    return kNoSquare;
+    return first;
 }
 
+/* emit(perspective, kind, sign, index): kind 0 = PSQ row, 1 = threat / pawn-pair row;
+ * sign +1 = add (feature of `after`), -1 = subtract (feature of `before`).
+ * Callers skip perspectives that are being rebuilt. */
 template <typename B, typename Emit>
 SP_HD void emit_threat(const FeatureTables& t, const B& b, int sign, int attacker, int asq, int victim, int vsq, Emit&& emit) {
     const int32_t fb = threat_index(t, kBlack, b.king[kBlack], attacker, asq, victim, vsq);
@@ -98,75 +107,80 @@ SP_HD void emit_threat(const FeatureTables& t, const B& b, int sign, int attacke
     if (fw >= 0) emit(kWhite, 1, sign, static_cast<uint32_t>(fw));
 }
 
-/* emit(perspective, kind, sign, index): kind 0 = PSQ row, 1 = threat / pawn-pair row;
- * sign +1 = add (feature of `after`), -1 = subtract (feature of `before`).
- * Callers skip perspectives that are being refreshed. */
+/* Line item k of unit (s, b). */
 template <typename B, typename Emit>
-SP_HD void delta_item(const FeatureTables& t, const B& before, const B& after, uint64_t changed, int item, Emit&& emit) {
-    const int j = item / (2 * kItemsPerSquareBoard);
-    const int rem = item - j * (2 * kItemsPerSquareBoard);
-    const bool is_after = rem >= kItemsPerSquareBoard;
-    const int k = is_after ? rem - kItemsPerSquareBoard : rem;
-    if (j >= popcount64(changed)) return;
-    uint64_t rest = changed;
-    for (int i = 0; i < j; ++i) rest &= rest - 1;
-    const int s = lsb64(rest);
-    const B& b = is_after ? after : before;
-    const int sign = is_after ? 1 : -1;
+SP_HD void delta_line_item(const FeatureTables& t, const B& b, int sign, uint64_t changed, int s, int k, Emit&& emit) {
     const int piece = b.mailbox[s];
-
-    if (k == 16) {
-        if (piece == kNoPiece) return;
-        emit(kBlack, 0, sign, psq_index(t, kBlack, piece, s, b.king[kBlack]));
-        emit(kWhite, 0, sign, psq_index(t, kWhite, piece, s, b.king[kWhite]));
-        if ((piece >> 1) != kPawn) return;
-        uint64_t partners = (b.pawns[0] | b.pawns[1]) & pp_mask(s) & ~bit(s);
-        partners &= ~(changed & (bit(s) - 1)); /* a pair of two changed pawns belongs to the lower square */
-        while (partners) {
-            const int o = lsb64(partners);
-            partners &= partners - 1;
-            const int oc = b.mailbox[o] & 1;
-            emit(kBlack, 1, sign, pp_index(kBlack, b.king[kBlack], piece & 1, s, oc, o));
-            emit(kWhite, 1, sign, pp_index(kWhite, b.king[kWhite], piece & 1, s, oc, o));
-        }
-        return;
-    }
-
-    if (k >= 8) { /* knight offsets */
-        const int kdx[8] = {1, 2, 2, 1, -1, -2, -2, -1};
-        const int kdy[8] = {2, 1, -1, -2, -2, -1, 1, 2};
-        if (piece == kNoPiece) return;
-        const int f = (s & 7) + kdx[k - 8], r = (s >> 3) + kdy[k - 8];
-        if (f < 0 || f > 7 || r < 0 || r > 7) return;
-        const int o = r * 8 + f;
-        const int other = b.mailbox[o];
-        if (other == kNoPiece) return;
-        if ((piece >> 1) == kKnight) emit_threat(t, b, sign, piece, s, other, o, emit);
-        if ((other >> 1) == kKnight && !((changed >> o) & 1)) emit_threat(t, b, sign, other, o, piece, s, emit);
-        return;
-    }
-
-    /* ray direction k */
     uint64_t gap_ahead;
-    int dist_ahead;
-    const int ahead = ray_first(b, s, k, gap_ahead, dist_ahead);
+    const int ahead = ray_first(t, b.occ, s, k, gap_ahead);
     if (piece != kNoPiece) {
-        if (ahead == kNoSquare) return;
-        const int other = b.mailbox[ahead];
-        if (attacks_along(piece, k, dist_ahead)) emit_threat(t, b, sign, piece, s, other, ahead, emit);
-        if (!((changed >> ahead) & 1) && attacks_along(other, k ^ 4, dist_ahead))
-            emit_threat(t, b, sign, other, ahead, piece, s, emit);
+        if (ahead != kNoSquare) {
+            const int other = b.mailbox[ahead];
+            const bool adjacent = gap_ahead == 0;
+            if (attacks_along(piece, k, adjacent)) emit_threat(t, b, sign, piece, s, other, ahead, emit);
+            if (!((changed >> ahead) & 1) && attacks_along(other, k ^ 4, adjacent))
+                emit_threat(t, b, sign, other, ahead, piece, s, emit);
+        }
+        /* knight offset k: dx = {1,2,2,1,-1,-2,-2,-1}, dy = {2,1,-1,-2,-2,-1,1,2}, stored +2 per nibble */
+        const int fx = (s & 7) + static_cast<int>((0x10013443u >> (4 * k)) & 0xF) - 2;
+        const int ry = (s >> 3) + static_cast<int>((0x43100134u >> (4 * k)) & 0xF) - 2;
+        if (fx >= 0 && fx < 8 && ry >= 0 && ry < 8) {
+            const int o = ry * 8 + fx;
+            const int other = b.mailbox[o];
+            if (other != kNoPiece) {
+                if ((piece >> 1) == kKnight) emit_threat(t, b, sign, piece, s, other, o, emit);
+                if ((other >> 1) == kKnight && !((changed >> o) & 1)) emit_threat(t, b, sign, other, o, piece, s, emit);
+            }
+        }
         return;
     }
     /* s is empty in this board: sliders behind s see through it to the first piece ahead */
     if (ahead == kNoSquare || ((changed >> ahead) & 1)) return;
     uint64_t gap_behind;
-    int dist_behind;
-    const int behind = ray_first(b, s, k ^ 4, gap_behind, dist_behind);
+    const int behind = ray_first(t, b.occ, s, k ^ 4, gap_behind);
     if (behind == kNoSquare || ((changed >> behind) & 1)) return;
     if (gap_behind & changed) return; /* a changed square nearer to the attacker owns this pair */
     const int attacker = b.mailbox[behind];
     if (slides_along(attacker, k)) emit_threat(t, b, sign, attacker, behind, b.mailbox[ahead], ahead, emit);
+}
+
+/* Square item of unit (s, b): PSQ row and pawn pairs. */
+template <typename B, typename Emit>
+SP_HD void delta_square_item(const FeatureTables& t, const B& b, int sign, uint64_t changed, int s, Emit&& emit) {
+    const int piece = b.mailbox[s];
+    if (piece == kNoPiece) return;
+    emit(kBlack, 0, sign, psq_index(t, kBlack, piece, s, b.king[kBlack]));
+    emit(kWhite, 0, sign, psq_index(t, kWhite, piece, s, b.king[kWhite]));
+    if ((piece >> 1) != kPawn) return;
+    uint64_t partners = (b.pawns[0] | b.pawns[1]) & pp_mask(s) & ~bit(s);
+    partners &= ~(changed & squares_below(s)); /* a pair of two changed pawns belongs to the lower square */
+    while (partners) {
+        const int o = lsb64(partners);
+        partners &= partners - 1;
+        const int oc = b.mailbox[o] & 1;
+        emit(kBlack, 1, sign, pp_index(kBlack, b.king[kBlack], piece & 1, s, oc, o));
+        emit(kWhite, 1, sign, pp_index(kWhite, b.king[kWhite], piece & 1, s, oc, o));
+    }
+}
+
+/* Square s of unit u (u = 2 * index-into-D + (after ? 1 : 0)). */
+SP_HD int unit_square(uint64_t changed, int unit) {
+    uint64_t rest = changed;
+    for (int i = 0; i < (unit >> 1); ++i) rest &= rest - 1;
+    return lsb64(rest);
+}
+
+/* Everything, sequentially (host tests; the kernels spread the items over lanes). */
+template <typename B, typename Emit>
+SP_HD void delta_all(const FeatureTables& t, const B& before, const B& after, uint64_t changed, Emit&& emit) {
+    const int units = 2 * popcount64(changed);
+    for (int u = 0; u < units; ++u) {
+        const int s = unit_square(changed, u);
+        const B& b = (u & 1) ? after : before;
+        const int sign = (u & 1) ? 1 : -1;
+        for (int k = 0; k < kLineItemsPerUnit; ++k) delta_line_item(t, b, sign, changed, s, k, emit);
+        delta_square_item(t, b, sign, changed, s, emit);
+    }
 }
 
 } // namespace sp

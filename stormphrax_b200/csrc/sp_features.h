@@ -49,6 +49,13 @@ SP_HD int lsb64(uint64_t x) {
     return __builtin_ctzll(x);
 #endif
 }
+SP_HD int msb64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return 63 - __clzll((long long)x);
+#else
+    return 63 - __builtin_clzll(x);
+#endif
+}
 SP_HD uint64_t bitrev64(uint64_t x) {
 #if defined(__CUDA_ARCH__)
     return __brevll(x);
@@ -131,6 +138,7 @@ struct FeatureTables {
     int32_t attack_idx[12][12][2]; /* kAttackIndices, threats.cpp:138-167; INT32_MIN = excluded */
     uint16_t offsets[12][64];      /* kOffsets.offsets, threats.cpp:108-136 */
     uint8_t half_buckets[32];      /* eval/arch.h:53-65 */
+    uint64_t rays[8][64];          /* empty-board ray from sq: N, NE, E, SE, S, SW, W, NW (sq excluded) */
 };
 
 /* Host-side construction; mirrors the constexpr lambdas in threats.cpp. */
@@ -151,6 +159,14 @@ inline void build_feature_tables(FeatureTables& t) {
     }
     for (int piece = 0; piece < 12; ++piece)
         for (int sq = 0; sq < 64; ++sq) t.pseudo[piece][sq] = piece_attacks(piece, sq, 0);
+    static const int kDx[8] = {0, 1, 1, 1, 0, -1, -1, -1}, kDy[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+    for (int k = 0; k < 8; ++k)
+        for (int sq = 0; sq < 64; ++sq) {
+            uint64_t ray = 0;
+            for (int f = (sq & 7) + kDx[k], r = (sq >> 3) + kDy[k]; f >= 0 && f < 8 && r >= 0 && r < 8; f += kDx[k], r += kDy[k])
+                ray |= bit(r * 8 + f);
+            t.rays[k][sq] = ray;
+        }
     int32_t total[12], base[12];
     int32_t running = 0;
     for (int ci = 0; ci < 2; ++ci) { /* white pieces first, then black: threats.cpp:116 */
