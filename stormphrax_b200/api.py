@@ -85,7 +85,9 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         path = _build.LIB_PATH
-        if os.path.exists(os.path.join(_build.CSRC, "kernels.cu")) and _build.shutil.which("nvcc"):
+        if os.environ.get("SP_NNUE_LIB"):  # experiments: a variant build of the same sources
+            path = os.environ["SP_NNUE_LIB"]
+        elif os.path.exists(os.path.join(_build.CSRC, "kernels.cu")) and _build.shutil.which("nvcc"):
             path = _build.build()
         if not os.path.exists(path):
             raise ImportError(f"{path} is missing and cannot be built here: run `python -m stormphrax_b200.build`")

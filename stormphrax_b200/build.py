@@ -44,17 +44,19 @@ def _stale() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines: dict | None = None, out: str | None = None) -> str:
+    """`defines` / `out` build a tuning variant (see the SP_* knobs at the top of kernels.cu)."""
+    target = out or LIB_PATH
+    if not force and not defines and not out and not _stale():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(os.path.dirname(target), exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in CUDA_SOURCES + HOST_SOURCES if os.path.exists(os.path.join(CSRC, f))]
-    cmd = [nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB_PATH, *srcs, "-lpthread"]
+    cmd = [nvcc(), *NVCC_FLAGS, *[f"-D{k}={v}" for k, v in (defines or {}).items()], "-shared", "-o", target, *srcs, "-lpthread"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":

@@ -26,8 +26,21 @@ namespace {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kPsqGroup = 4;       /* PSQ rows fetched per batch on the rebuild path (16 x LDG.128 in flight per lane) */
-constexpr int kThrGroupFull = 8;   /* threat rows per batch on the rebuild path (16 x LDG.128) */
+/* tuning knobs (overridable at compile time for experiments; defaults are the measured best) */
+#ifndef SP_PSQ_GROUP
+#define SP_PSQ_GROUP 4
+#endif
+#ifndef SP_THR_GROUP
+#define SP_THR_GROUP 8
+#endif
+#ifndef SP_FULL_MIN_BLOCKS
+#define SP_FULL_MIN_BLOCKS 2
+#endif
+#ifndef SP_GAMES_MIN_BLOCKS
+#define SP_GAMES_MIN_BLOCKS 2
+#endif
+constexpr int kPsqGroup = SP_PSQ_GROUP;      /* PSQ rows fetched per batch on the rebuild path (4 x LDG.128 each per lane) */
+constexpr int kThrGroupFull = SP_THR_GROUP;  /* threat rows per batch on the rebuild path (2 x LDG.128 each per lane) */
 constexpr int kPsqGroupDelta = 2;  /* per sign on the incremental path (2 adds + 2 subs = 16 x LDG.128) */
 constexpr int kThrGroupDelta = 4;  /* per sign on the incremental path (4 adds + 4 subs = 16 x LDG.128) */
 constexpr int kPsqListCap = 40;    /* 32 pieces + bias row */
@@ -57,62 +70,53 @@ struct BoardView {
     int stm;
 };
 
-/* What lane `lane` knows after decoding: warp-uniform board facts + its own piece. */
+/* Warp-uniform result of decoding a record; the mailbox itself lives in shared memory. */
 struct Decoded {
     BoardView view;
     int n_pieces;
-    int piece; /* kNoPiece for lanes >= n_pieces */
-    int sq;
     bool ok;
 };
 
-__device__ __forceinline__ int nth_set_bit(uint64_t m, int n) {
-    const uint32_t lo = static_cast<uint32_t>(m), hi = static_cast<uint32_t>(m >> 32);
-    const int c = __popc(lo);
-    return n < c ? static_cast<int>(__fns(lo, 0, n + 1)) : 32 + static_cast<int>(__fns(hi, 0, n - c + 1));
-}
-
-__device__ __forceinline__ uint64_t warp_or64(uint64_t v) {
-    const uint32_t lo = __reduce_or_sync(kFull, static_cast<uint32_t>(v));
-    const uint32_t hi = __reduce_or_sync(kFull, static_cast<uint32_t>(v >> 32));
-    return static_cast<uint64_t>(hi) << 32 | lo;
-}
-
-/* Decode one marlinformat record (src/datagen/marlinformat.h:43-77) cooperatively.
- * The mailbox is written to shared memory; everything else stays in registers. */
+/* Decode one marlinformat record (src/datagen/marlinformat.h:43-77) cooperatively: lane l owns
+ * squares l and l + 32, so one ballot per piece kind yields one half of a bitboard. */
 __device__ __forceinline__ Decoded decode_board(uint4 lo, uint4 hi, int lane, uint8_t* mailbox) {
     Decoded d;
     d.view.mailbox = mailbox;
     d.view.occ = static_cast<uint64_t>(lo.y) << 32 | lo.x;
     d.view.stm = (hi.z & 0x80) ? kBlack : kWhite;
-    d.n_pieces = __popcll(d.view.occ);
+    const int n_lo = __popc(lo.x);
+    d.n_pieces = n_lo + __popc(lo.y);
     d.ok = d.n_pieces <= 32 && d.n_pieces >= 2;
-    d.piece = kNoPiece;
-    d.sq = 0;
-    __syncwarp();
-    reinterpret_cast<uint16_t*>(mailbox)[lane] = static_cast<uint16_t>(kNoPiece | kNoPiece << 8);
-    __syncwarp();
-    if (lane < d.n_pieces && d.ok) {
-        d.sq = nth_set_bit(d.view.occ, lane);
-        const uint32_t word = lane < 8 ? lo.z : (lane < 16 ? lo.w : (lane < 24 ? hi.x : hi.y));
-        const uint32_t nib = (word >> ((lane & 7) * 4)) & 0xF;
-        uint32_t type = nib & 7;
-        if (type == 6) type = kRook;
-        if (type > kKing) {
-            d.ok = false;
-        } else {
-            d.piece = static_cast<int>(type << 1 | ((nib & 8) ? kBlack : kWhite));
-            mailbox[d.sq] = static_cast<uint8_t>(d.piece);
+    const uint32_t below = (1u << lane) - 1;
+    int piece[2];
+    bool bad = false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t half = h ? lo.y : lo.x;
+        piece[h] = kNoPiece;
+        if ((half >> lane) & 1) {
+            const int rank = (h ? n_lo : 0) + __popc(half & below); /* index into the nibble list */
+            const uint32_t word = rank < 8 ? lo.z : (rank < 16 ? lo.w : (rank < 24 ? hi.x : hi.y));
+            const uint32_t nib = (word >> ((rank & 7) * 4)) & 0xF;
+            uint32_t type = nib & 7;
+            if (type == 6) type = kRook; /* rook with castling rights */
+            if (type > kKing || rank >= 32) bad = true;
+            else piece[h] = static_cast<int>(type << 1 | ((nib & 8) ? kBlack : kWhite));
         }
     }
-    d.ok = __all_sync(kFull, d.ok);
-    const unsigned bk = __ballot_sync(kFull, d.piece == (kKing << 1 | kBlack));
-    const unsigned wk = __ballot_sync(kFull, d.piece == (kKing << 1 | kWhite));
-    if (__popc(bk) != 1 || __popc(wk) != 1) d.ok = false;
-    d.view.king[kBlack] = __shfl_sync(kFull, d.sq, bk ? __ffs(bk) - 1 : 0);
-    d.view.king[kWhite] = __shfl_sync(kFull, d.sq, wk ? __ffs(wk) - 1 : 0);
-    d.view.pawns[kBlack] = warp_or64(d.piece == (kPawn << 1 | kBlack) ? bit(d.sq) : 0);
-    d.view.pawns[kWhite] = warp_or64(d.piece == (kPawn << 1 | kWhite) ? bit(d.sq) : 0);
+    __syncwarp(); /* earlier readers of this mailbox buffer are done */
+    mailbox[lane] = static_cast<uint8_t>(piece[0]);
+    mailbox[lane + 32] = static_cast<uint8_t>(piece[1]);
+    if (__any_sync(kFull, bad)) d.ok = false;
+    auto board_of = [&](int p) {
+        return static_cast<uint64_t>(__ballot_sync(kFull, piece[1] == p)) << 32 | __ballot_sync(kFull, piece[0] == p);
+    };
+    const uint64_t bk = board_of(kKing << 1 | kBlack), wk = board_of(kKing << 1 | kWhite);
+    if (__popcll(bk) != 1 || __popcll(wk) != 1) d.ok = false;
+    d.view.king[kBlack] = bk ? lsb64(bk) : 0;
+    d.view.king[kWhite] = wk ? lsb64(wk) : 0;
+    d.view.pawns[kBlack] = board_of(kPawn << 1 | kBlack);
+    d.view.pawns[kWhite] = board_of(kPawn << 1 | kWhite);
     __syncwarp();
     return d;
 }
@@ -120,6 +124,25 @@ __device__ __forceinline__ Decoded decode_board(uint4 lo, uint4 hi, int lane, ui
 __device__ __forceinline__ Decoded decode_board(const SpPackedBoard* board, int lane, uint8_t* mailbox) {
     const uint4* p = reinterpret_cast<const uint4*>(board);
     return decode_board(__ldg(p), __ldg(p + 1), lane, mailbox);
+}
+
+/* Square of the n-th set bit (ascending), n < popcount(bits): binary search on prefix popcounts. */
+__device__ __forceinline__ int nth_piece_square(uint64_t bits, int n) {
+    uint32_t half = static_cast<uint32_t>(bits);
+    int base = 0;
+    const int n_lo = __popc(half);
+    if (n >= n_lo) {
+        n -= n_lo;
+        half = static_cast<uint32_t>(bits >> 32);
+        base = 32;
+    }
+    int pos = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const int c = __popc(half & ((1u << (pos + step)) - 1));
+        if (c <= n) pos += step;
+    }
+    return base + pos;
 }
 
 __device__ __forceinline__ void push(uint16_t* list, int* count, int cap, uint32_t value) {
@@ -163,19 +186,28 @@ __device__ __forceinline__ int build_lists(
                     push(ws.thr_sub[c], &ws.n_thr_sub[c], kThrListCap, idx);
                 }
             };
+            /* lane j < |D| finds the j-th changed square once; items fetch theirs by shuffle */
+            const int n_changed = __popcll(changed);
+            const int my_changed = lane < n_changed ? nth_piece_square(changed, lane) : 0;
             /* line items: lane = unit * 8 + k, uniform code in every lane */
-            const int units = 2 * __popcll(changed);
-            for (int item = lane; item < units * kLineItemsPerUnit; item += 32) {
+            const int units = 2 * n_changed;
+#pragma unroll 1
+            for (int base = 0; base < units * kLineItemsPerUnit; base += 32) {
+                const int item = base + lane;
                 const int u = item >> 3;
-                delta_line_item(t, (u & 1) ? d.view : *before, (u & 1) ? 1 : -1, changed, unit_square(changed, u), item & 7, emit);
+                const int s = __shfl_sync(kFull, my_changed, (u >> 1) & 31);
+                if (u < units) delta_line_item(t, (u & 1) ? d.view : *before, (u & 1) ? 1 : -1, changed, s, item & 7, emit);
             }
-            if (lane < units)
-                delta_square_item(t, (lane & 1) ? d.view : *before, (lane & 1) ? 1 : -1, changed, unit_square(changed, lane), emit);
+            const int s = __shfl_sync(kFull, my_changed, (lane >> 1) & 31);
+            if (lane < units) delta_square_item(t, (lane & 1) ? d.view : *before, (lane & 1) ? 1 : -1, changed, s, emit);
         }
-        if (rebuild && d.piece != kNoPiece) {
-            if (rebuild & 1) ws.psq_add[kBlack][lane] = static_cast<uint16_t>(psq_index(t, kBlack, d.piece, d.sq, d.view.king[kBlack]));
-            if (rebuild & 2) ws.psq_add[kWhite][lane] = static_cast<uint16_t>(psq_index(t, kWhite, d.piece, d.sq, d.view.king[kWhite]));
-            square_threat_features(t, d.view, d.sq, [&](int c, uint32_t idx) {
+        if (rebuild && lane < d.n_pieces) {
+            /* lane-per-piece enumeration of the whole board */
+            const int sq = nth_piece_square(d.view.occ, lane);
+            const int piece = d.view.mailbox[sq];
+            if (rebuild & 1) ws.psq_add[kBlack][lane] = static_cast<uint16_t>(psq_index(t, kBlack, piece, sq, d.view.king[kBlack]));
+            if (rebuild & 2) ws.psq_add[kWhite][lane] = static_cast<uint16_t>(psq_index(t, kWhite, piece, sq, d.view.king[kWhite]));
+            square_threat_features(t, d.view, sq, [&](int c, uint32_t idx) {
                 if ((rebuild >> c) & 1) push(ws.thr_add[c], &ws.n_thr_add[c], kThrListCap, idx);
             });
         }
@@ -266,6 +298,7 @@ __device__ __forceinline__ void rebuild_perspective(
     const DeviceNet& net, const uint16_t* psq_list, int n_psq, const uint16_t* thr_list, int n_thr, int lane, uint32_t (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = 0;
+#pragma unroll 1
     for (int i = 0; i < n_psq; i += kPsqGroup) {
         uint4 c[kPsqGroup][4];
 #pragma unroll
@@ -277,6 +310,7 @@ __device__ __forceinline__ void rebuild_perspective(
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = o[i] = 0;
     int rows = 0;
+#pragma unroll 1
     for (int i = 0; i < n_thr; i += kThrGroupFull) {
         uint4 c[kThrGroupFull][2];
 #pragma unroll
@@ -297,6 +331,16 @@ __device__ __forceinline__ void rebuild_perspective(
         }
 }
 
+/* Out-of-line copy for the kernels where a rebuild is the rare path (king crossed a bucket
+ * boundary): keeps their hot loop small enough for the instruction cache. */
+__device__ __noinline__ void rebuild_perspective_cold(
+    const DeviceNet& net, const uint16_t* psq_list, int n_psq, const uint16_t* thr_list, int n_thr, int lane, uint32_t* out) {
+    uint32_t v[16];
+    rebuild_perspective(net, psq_list, n_psq, thr_list, n_thr, lane, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[i] = v[i];
+}
+
 /* Advance one perspective by its delta lists: v += adds - subs.  Added and subtracted rows are
  * fetched in lock-step (equal row counts on both sides, so the +128 biases cancel). */
 __device__ __forceinline__ void update_perspective(const DeviceNet& net, const WarpScratch& ws, int c, int lane, uint32_t (&v)[16]) {
@@ -304,6 +348,7 @@ __device__ __forceinline__ void update_perspective(const DeviceNet& net, const W
 #pragma unroll
     for (int i = 0; i < 16; ++i) neg[i] = 0;
     const int n_pa = ws.n_psq_add[c], n_ps = ws.n_psq_sub[c];
+#pragma unroll 1
     for (int i = 0; i < max(n_pa, n_ps); i += kPsqGroupDelta) {
         uint4 ca[kPsqGroupDelta][4], cs[kPsqGroupDelta][4];
 #pragma unroll
@@ -318,6 +363,7 @@ __device__ __forceinline__ void update_perspective(const DeviceNet& net, const W
         }
     }
     const int n_ta = ws.n_thr_add[c], n_ts = ws.n_thr_sub[c];
+#pragma unroll 1
     for (int i = 0; i < max(n_ta, n_ts); i += kThrGroupDelta) {
         uint4 ca[kThrGroupDelta][2], cs[kThrGroupDelta][2];
 #pragma unroll
@@ -361,7 +407,7 @@ __device__ __forceinline__ void flag_error(DeviceStatus* status, int bits) { ato
 
 /* ------------------------------------------------------------------ full refresh: boards -> activations */
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, SP_FULL_MIN_BLOCKS)
 ft_full_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, size_t n, uint8_t* __restrict__ act,
                uint8_t* __restrict__ bucket, DeviceStatus* status) {
     __shared__ WarpScratch scratch[kWarpsPerCta];
@@ -452,7 +498,7 @@ ft_slots_kernel(DeviceNet net, SlotStore slots, const uint32_t* __restrict__ src
         for (int c = 0; c < 2; ++c) {
             uint32_t v[16];
             if ((rebuild >> c) & 1) {
-                rebuild_perspective(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, v);
+                rebuild_perspective_cold(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, v);
             } else {
                 load_slot_acc(slots, from, c, lane, v);
                 update_perspective(net, ws, c, lane, v);
@@ -510,7 +556,7 @@ slot_activate_kernel(SlotStore slots, const uint32_t* __restrict__ ids, const ui
 
 /* One warp plays through one game: both accumulators stay in registers from ply to ply
  * (datagen form, src/datagen/datagen.cpp:257-262: applyMove + applyImmediately + evaluate). */
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, SP_GAMES_MIN_BLOCKS)
 ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const uint32_t* __restrict__ game_start,
                 uint32_t n_games, uint8_t* __restrict__ act, uint8_t* __restrict__ bucket, DeviceStatus* status) {
     __shared__ WarpScratch scratch[kWarpsPerCta];
@@ -529,6 +575,7 @@ ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const u
             const uint4* p = reinterpret_cast<const uint4*>(boards + first);
             lo = __ldg(p), hi = __ldg(p + 1);
         }
+#pragma unroll 1
         for (size_t pos = first; pos < last; ++pos) {
             const int buf = static_cast<int>(pos - first) & 1;
             const Decoded d = decode_board(lo, hi, lane, ws.mailbox[buf]);
@@ -550,12 +597,26 @@ ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const u
                 have_prev = false; /* the next good board restarts the chain */
                 continue;
             }
-#pragma unroll
+            /* one copy of the loop body: v[0] is always "the perspective being advanced", the two
+             * register sets swap places after each pass */
+#pragma unroll 1
             for (int c = 0; c < 2; ++c) {
-                if ((rebuild >> c) & 1) rebuild_perspective(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, v[c]);
-                else update_perspective(net, ws, c, lane, v[c]);
+                if ((rebuild >> c) & 1) {
+                    uint32_t fresh[16];
+                    rebuild_perspective_cold(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, fresh);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[0][i] = fresh[i];
+                } else {
+                    update_perspective(net, ws, c, lane, v[0]);
+                }
                 const int half = c == d.view.stm ? 0 : 1;
-                reinterpret_cast<uint4*>(act + pos * SP_L1_SIZE)[half * 32 + lane] = activate(v[c]);
+                reinterpret_cast<uint4*>(act + pos * SP_L1_SIZE)[half * 32 + lane] = activate(v[0]);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t tmp = v[0][i];
+                    v[0][i] = v[1][i];
+                    v[1][i] = tmp;
+                }
             }
             if (lane == 0) bucket[pos] = static_cast<uint8_t>(output_bucket(d.view.occ));
             prev = d.view;
@@ -713,7 +774,7 @@ void launch_ft_full(
     const DeviceNet& net, const SpPackedBoard* boards, size_t n, uint8_t* act, uint8_t* bucket, DeviceStatus* status,
     int sm_count, cudaStream_t stream) {
     if (!n) return;
-    ft_full_kernel<<<grid_for(n, kWarpsPerCta, sm_count, 2), kThreads, 0, stream>>>(net, boards, n, act, bucket, status);
+    ft_full_kernel<<<grid_for(n, kWarpsPerCta, sm_count, SP_FULL_MIN_BLOCKS), kThreads, 0, stream>>>(net, boards, n, act, bucket, status);
 }
 
 void launch_ft_slots(
@@ -727,7 +788,7 @@ void launch_ft_games(
     const DeviceNet& net, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, uint8_t* act,
     uint8_t* bucket, DeviceStatus* status, int sm_count, cudaStream_t stream) {
     if (!n_games) return;
-    ft_games_kernel<<<grid_for(n_games, kWarpsPerCta, sm_count, 2), kThreads, 0, stream>>>(net, boards, game_start, n_games, act, bucket, status);
+    ft_games_kernel<<<grid_for(n_games, kWarpsPerCta, sm_count, SP_GAMES_MIN_BLOCKS), kThreads, 0, stream>>>(net, boards, game_start, n_games, act, bucket, status);
 }
 
 void launch_slot_activate(

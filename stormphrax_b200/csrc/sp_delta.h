@@ -107,9 +107,18 @@ SP_HD void emit_threat(const FeatureTables& t, const B& b, int sign, int attacke
     if (fw >= 0) emit(kWhite, 1, sign, static_cast<uint32_t>(fw));
 }
 
-/* Line item k of unit (s, b). */
+/* Line item k of unit (s, b).  Up to four (attacker, victim) candidates are collected first and
+ * emitted by ONE copy of the indexing code (keeps the kernels' instruction footprint small). */
 template <typename B, typename Emit>
 SP_HD void delta_line_item(const FeatureTables& t, const B& b, int sign, uint64_t changed, int s, int k, Emit&& emit) {
+    /* candidate i: attacker squares/pieces packed as asq | vsq << 8 | attacker << 16 | victim << 24 */
+    /* fixed slots (0: piece -> ahead / x-ray, 1: ahead -> piece, 2: knight out, 3: knight in) so the
+     * candidates stay in registers */
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    unsigned valid = 0;
+    auto pack = [](int attacker, int asq, int victim, int vsq) {
+        return static_cast<uint32_t>(asq | vsq << 8 | attacker << 16 | victim << 24);
+    };
     const int piece = b.mailbox[s];
     uint64_t gap_ahead;
     const int ahead = ray_first(t, b.occ, s, k, gap_ahead);
@@ -117,9 +126,8 @@ SP_HD void delta_line_item(const FeatureTables& t, const B& b, int sign, uint64_
         if (ahead != kNoSquare) {
             const int other = b.mailbox[ahead];
             const bool adjacent = gap_ahead == 0;
-            if (attacks_along(piece, k, adjacent)) emit_threat(t, b, sign, piece, s, other, ahead, emit);
-            if (!((changed >> ahead) & 1) && attacks_along(other, k ^ 4, adjacent))
-                emit_threat(t, b, sign, other, ahead, piece, s, emit);
+            if (attacks_along(piece, k, adjacent)) c0 = pack(piece, s, other, ahead), valid |= 1;
+            if (!((changed >> ahead) & 1) && attacks_along(other, k ^ 4, adjacent)) c1 = pack(other, ahead, piece, s), valid |= 2;
         }
         /* knight offset k: dx = {1,2,2,1,-1,-2,-2,-1}, dy = {2,1,-1,-2,-2,-1,1,2}, stored +2 per nibble */
         const int fx = (s & 7) + static_cast<int>((0x10013443u >> (4 * k)) & 0xF) - 2;
@@ -128,20 +136,29 @@ SP_HD void delta_line_item(const FeatureTables& t, const B& b, int sign, uint64_
             const int o = ry * 8 + fx;
             const int other = b.mailbox[o];
             if (other != kNoPiece) {
-                if ((piece >> 1) == kKnight) emit_threat(t, b, sign, piece, s, other, o, emit);
-                if ((other >> 1) == kKnight && !((changed >> o) & 1)) emit_threat(t, b, sign, other, o, piece, s, emit);
+                if ((piece >> 1) == kKnight) c2 = pack(piece, s, other, o), valid |= 4;
+                if ((other >> 1) == kKnight && !((changed >> o) & 1)) c3 = pack(other, o, piece, s), valid |= 8;
             }
         }
-        return;
+    } else if (ahead != kNoSquare && !((changed >> ahead) & 1)) {
+        /* s is empty in this board: sliders behind s see through it to the first piece ahead */
+        uint64_t gap_behind;
+        const int behind = ray_first(t, b.occ, s, k ^ 4, gap_behind);
+        /* a changed square nearer to the attacker would own this pair */
+        if (behind != kNoSquare && !((changed >> behind) & 1) && !(gap_behind & changed)) {
+            const int attacker = b.mailbox[behind];
+            if (slides_along(attacker, k)) c0 = pack(attacker, behind, b.mailbox[ahead], ahead), valid |= 1;
+        }
     }
-    /* s is empty in this board: sliders behind s see through it to the first piece ahead */
-    if (ahead == kNoSquare || ((changed >> ahead) & 1)) return;
-    uint64_t gap_behind;
-    const int behind = ray_first(t, b.occ, s, k ^ 4, gap_behind);
-    if (behind == kNoSquare || ((changed >> behind) & 1)) return;
-    if (gap_behind & changed) return; /* a changed square nearer to the attacker owns this pair */
-    const int attacker = b.mailbox[behind];
-    if (slides_along(attacker, k)) emit_threat(t, b, sign, attacker, behind, b.mailbox[ahead], ahead, emit);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = 0; i < 4; ++i) {
+        if (!((valid >> i) & 1)) continue;
+        const uint32_t c = i == 0 ? c0 : (i == 1 ? c1 : (i == 2 ? c2 : c3));
+        emit_threat(t, b, sign, static_cast<int>((c >> 16) & 0xFF), static_cast<int>(c & 0xFF), static_cast<int>(c >> 24),
+                    static_cast<int>((c >> 8) & 0xFF), emit);
+    }
 }
 
 /* Square item of unit (s, b): PSQ row and pawn pairs. */
