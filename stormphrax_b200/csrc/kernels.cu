@@ -41,24 +41,26 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #endif
 constexpr int kPsqGroup = SP_PSQ_GROUP;      /* PSQ rows fetched per batch on the rebuild path (4 x LDG.128 each per lane) */
 constexpr int kThrGroupFull = SP_THR_GROUP;  /* threat rows per batch on the rebuild path (2 x LDG.128 each per lane) */
-constexpr int kPsqGroupDelta = 2;  /* per sign on the incremental path (2 adds + 2 subs = 16 x LDG.128) */
-constexpr int kThrGroupDelta = 4;  /* per sign on the incremental path (4 adds + 4 subs = 16 x LDG.128) */
+constexpr int kPsqGroupDelta = 4;  /* delta rows per batch on the incremental path (16 x LDG.128) */
+constexpr int kThrGroupDelta = 4;  /* (8 x LDG.128) */
 constexpr int kPsqListCap = 40;    /* 32 pieces + bias row */
 constexpr int kPsqDeltaCap = 16;
+constexpr int kThrDeltaCap = 96;
 constexpr int kThrListCap = SP_MAX_THREAT_INDICES;
+constexpr uint32_t kSubFlag = 0x80000000u; /* delta list entry: subtract this row */
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 /* Per-warp shared memory. */
 struct WarpScratch {
-    uint16_t thr_add[2][kThrListCap];
-    uint16_t thr_sub[2][kThrListCap];
-    uint16_t psq_add[2][kPsqListCap];
-    uint16_t psq_sub[2][kPsqDeltaCap];
-    uint8_t mailbox[2][64]; /* two boards: the one being evaluated and its predecessor */
+    uint16_t thr_add[2][kThrListCap];      /* rebuild: every threat / pawn-pair row of the board */
+    uint32_t thr_delta[2][kThrDeltaCap];   /* update: changed rows, kSubFlag = subtract */
+    uint16_t psq_add[2][kPsqListCap];      /* rebuild: one row per piece + the bias row */
+    uint32_t psq_delta[2][kPsqDeltaCap];   /* update */
+    uint8_t mailbox[2][64];                /* two boards: the one being evaluated and its predecessor */
     int n_thr_add[2];
-    int n_thr_sub[2];
+    int n_thr_delta[2];
     int n_psq_add[2];
-    int n_psq_sub[2];
+    int n_psq_delta[2];
 };
 
 /* Board as the shared feature code (sp_features.h, sp_delta.h) wants to see it. */
@@ -145,16 +147,17 @@ __device__ __forceinline__ int nth_piece_square(uint64_t bits, int n) {
     return base + pos;
 }
 
-__device__ __forceinline__ void push(uint16_t* list, int* count, int cap, uint32_t value) {
+template <typename T>
+__device__ __forceinline__ void push(T* list, int* count, int cap, uint32_t value) {
     const int at = atomicAdd(count, 1);
-    if (at < cap) list[at] = static_cast<uint16_t>(value);
+    if (at < cap) list[at] = static_cast<T>(value);
 }
 
 /*
  * Fill the warp's feature lists for the step `before` -> `d` (before == nullptr: no predecessor).
  *   perspectives in the returned mask are rebuilt from scratch: psq_add = all pieces + bias row,
  *     thr_add = every threat / pawn-pair feature of the board (nnue_state.cpp:309-354, 440-449)
- *   the others are updated: psq_add / psq_sub / thr_add / thr_sub = delta rows (sp_delta.h;
+ *   the others are updated: psq_delta / thr_delta = signed delta rows (sp_delta.h;
  *     replaces nnue.cpp:490-599, nnue_state.cpp:34-87, 163-307)
  * A perspective is rebuilt when its king changes input bucket or board half (psq.h:264-283,
  * nnue_state.h:118-128), when more than kMaxChanged squares differ, or when a delta list overflows.
@@ -172,19 +175,14 @@ __device__ __forceinline__ int build_lists(
         if (__popcll(changed) > kMaxChanged) rebuild = 3;
     }
     for (;;) {
-        if (lane < 2) ws.n_thr_add[lane] = ws.n_thr_sub[lane] = ws.n_psq_add[lane] = ws.n_psq_sub[lane] = 0;
+        if (lane < 2) ws.n_thr_add[lane] = ws.n_thr_delta[lane] = ws.n_psq_add[lane] = ws.n_psq_delta[lane] = 0;
         __syncwarp();
         if (rebuild != 3) {
             auto emit = [&](int c, int kind, int sign, uint32_t idx) {
                 if ((rebuild >> c) & 1) return;
-                if (kind == 0) {
-                    if (sign > 0) push(ws.psq_add[c], &ws.n_psq_add[c], kPsqDeltaCap, idx);
-                    else push(ws.psq_sub[c], &ws.n_psq_sub[c], kPsqDeltaCap, idx);
-                } else if (sign > 0) {
-                    push(ws.thr_add[c], &ws.n_thr_add[c], kThrListCap, idx);
-                } else {
-                    push(ws.thr_sub[c], &ws.n_thr_sub[c], kThrListCap, idx);
-                }
+                const uint32_t entry = sign > 0 ? idx : idx | kSubFlag;
+                if (kind == 0) push(ws.psq_delta[c], &ws.n_psq_delta[c], kPsqDeltaCap, entry);
+                else push(ws.thr_delta[c], &ws.n_thr_delta[c], kThrDeltaCap, entry);
             };
             /* lane j < |D| finds the j-th changed square once; items fetch theirs by shuffle */
             const int n_changed = __popcll(changed);
@@ -219,9 +217,8 @@ __device__ __forceinline__ int build_lists(
         __syncwarp();
         int overflow = 0;
         for (int c = 0; c < 2; ++c) {
-            const int psq_cap = ((rebuild >> c) & 1) ? kPsqListCap : kPsqDeltaCap;
-            if (ws.n_thr_add[c] > kThrListCap || ws.n_thr_sub[c] > kThrListCap || ws.n_psq_add[c] > psq_cap
-                || ws.n_psq_sub[c] > kPsqDeltaCap)
+            if (ws.n_thr_add[c] > kThrListCap || ws.n_psq_add[c] > kPsqListCap || ws.n_thr_delta[c] > kThrDeltaCap
+                || ws.n_psq_delta[c] > kPsqDeltaCap)
                 overflow |= 1 << c;
         }
         if (!overflow) return rebuild;
@@ -262,19 +259,6 @@ __device__ __forceinline__ void add_psq(uint32_t (&v)[16], const uint4 (&c)[4]) 
         v[k * 4 + 1] = __vadd2(v[k * 4 + 1], c[k].y);
         v[k * 4 + 2] = __vadd2(v[k * 4 + 2], c[k].z);
         v[k * 4 + 3] = __vadd2(v[k * 4 + 3], c[k].w);
-    }
-}
-
-/* threat row (biased bytes) straight into packed int16 registers: used for the few delta rows */
-__device__ __forceinline__ void add_thr_packed(uint32_t (&v)[16], const uint4 (&c)[2]) {
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const uint32_t w[4] = {c[u].x, c[u].y, c[u].z, c[u].w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            v[(2 * u) * 4 + t] = __vadd2(v[(2 * u) * 4 + t], even_bytes(w[t]));
-            v[(2 * u + 1) * 4 + t] = __vadd2(v[(2 * u + 1) * 4 + t], odd_bytes(w[t]));
-        }
     }
 }
 
@@ -341,44 +325,64 @@ __device__ __noinline__ void rebuild_perspective_cold(
     for (int i = 0; i < 16; ++i) out[i] = v[i];
 }
 
-/* Advance one perspective by its delta lists: v += adds - subs.  Added and subtracted rows are
- * fetched in lock-step (equal row counts on both sides, so the +128 biases cancel). */
+/* Advance one perspective by its signed delta lists.  A subtracted row is added complemented:
+ * PSQ words ~w = -w - 1 per int16, biased threat bytes ~b = (-s) + 127, so one accumulator serves both
+ * signs and the constant offsets (+1 per subtracted PSQ row, 128 per added and 127 per subtracted
+ * threat row, zero-row top-ups counting as added) are removed once at the end. */
 __device__ __forceinline__ void update_perspective(const DeviceNet& net, const WarpScratch& ws, int c, int lane, uint32_t (&v)[16]) {
-    uint32_t neg[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) neg[i] = 0;
-    const int n_pa = ws.n_psq_add[c], n_ps = ws.n_psq_sub[c];
+    const int n_psq = ws.n_psq_delta[c];
+    int psq_subs = 0;
 #pragma unroll 1
-    for (int i = 0; i < max(n_pa, n_ps); i += kPsqGroupDelta) {
-        uint4 ca[kPsqGroupDelta][4], cs[kPsqGroupDelta][4];
+    for (int i = 0; i < n_psq; i += kPsqGroupDelta) {
+        uint4 rows[kPsqGroupDelta][4];
+        uint32_t mask[kPsqGroupDelta];
 #pragma unroll
         for (int j = 0; j < kPsqGroupDelta; ++j) {
-            load_psq_row(net, i + j < n_pa ? ws.psq_add[c][i + j] : static_cast<uint32_t>(kPsqZeroRow), lane, ca[j]);
-            load_psq_row(net, i + j < n_ps ? ws.psq_sub[c][i + j] : static_cast<uint32_t>(kPsqZeroRow), lane, cs[j]);
+            const uint32_t e = i + j < n_psq ? ws.psq_delta[c][i + j] : static_cast<uint32_t>(kPsqZeroRow);
+            mask[j] = static_cast<uint32_t>(static_cast<int32_t>(e) >> 31);
+            psq_subs += mask[j] & 1;
+            load_psq_row(net, e & ~kSubFlag, lane, rows[j]);
         }
 #pragma unroll
-        for (int j = 0; j < kPsqGroupDelta; ++j) {
-            add_psq(v, ca[j]);
-            add_psq(neg, cs[j]);
-        }
+        for (int j = 0; j < kPsqGroupDelta; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[k * 4 + 0] = __vadd2(v[k * 4 + 0], rows[j][k].x ^ mask[j]);
+                v[k * 4 + 1] = __vadd2(v[k * 4 + 1], rows[j][k].y ^ mask[j]);
+                v[k * 4 + 2] = __vadd2(v[k * 4 + 2], rows[j][k].z ^ mask[j]);
+                v[k * 4 + 3] = __vadd2(v[k * 4 + 3], rows[j][k].w ^ mask[j]);
+            }
     }
-    const int n_ta = ws.n_thr_add[c], n_ts = ws.n_thr_sub[c];
+    const int n_thr = ws.n_thr_delta[c];
+    int thr_rows = 0, thr_subs = 0;
 #pragma unroll 1
-    for (int i = 0; i < max(n_ta, n_ts); i += kThrGroupDelta) {
-        uint4 ca[kThrGroupDelta][2], cs[kThrGroupDelta][2];
+    for (int i = 0; i < n_thr; i += kThrGroupDelta) {
+        uint4 rows[kThrGroupDelta][2];
+        uint32_t mask[kThrGroupDelta];
 #pragma unroll
         for (int j = 0; j < kThrGroupDelta; ++j) {
-            load_thr_row(net, i + j < n_ta ? ws.thr_add[c][i + j] : static_cast<uint32_t>(kThrZeroRow), lane, ca[j]);
-            load_thr_row(net, i + j < n_ts ? ws.thr_sub[c][i + j] : static_cast<uint32_t>(kThrZeroRow), lane, cs[j]);
+            const uint32_t e = i + j < n_thr ? ws.thr_delta[c][i + j] : static_cast<uint32_t>(kThrZeroRow);
+            mask[j] = static_cast<uint32_t>(static_cast<int32_t>(e) >> 31);
+            thr_subs += mask[j] & 1;
+            load_thr_row(net, e & ~kSubFlag, lane, rows[j]);
         }
 #pragma unroll
-        for (int j = 0; j < kThrGroupDelta; ++j) {
-            add_thr_packed(v, ca[j]);
-            add_thr_packed(neg, cs[j]);
-        }
+        for (int j = 0; j < kThrGroupDelta; ++j)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const uint32_t w[4] = {rows[j][u].x ^ mask[j], rows[j][u].y ^ mask[j], rows[j][u].z ^ mask[j], rows[j][u].w ^ mask[j]};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    v[(2 * u) * 4 + t] = __vadd2(v[(2 * u) * 4 + t], even_bytes(w[t]));
+                    v[(2 * u + 1) * 4 + t] = __vadd2(v[(2 * u + 1) * 4 + t], odd_bytes(w[t]));
+                }
+            }
+        thr_rows += kThrGroupDelta;
     }
+    const int offset = psq_subs - 128 * (thr_rows - thr_subs) - 127 * thr_subs;
+    const uint32_t corr = (static_cast<uint32_t>(offset) & 0xFFFFu) * 0x10001u;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __vsub2(v[i], neg[i]);
+    for (int i = 0; i < 16; ++i) v[i] = __vadd2(v[i], corr);
 }
 
 /* activateFt, multilayer.h:92-152, on packed pairs: out = (clamp(a,0,255) * clamp(d,0,255)) >> 9.
@@ -389,16 +393,17 @@ __device__ __forceinline__ uint4 activate(const uint32_t (&v)[16]) {
     uint32_t out[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-        uint32_t word = 0;
+        uint32_t pair[2];
 #pragma unroll
         for (int par = 0; par < 2; ++par) {
             const uint32_t a = __vmins2(__vmaxs2(v[par * 4 + t], 0u), 0x00FF00FFu);
             const uint32_t d = __vmins2(__vmaxs2(v[(2 + par) * 4 + t], 0u), 0x00FF00FFu);
-            const uint32_t lo = ((a & 0xFFFFu) * (d & 0xFFFFu)) >> 9; /* element 4t + par     -> byte par     */
-            const uint32_t hi = ((a >> 16) * (d >> 16)) >> 9;         /* element 4t + par + 2 -> byte par + 2 */
-            word |= lo << (8 * par) | hi << (8 * par + 16);
+            /* d's bytes are (d_lo, 0, d_hi, 0): dp2a.lo multiplies a's halves by bytes 0 and 1 */
+            const uint32_t lo = __dp2a_lo(a, d, 0u);      /* a_lo * d_lo : element 4t + par     */
+            const uint32_t hi = __dp2a_lo(a, d >> 8, 0u); /* a_hi * d_hi : element 4t + par + 2 */
+            pair[par] = ((hi << 16 | lo) >> 9) & 0x007F007Fu; /* both products < 2^16, >> 9 leaves 7 bits */
         }
-        out[t] = word;
+        out[t] = pair[0] | pair[1] << 8; /* bytes: 4t, 4t+1, 4t+2, 4t+3 */
     }
     return make_uint4(out[0], out[1], out[2], out[3]);
 }
@@ -560,13 +565,15 @@ __global__ void __launch_bounds__(kThreads, SP_GAMES_MIN_BLOCKS)
 ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const uint32_t* __restrict__ game_start,
                 uint32_t n_games, uint8_t* __restrict__ act, uint8_t* __restrict__ bucket, DeviceStatus* status) {
     __shared__ WarpScratch scratch[kWarpsPerCta];
+    __shared__ uint32_t parked[kWarpsPerCta][16][32]; /* one perspective's registers, parked between passes */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& ws = scratch[warp];
     const FeatureTables& t = *net.tables;
     const uint32_t stride = gridDim.x * kWarpsPerCta;
     for (uint32_t g = blockIdx.x * kWarpsPerCta + warp; g < n_games; g += stride) {
         const size_t first = game_start[g], last = game_start[g + 1];
-        uint32_t v[2][16];
+        uint32_t v[16];
+        int in_regs = 0; /* which perspective `v` currently holds */
         BoardView prev{};
         bool have_prev = false;
         /* the next record is fetched one ply ahead so its latency hides behind this ply's work */
@@ -597,25 +604,30 @@ ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const u
                 have_prev = false; /* the next good board restarts the chain */
                 continue;
             }
-            /* one copy of the loop body: v[0] is always "the perspective being advanced", the two
-             * register sets swap places after each pass */
+            /* One copy of the loop body.  `v` holds the perspective being advanced, the other one is
+             * parked in shared memory; they swap once per ply and the order alternates, so that each
+             * ply starts with the perspective that is already in registers. */
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
+            for (int pass = 0; pass < 2; ++pass) {
+                const int c = in_regs;
                 if ((rebuild >> c) & 1) {
                     uint32_t fresh[16];
                     rebuild_perspective_cold(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, fresh);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[0][i] = fresh[i];
+                    for (int i = 0; i < 16; ++i) v[i] = fresh[i];
                 } else {
-                    update_perspective(net, ws, c, lane, v[0]);
+                    update_perspective(net, ws, c, lane, v);
                 }
                 const int half = c == d.view.stm ? 0 : 1;
-                reinterpret_cast<uint4*>(act + pos * SP_L1_SIZE)[half * 32 + lane] = activate(v[0]);
+                reinterpret_cast<uint4*>(act + pos * SP_L1_SIZE)[half * 32 + lane] = activate(v);
+                if (pass == 0) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t tmp = v[0][i];
-                    v[0][i] = v[1][i];
-                    v[1][i] = tmp;
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t other = parked[warp][i][lane];
+                        parked[warp][i][lane] = v[i];
+                        v[i] = other;
+                    }
+                    in_regs ^= 1;
                 }
             }
             if (lane == 0) bucket[pos] = static_cast<uint8_t>(output_bucket(d.view.occ));
@@ -638,17 +650,24 @@ constexpr int kHeadWarps = 4;
 constexpr int kSkipStride = 65; /* int32 words per row, padded against bank conflicts */
 
 /*
- * The contraction index k may be visited in any order as long as A and B agree.  Per 64-wide
+ * L1: the contraction index k may be visited in any order as long as A and B agree.  Per 64-wide
  * k-step, lane (g = lane / 4, t = lane % 4) loads 16 contiguous activation bytes of rows g and
  * g + 8 (k = 64 s + 16 t ...) and, for each of the 4 k-quads inside them, 16 contiguous weight
  * bytes = outputs 4 g .. 4 g + 3 of that quad ([k/4][o][k%4] layout, multilayer.h:180-196).  MMA
  * column g of n-tile nt is therefore output o = 4 g + nt, and the C fragment of lane (g, t)
  * holds outputs 8 t + nt and 8 t + 4 + nt of rows g and g + 8.
+ *
+ * L2 / L3: lane p owns L2 outputs p and p + 32 for all 16 rows of the tile; per input i it needs two
+ * weights (one coalesced 128-byte load per half across the warp) and the 16 rows' inputs (four
+ * broadcast LDS.128 from the transposed l2in[i][row] array).  The L3 dot product is closed with one
+ * REDUX per row.  Rows of different output buckets are handled by looping over the buckets present
+ * in the tile (normally one) and keeping each row's result from its own bucket's pass.
  */
 __global__ void __launch_bounds__(kHeadWarps * 32)
 head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __restrict__ bucket, size_t n,
             int32_t* __restrict__ out) {
-    __shared__ int skip[kHeadWarps][16][kSkipStride];
+    __shared__ int skip[kHeadWarps][16][kSkipStride];                   /* L1 output incl. the squared half: L3's skip input */
+    __shared__ __align__(16) int l2in[kHeadWarps][2 * SP_L2_SIZE][16];  /* skip >> 6, transposed: [input][row] */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const size_t tile = static_cast<size_t>(blockIdx.x) * kHeadWarps + warp;
@@ -658,16 +677,15 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
     const size_t r0 = min(base + g, last), r1 = min(base + g + 8, last);
     /* buckets of the 16 rows: lane i < 16 holds row i's */
     int my_bucket = 0xFF;
-    if (lane < 16) my_bucket = bucket[min(base + lane, last)];
+    if (lane < 16 && base + lane < n) my_bucket = bucket[base + lane];
     const int b0 = __shfl_sync(kFull, my_bucket, g), b1 = __shfl_sync(kFull, my_bucket, g + 8);
-    unsigned present = __reduce_or_sync(kFull, my_bucket < SP_OUTPUT_BUCKETS ? 1u << my_bucket : 0u);
+    const unsigned present = __reduce_or_sync(kFull, my_bucket < SP_OUTPUT_BUCKETS ? 1u << my_bucket : 0u);
 
     const uint4* a_row0 = reinterpret_cast<const uint4*>(act + r0 * SP_L1_SIZE) + t;
     const uint4* a_row1 = reinterpret_cast<const uint4*>(act + r1 * SP_L1_SIZE) + t;
 
-    while (present) {
-        const int b = __ffs(present) - 1;
-        present &= present - 1;
+    for (unsigned todo = present; todo; todo &= todo - 1) {
+        const int b = __ffs(todo) - 1;
         int c[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -706,60 +724,56 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
                     sq = min(sq, 16777216);
                     skip[warp][r][o] = cr << 6;
                     skip[warp][r][SP_L2_SIZE + o] = sq >> 6;
+                    l2in[warp][o][r] = cr;                    /* (cr << 6) >> 6 */
+                    l2in[warp][SP_L2_SIZE + o][r] = sq >> 12; /* (sq >> 6) >> 6 */
                 }
         }
     }
     __syncwarp();
 
-    /* L2 + L3: lanes 2r, 2r+1 share row r; each owns 32 of the 64 L2 outputs. multilayer.h:261-447 */
-    const int r = lane >> 1, half = lane & 1;
-    const size_t pos = base + r;
-    const int rb = __shfl_sync(kFull, my_bucket, r);
-    const bool valid = pos < n && rb < SP_OUTPUT_BUCKETS;
-    const int wb = valid ? rb : 0;
-    uint32_t acc[32];
-    {
-        const int4* bias = reinterpret_cast<const int4*>(net.l2_b + wb * SP_L3_SIZE + half * 32);
+    /* L2 + L3, multilayer.h:261-447 */
+    int32_t result = INT32_MIN;
+    for (unsigned todo = present; todo; todo &= todo - 1) {
+        const int b = __ffs(todo) - 1;
+        uint32_t acc[16][2];
+        {
+            const uint32_t bias0 = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + lane));
+            const uint32_t bias1 = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + lane + 32));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int4 v = __ldg(bias + i);
-            acc[4 * i] = v.x, acc[4 * i + 1] = v.y, acc[4 * i + 2] = v.z, acc[4 * i + 3] = v.w;
+            for (int r = 0; r < 16; ++r) acc[r][0] = bias0, acc[r][1] = bias1;
         }
-    }
-    const int* srow = skip[warp][r];
-    if (valid) {
-        const int4* w2 = reinterpret_cast<const int4*>(net.l2_w + static_cast<size_t>(wb) * 2 * SP_L2_SIZE * SP_L3_SIZE + half * 32);
-#pragma unroll 2
+        const int* w2 = net.l2_w + static_cast<size_t>(b) * 2 * SP_L2_SIZE * SP_L3_SIZE + lane;
+#pragma unroll 4
         for (int i = 0; i < 2 * SP_L2_SIZE; ++i) {
-            const uint32_t in = static_cast<uint32_t>(srow[i] >> 6);
+            const uint32_t w0 = static_cast<uint32_t>(__ldg(w2 + i * SP_L3_SIZE));
+            const uint32_t w1 = static_cast<uint32_t>(__ldg(w2 + i * SP_L3_SIZE + 32));
+            const int4* in4 = reinterpret_cast<const int4*>(l2in[warp][i]);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int4 v = __ldg(w2 + i * (SP_L3_SIZE / 4) + q);
-                acc[4 * q] += in * static_cast<uint32_t>(v.x);
-                acc[4 * q + 1] += in * static_cast<uint32_t>(v.y);
-                acc[4 * q + 2] += in * static_cast<uint32_t>(v.z);
-                acc[4 * q + 3] += in * static_cast<uint32_t>(v.w);
+            for (int q = 0; q < 4; ++q) {
+                const int4 v = in4[q];
+                const uint32_t in[4] = {static_cast<uint32_t>(v.x), static_cast<uint32_t>(v.y), static_cast<uint32_t>(v.z), static_cast<uint32_t>(v.w)};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc[q * 4 + e][0] += in[e] * w0;
+                    acc[q * 4 + e][1] += in[e] * w1;
+                }
             }
         }
-    }
-    uint32_t l3 = 0;
-    if (valid) {
-        const int* w3 = net.l3_w + wb * SP_L3_SIZE + half * 32;
+        const uint32_t w3_0 = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + lane));
+        const uint32_t w3_1 = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + lane + 32));
+        const uint32_t bias3 = static_cast<uint32_t>(__ldg(net.l3_b + b));
 #pragma unroll
-        for (int p = 0; p < 32; ++p) {
-            const int cl = min(max(static_cast<int>(acc[p]), 0), 262144);
-            l3 += (static_cast<uint32_t>(cl) + static_cast<uint32_t>(srow[half * 32 + p])) * static_cast<uint32_t>(__ldg(w3 + p));
+        for (int r = 0; r < 16; ++r) {
+            const int c0 = min(max(static_cast<int>(acc[r][0]), 0), 262144);
+            const int c1 = min(max(static_cast<int>(acc[r][1]), 0), 262144);
+            const uint32_t part = (static_cast<uint32_t>(c0) + static_cast<uint32_t>(skip[warp][r][lane])) * w3_0
+                                + (static_cast<uint32_t>(c1) + static_cast<uint32_t>(skip[warp][r][lane + 32])) * w3_1;
+            const uint32_t l3 = __reduce_add_sync(kFull, part) + bias3;
+            if (lane == r && my_bucket == b)
+                result = static_cast<int32_t>(static_cast<int64_t>(static_cast<int32_t>(l3)) * 400 / 16777216); /* truncates toward zero */
         }
     }
-    l3 += __shfl_xor_sync(kFull, l3, 1);
-    if (half == 0 && pos < n) {
-        int32_t result = INT32_MIN;
-        if (valid) {
-            const int32_t sum = static_cast<int32_t>(l3 + static_cast<uint32_t>(__ldg(net.l3_b + wb)));
-            result = static_cast<int32_t>(static_cast<int64_t>(sum) * 400 / 16777216); /* truncates toward zero */
-        }
-        out[pos] = result;
-    }
+    if (lane < 16 && base + lane < n) out[base + lane] = result;
 }
 
 int grid_for(size_t n_warp_items, int warps_per_cta, int sm_count, int ctas_per_sm) {
