@@ -200,16 +200,15 @@ def workload_config(workload: str, **extra):
 
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
-    import torch.distributed as dist
 
     from stormphrax_b200 import api
+    from stormphrax_b200 import dist as D
     from stormphrax_b200 import net as N
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the evaluator has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    D.init("nccl", local_rank)
 
     boards, moves, starts = make_workload(rank, POSITIONS_PER_GPU)
     n = len(boards)
@@ -245,8 +244,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        D.barrier()
         torch.cuda.synchronize()
 
     def timed(step, steps):
@@ -259,11 +257,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             step()
             b.record(stream)
         barrier()
-        total_ms = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return D.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
 
     # warm-up (also verifies results once against the CPU checker on rank 0)
     for _ in range(max(args.warmup, 3)):
@@ -285,9 +279,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         e2e_ms = timed(host_step, args.steps)
     clock_summary = clocks.summary()
 
-    counters = torch.from_numpy(ctx.counters().astype(np.int64)).cuda()
-    if world > 1:
-        dist.all_reduce(counters, op=dist.ReduceOp.SUM)  # the one collective this path has: reporting counters
+    counters = D.allreduce_counters(ctx.counters())  # the one collective this path has: reporting counters (NCCL)
 
     ms_per_step = total_ms / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e6
@@ -303,7 +295,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             # 2*(n_psq*2048 + n_thr*1024) + 2048 (bias) + record + eval, per position
             bytes_per_pos = (counts["psq_rows"] * 2048 + (counts["threat_rows"] + counts["pawn_pair_rows"]) * 1024) / n + 2048 + 32 + 4
         else:
-            bytes_per_pos = 41.5e3  # SURVEY 8(d) incremental figure; refined by the playout statistics below
+            # SURVEY 8(d) incremental formula per perspective: delta rows + read and write of the PSQ and
+            # threat accumulators (2 x 2048 B each way); rebuilt perspectives read their full row lists
+            st = api.playout_stats(boards, starts)
+            bytes_per_pos = (st["psq_delta_rows"] * 2048 + st["threat_delta_rows"] * 1024 + st["rebuild_psq_rows"] * 2048
+                             + st["rebuild_threat_rows"] * 1024 + st["updated_perspectives"] * 2 * 4096
+                             + st["rebuilt_perspectives"] * 4096) / n + 32 + 4
         algo_bytes_per_launch = bytes_per_pos * n * args.steps / max(k_launches, 1)
         avg_launch_ms = k_ms / max(k_launches, 1)
         achieved = algo_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms else 0.0
@@ -329,6 +326,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "config": workload_config(
                 args.workload,
                 mean_rows_per_perspective={k: v / n / 2 for k, v in counts.items()},
+                playout_stats_per_position=({k: v / n for k, v in st.items()} if args.workload == "playouts" else None),
             ),
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_rate / 1e6, "unit": UNIT, **{k: cpu_info[k] for k in ("cores", "kind", "sample", "isa")}},
@@ -343,6 +341,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
+        import torch.distributed as dist
+
         dist.barrier()
         dist.destroy_process_group()
 

@@ -186,6 +186,10 @@ int sp_host_features(const SpPackedBoard* board, int perspective, int kind, uint
 /* Workload statistics for the roofline: out[0] = PSQ rows, out[1] = threat rows, out[2] = pawn-pair
  * rows, summed over both perspectives of all n boards (what a full refresh must read). */
 int sp_host_feature_counts(const SpPackedBoard* boards, size_t n, int threads, uint64_t out[3]);
+/* The same for the incremental walker over a playout stream: out = {PSQ delta rows, threat delta rows,
+ * PSQ rows of rebuilt perspectives, threat rows of rebuilt perspectives, updated perspectives,
+ * rebuilt perspectives}, counted with the delta generator the kernels run (csrc/sp_delta.h). */
+int sp_host_playout_stats(const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, int threads, uint64_t out[6]);
 int sp_host_feature_delta(
     const SpPackedBoard* before,
     const SpPackedBoard* after,

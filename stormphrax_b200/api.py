@@ -47,6 +47,7 @@ SIGNATURES = {
     "sp_nnue_profile": (C.c_int, [_vp, C.c_int]),
     "sp_nnue_profile_read": (C.c_int, [_vp, _vp, _vp]),
     "sp_host_feature_counts": (C.c_int, [_vp, _sz, C.c_int, _vp]),
+    "sp_host_playout_stats": (C.c_int, [_vp, _vp, C.c_uint32, C.c_int, _vp]),
     "sp_nnue_eval_full": (C.c_int, [_vp, _vp, _sz, _vp]),
     "sp_nnue_eval_full_device": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
     "sp_nnue_slots_reserve": (C.c_int, [_vp, _sz]),
@@ -315,6 +316,19 @@ def feature_counts(boards, threads: int = 0) -> dict:
     if rc:
         raise NnueError(rc, "bad board")
     return {"psq_rows": int(out[0]), "threat_rows": int(out[1]), "pawn_pair_rows": int(out[2])}
+
+
+def playout_stats(boards, game_start, threads: int = 0) -> dict:
+    """Rows the incremental walker must read for a playout stream (see sp_host_playout_stats)."""
+    boards = _boards(boards)
+    game_start = np.ascontiguousarray(game_start, dtype=np.uint32)
+    out = np.zeros(6, dtype=np.uint64)
+    rc = lib().sp_host_playout_stats(boards.ctypes.data, game_start.ctypes.data, game_start.size - 1,
+                                     threads or min(os.cpu_count() or 1, 32), out.ctypes.data)
+    if rc:
+        raise NnueError(rc, "bad board")
+    keys = ["psq_delta_rows", "threat_delta_rows", "rebuild_psq_rows", "rebuild_threat_rows", "updated_perspectives", "rebuilt_perspectives"]
+    return {k: int(v) for k, v in zip(keys, out)}
 
 
 def feature_delta(before, after, perspective: int):

@@ -218,6 +218,57 @@ int sp_host_feature_counts(const SpPackedBoard* boards, size_t n, int threads, u
     return bad ? SP_ERR_BAD_BOARD : SP_OK;
 }
 
+/* What the incremental walker must read for a playout stream (roofline bookkeeping): per perspective
+ * of every board either the delta rows against the previous board of its game, or -- first board of
+ * a game / king changed bucket or side / too many changed squares -- its full row lists.
+ * out = {psq_delta_rows, threat_delta_rows, rebuild_psq_rows, rebuild_threat_rows,
+ *        updated_perspectives, rebuilt_perspectives}. */
+int sp_host_playout_stats(const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, int threads, uint64_t out[6]) {
+    if (threads < 1) threads = 1;
+    std::vector<std::array<uint64_t, 7>> part(static_cast<size_t>(threads), {0, 0, 0, 0, 0, 0, 0});
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        pool.emplace_back([&, t] {
+            auto& p = part[static_cast<size_t>(t)];
+            for (uint32_t g = static_cast<uint32_t>(t); g < n_games; g += static_cast<uint32_t>(threads)) {
+                Board prev{}, cur{};
+                for (uint32_t i = game_start[g]; i < game_start[g + 1]; ++i) {
+                    if (unpack_board(boards[i], cur)) {
+                        p[6] = 1;
+                        continue;
+                    }
+                    const bool first = i == game_start[g];
+                    const uint64_t changed = first ? 0 : changed_squares(prev, cur);
+                    for (int c = 0; c < 2; ++c) {
+                        const bool rebuild = first || popcount64(changed) > kMaxChanged || needs_refresh(tables(), prev, cur, c);
+                        if (rebuild) {
+                            ++p[5];
+                            for (int sq = 0; sq < 64; ++sq) {
+                                square_psq_features(tables(), cur, sq, [&](int pc, uint32_t) { p[2] += pc == c; });
+                                square_threat_features(tables(), cur, sq, [&](int pc, uint32_t) { p[3] += pc == c; });
+                            }
+                        } else {
+                            ++p[4];
+                            delta_all(tables(), prev, cur, changed, [&](int pc, int kind, int, uint32_t) {
+                                if (pc == c) ++p[kind == 0 ? 0 : 1];
+                            });
+                        }
+                    }
+                    prev = cur;
+                }
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    bool bad = false;
+    for (int k = 0; k < 6; ++k) out[k] = 0;
+    for (const auto& p : part) {
+        for (int k = 0; k < 6; ++k) out[k] += p[static_cast<size_t>(k)];
+        bad |= p[6] != 0;
+    }
+    return bad ? SP_ERR_BAD_BOARD : SP_OK;
+}
+
 /* Feature deltas between two boards for perspective c, computed by the shared delta generator
  * (sp_delta.h) on the CPU. Returns 0, or 1 if the perspective needs a full refresh. */
 int sp_host_feature_delta(
