@@ -30,10 +30,17 @@ struct SpNnue {
     DeviceStatus* d_status = nullptr;
     DeviceStatus* h_status = nullptr; /* pinned */
 
-    /* scratch for one chunk of positions */
+    /* scratch for one chunk of positions, double-buffered: the head of chunk i runs on `aux` while the
+     * feature transformer of chunk i + 1 runs on the caller's stream */
     size_t chunk = 32768;
-    uint8_t* d_act = nullptr;
-    uint8_t* d_bucket = nullptr;
+    uint32_t games_chunk = 4736; /* playout walker: games per launch (2 per resident warp) */
+    uint8_t* d_act2[2] = {nullptr, nullptr};
+    uint8_t* d_bucket2[2] = {nullptr, nullptr};
+    uint8_t* d_act = nullptr;    /* = d_act2[0] */
+    uint8_t* d_bucket = nullptr; /* = d_bucket2[0] */
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_ft[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr}, ev_join = nullptr;
+    bool overlap = true;
     /* whole-stream scratch of the playout walker (one activation row per board) */
     uint8_t* d_act_big = nullptr;
     uint8_t* d_bucket_big = nullptr;
@@ -224,19 +231,36 @@ struct Timed {
     }
 };
 
-/* boards (device) -> out (device), in chunks that keep the activation scratch L2-sized */
+/* boards (device) -> out (device), in chunks that keep the activation scratch L2-sized.  The dense
+ * head of chunk i (latency-bound, low occupancy) runs on the auxiliary stream underneath the feature
+ * transformer of chunk i + 1; everything is ordered with events, the host never waits. */
 int eval_full_device(SpNnue* ctx, const SpPackedBoard* d_boards, size_t n, int32_t* d_out, cudaStream_t stream) {
-    for (size_t off = 0; off < n; off += ctx->chunk) {
+    const bool overlap = ctx->overlap && n > ctx->chunk;
+    size_t i = 0;
+    for (size_t off = 0; off < n; off += ctx->chunk, ++i) {
         const size_t m = std::min(ctx->chunk, n - off);
+        const int buf = overlap ? static_cast<int>(i & 1) : 0;
+        if (overlap && i >= 2) SP_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_head[buf], 0)); /* scratch is free again */
         {
             Timed timed{ctx, stream, SP_KERNEL_FT_FULL};
-            launch_ft_full(ctx->net, d_boards + off, m, ctx->d_act, ctx->d_bucket, ctx->d_status, ctx->sm_count, stream);
+            launch_ft_full(ctx->net, d_boards + off, m, ctx->d_act2[buf], ctx->d_bucket2[buf], ctx->d_status, ctx->sm_count, stream);
+        }
+        cudaStream_t hs = stream;
+        if (overlap) {
+            SP_CUDA(ctx, cudaEventRecord(ctx->ev_ft[buf], stream));
+            SP_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_ft[buf], 0));
+            hs = ctx->aux;
         }
         {
-            Timed timed{ctx, stream, SP_KERNEL_HEAD};
-            launch_head(ctx->net, ctx->d_act, ctx->d_bucket, m, d_out + off, ctx->d_status, ctx->sm_count, stream);
+            Timed timed{ctx, hs, SP_KERNEL_HEAD};
+            launch_head(ctx->net, ctx->d_act2[buf], ctx->d_bucket2[buf], m, d_out + off, nullptr, ctx->d_status, ctx->sm_count, hs);
         }
+        if (overlap) SP_CUDA(ctx, cudaEventRecord(ctx->ev_head[buf], ctx->aux));
         ctx->counters[SP_CTR_LAUNCHES] += 2;
+    }
+    if (overlap) { /* join: later work on `stream` sees every result */
+        SP_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux));
+        SP_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_join, 0));
     }
     ctx->counters[SP_CTR_EVALS] += n;
     ctx->counters[SP_CTR_FULL_REFRESH] += 2 * n;
@@ -290,8 +314,21 @@ int sp_nnue_create(const void* net_image, size_t len, int device, SpNnue** out) 
     SP_CUDA(nullptr, cudaMalloc(&ctx->d_status, sizeof(DeviceStatus)));
     SP_CUDA(nullptr, cudaMemset(ctx->d_status, 0, sizeof(DeviceStatus)));
     SP_CUDA(nullptr, cudaMallocHost(&ctx->h_status, sizeof(DeviceStatus)));
-    SP_CUDA(nullptr, cudaMalloc(&ctx->d_act, ctx->chunk * SP_L1_SIZE));
-    SP_CUDA(nullptr, cudaMalloc(&ctx->d_bucket, ctx->chunk));
+    if (const char* env = std::getenv("SP_NNUE_GAMES_CHUNK")) {
+        const long v = std::atol(env);
+        if (v >= 1) ctx->games_chunk = static_cast<uint32_t>(v);
+    }
+    if (const char* env = std::getenv("SP_NNUE_OVERLAP")) ctx->overlap = std::atoi(env) != 0;
+    for (int b = 0; b < 2; ++b) {
+        SP_CUDA(nullptr, cudaMalloc(&ctx->d_act2[b], ctx->chunk * SP_L1_SIZE));
+        SP_CUDA(nullptr, cudaMalloc(&ctx->d_bucket2[b], ctx->chunk));
+        SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_ft[b], cudaEventDisableTiming));
+        SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_head[b], cudaEventDisableTiming));
+    }
+    SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    SP_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+    ctx->d_act = ctx->d_act2[0];
+    ctx->d_bucket = ctx->d_bucket2[0];
 
     uint8_t* b = ctx->d_net_blob;
     ctx->net.psq = reinterpret_cast<const uint4*>(b + L.psq);
@@ -315,8 +352,15 @@ void sp_nnue_destroy(SpNnue* ctx) {
     cudaFree(ctx->d_tables);
     cudaFree(ctx->d_status);
     cudaFreeHost(ctx->h_status);
-    cudaFree(ctx->d_act);
-    cudaFree(ctx->d_bucket);
+    if (ctx->aux) cudaStreamSynchronize(ctx->aux);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(ctx->d_act2[b]);
+        cudaFree(ctx->d_bucket2[b]);
+        if (ctx->ev_ft[b]) cudaEventDestroy(ctx->ev_ft[b]);
+        if (ctx->ev_head[b]) cudaEventDestroy(ctx->ev_head[b]);
+    }
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
     cudaFree(ctx->d_act_big);
     cudaFree(ctx->d_bucket_big);
     cudaFree(ctx->d_boards);
@@ -424,7 +468,7 @@ int sp_nnue_forward_device(SpNnue* ctx, const uint8_t* d_act, const uint8_t* d_b
     if (!d_act || !d_bucket || !d_out) return fail(ctx, SP_ERR_INVALID, "null argument");
     if (reinterpret_cast<uintptr_t>(d_act) & 15) return fail(ctx, SP_ERR_INVALID, "d_act must be 16-byte aligned");
     DeviceGuard guard{ctx->device};
-    launch_head(ctx->net, d_act, d_bucket, n, d_out, ctx->d_status, ctx->sm_count, pick(ctx, stream));
+    launch_head(ctx->net, d_act, d_bucket, n, d_out, nullptr, ctx->d_status, ctx->sm_count, pick(ctx, stream));
     ctx->counters[SP_CTR_LAUNCHES] += 1;
     ctx->counters[SP_CTR_EVALS] += n;
     SP_CUDA(ctx, cudaGetLastError());

@@ -665,13 +665,17 @@ constexpr int kSkipStride = 65; /* int32 words per row, padded against bank conf
  */
 __global__ void __launch_bounds__(kHeadWarps * 32)
 head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __restrict__ bucket, size_t n,
-            int32_t* __restrict__ out) {
+            int32_t* __restrict__ out, const uint32_t* __restrict__ range, uint32_t range_len) {
     __shared__ int skip[kHeadWarps][16][kSkipStride];                   /* L1 output incl. the squared half: L3's skip input */
     __shared__ __align__(16) int l2in[kHeadWarps][2 * SP_L2_SIZE][16];  /* skip >> 6, transposed: [input][row] */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const size_t tile = static_cast<size_t>(blockIdx.x) * kHeadWarps + warp;
-    const size_t base = tile * 16;
+    size_t base = tile * 16;
+    if (range) { /* positions [range[0], range[range_len]) */
+        base += range[0];
+        n = range[range_len];
+    }
     if (base >= n) return;
     const size_t last = n - 1;
     const size_t r0 = min(base + g, last), r1 = min(base + g + 8, last);
@@ -813,12 +817,12 @@ void launch_slot_activate(
 }
 
 void launch_head(
-    const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, DeviceStatus*, int,
-    cudaStream_t stream) {
+    const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, const uint32_t* range,
+    DeviceStatus*, int, cudaStream_t stream, uint32_t range_len) {
     if (!n) return;
     const size_t tiles = (n + 15) / 16;
     const unsigned grid = static_cast<unsigned>((tiles + kHeadWarps - 1) / kHeadWarps);
-    head_kernel<<<grid, kHeadWarps * 32, 0, stream>>>(net, act, bucket, n, out);
+    head_kernel<<<grid, kHeadWarps * 32, 0, stream>>>(net, act, bucket, n, out, range, range_len);
 }
 
 } // namespace sp::gpu

@@ -85,10 +85,12 @@ void launch_slot_activate(
     DeviceStatus* status, int sm_count, cudaStream_t stream);
 
 /* act[i], bucket[i] -> out[i] : L1 (int8 IMMA) + L2 + L3 + scale.  bucket[i] > 7 marks a
- * position whose board was rejected: out[i] = INT32_MIN. */
+ * position whose board was rejected: out[i] = INT32_MIN.
+ * range == nullptr: positions [0, n).  Otherwise positions [range[0], range[range_len]) read on the
+ * device (a span of a game_start array) and n is only an upper bound of their count for the grid. */
 void launch_head(
-    const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, DeviceStatus* status,
-    int sm_count, cudaStream_t stream);
+    const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, const uint32_t* range,
+    DeviceStatus* status, int sm_count, cudaStream_t stream, uint32_t range_len = 0);
 
 } // namespace sp::gpu
 
