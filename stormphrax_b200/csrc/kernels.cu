@@ -42,23 +42,29 @@ constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kPsqGroup = SP_PSQ_GROUP;      /* PSQ rows fetched per batch on the rebuild path (4 x LDG.128 each per lane) */
 constexpr int kThrGroupFull = SP_THR_GROUP;  /* threat rows per batch on the rebuild path (2 x LDG.128 each per lane) */
 constexpr int kPsqGroupDelta = 4;  /* delta rows per batch on the incremental path (16 x LDG.128) */
-constexpr int kThrGroupDelta = 4;  /* (8 x LDG.128) */
+constexpr int kThrGroupDelta = 4;  /* per sign: 4 added + 4 subtracted rows (16 x LDG.128) */
 constexpr int kPsqListCap = 40;    /* 32 pieces + bias row */
 constexpr int kPsqDeltaCap = 16;
-constexpr int kThrDeltaCap = 96;
+constexpr int kThrDeltaCap = 96;   /* added rows grow from the front, subtracted rows from the back */
 constexpr int kThrListCap = SP_MAX_THREAT_INDICES;
-constexpr uint32_t kSubFlag = 0x80000000u; /* delta list entry: subtract this row */
+constexpr int kTaskCap = 256;
+constexpr uint32_t kSubFlag = 0x80000000u;      /* PSQ delta list entry: subtract this row */
+constexpr uint32_t kTaskPawnPair = 1u << 31;    /* task = pawn pair (else attacker -> victim candidate) */
+constexpr uint32_t kTaskSub = 1u << 30;         /* feature of the predecessor board: subtract */
+constexpr uint32_t kTaskFull = 1u << 29;        /* from a whole-board enumeration: for rebuilt perspectives */
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 /* Per-warp shared memory. */
 struct WarpScratch {
+    uint32_t tasks[kTaskCap];              /* (attacker, victim) candidates and pawn pairs awaiting indexing */
     uint16_t thr_add[2][kThrListCap];      /* rebuild: every threat / pawn-pair row of the board */
-    uint32_t thr_delta[2][kThrDeltaCap];   /* update: changed rows, kSubFlag = subtract */
+    uint32_t thr_delta[2][kThrDeltaCap];   /* update: added rows [0, n_add), subtracted rows [cap - n_sub, cap) */
     uint16_t psq_add[2][kPsqListCap];      /* rebuild: one row per piece + the bias row */
-    uint32_t psq_delta[2][kPsqDeltaCap];   /* update */
+    uint32_t psq_delta[2][kPsqDeltaCap];   /* update: kSubFlag = subtract */
     uint8_t mailbox[2][64];                /* two boards: the one being evaluated and its predecessor */
     int n_thr_add[2];
-    int n_thr_delta[2];
+    int n_thr_dadd[2];
+    int n_thr_dsub[2];
     int n_psq_add[2];
     int n_psq_delta[2];
 };
@@ -147,18 +153,180 @@ __device__ __forceinline__ int nth_piece_square(uint64_t bits, int n) {
     return base + pos;
 }
 
-template <typename T>
-__device__ __forceinline__ void push(T* list, int* count, int cap, uint32_t value) {
-    const int at = atomicAdd(count, 1);
-    if (at < cap) list[at] = static_cast<T>(value);
+/* Append `task` from every lane where `valid` (ballot compaction, no atomics). Returns the new count. */
+__device__ __forceinline__ int enqueue(WarpScratch& ws, int n_tasks, bool valid, uint32_t task, int lane) {
+    const unsigned m = __ballot_sync(kFull, valid);
+    if (valid) {
+        const int at = n_tasks + __popc(m & ((1u << lane) - 1));
+        if (at < kTaskCap) ws.tasks[at] = task;
+    }
+    return n_tasks + __popc(m);
+}
+
+__device__ __forceinline__ uint32_t pawn_pair_task(int a_color, int asq, int b_color, int bsq) {
+    return static_cast<uint32_t>(asq | bsq << 8 | a_color << 16 | b_color << 24) | kTaskPawnPair;
+}
+
+/* Pawn-pair tasks: each lane holds a pawn square (or none) and the bitboard of its partners. */
+__device__ __forceinline__ int enqueue_pawn_pairs(
+    WarpScratch& ws, int n_tasks, const uint8_t* mailbox, int sq, int color, uint64_t partners, uint32_t flags, int lane) {
+#pragma unroll 1
+    while (__any_sync(kFull, partners != 0)) {
+        const bool valid = partners != 0;
+        uint32_t task = 0;
+        if (valid) {
+            const int o = lsb64(partners);
+            partners &= partners - 1;
+            task = pawn_pair_task(color, sq, mailbox[o] & 1, o) | flags;
+        }
+        n_tasks = enqueue(ws, n_tasks, valid, task, lane);
+    }
+    return n_tasks;
+}
+
+/* Whole-board enumeration (nnue_state.cpp:309-354, 440-449), lane-per-piece: eight uniform rounds, round k
+ * looks along ray k (sliders, pawns) or at knight offset k; then the pawn pairs. */
+template <typename Flush>
+__device__ __forceinline__ int enqueue_board(
+    const FeatureTables& t, const BoardView& b, int n_pieces, int rebuild, int lane, WarpScratch& ws, int n_tasks, Flush&& flush) {
+    const bool has = lane < n_pieces;
+    const int sq = has ? nth_piece_square(b.occ, lane) : 0;
+    const int piece = has ? b.mailbox[sq] : kNoPiece;
+    const int type = piece >> 1;
+    if (has) {
+        if (rebuild & 1) ws.psq_add[kBlack][lane] = static_cast<uint16_t>(psq_index(t, kBlack, piece, sq, b.king[kBlack]));
+        if (rebuild & 2) ws.psq_add[kWhite][lane] = static_cast<uint16_t>(psq_index(t, kWhite, piece, sq, b.king[kWhite]));
+    }
+    const bool attacker = has && type != kKing;
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        int target = kNoSquare;
+        if (attacker) {
+            if (type == kKnight) {
+                const int fx = (sq & 7) + static_cast<int>((0x10013443u >> (4 * k)) & 0xF) - 2;
+                const int ry = (sq >> 3) + static_cast<int>((0x43100134u >> (4 * k)) & 0xF) - 2;
+                if (fx >= 0 && fx < 8 && ry >= 0 && ry < 8) target = ry * 8 + fx;
+            } else {
+                uint64_t gap;
+                const int ahead = ray_first(t, b.occ, sq, k, gap);
+                if (ahead != kNoSquare && attacks_along(piece, k, gap == 0)) target = ahead;
+            }
+        }
+        int victim = kNoPiece;
+        if (target != kNoSquare) victim = b.mailbox[target];
+        const bool valid = victim != kNoPiece && (victim >> 1) != kKing;
+        n_tasks = enqueue(ws, n_tasks, valid, pack_candidate(piece, sq, victim, target) | kTaskFull, lane);
+        if (n_tasks > kTaskCap - 32) n_tasks = flush(n_tasks); /* the next round might not fit: index what is queued */
+    }
+    /* every unordered pawn pair within one file of each other, once: partner on a higher square */
+    const bool pawn = has && type == kPawn;
+    uint64_t partners = pawn ? (b.pawns[0] | b.pawns[1]) & pp_mask(sq) & squares_above(sq) : 0;
+#pragma unroll 1
+    while (__any_sync(kFull, partners != 0)) {
+        const bool valid = partners != 0;
+        uint32_t task = 0;
+        if (valid) {
+            const int o = lsb64(partners);
+            partners &= partners - 1;
+            task = pawn_pair_task(piece & 1, sq, b.mailbox[o] & 1, o) | kTaskFull;
+        }
+        n_tasks = enqueue(ws, n_tasks, valid, task, lane);
+        if (n_tasks > kTaskCap - 32) n_tasks = flush(n_tasks);
+    }
+    return n_tasks;
+}
+
+/* Changed-square enumeration (sp_delta.h): line items lane = unit * 8 + k, then one square item per unit. */
+__device__ __forceinline__ int enqueue_delta(
+    const FeatureTables& t, const BoardView& before, const BoardView& after, uint64_t changed, int rebuild, int lane,
+    WarpScratch& ws, int n_tasks, int (&n_psq_delta)[2]) {
+    const int n_changed = __popcll(changed);
+    const int my_changed = lane < n_changed ? nth_piece_square(changed, lane) : 0;
+    const int units = 2 * n_changed;
+#pragma unroll 1
+    for (int base = 0; base < units * kLineItemsPerUnit; base += 32) {
+        const int item = base + lane;
+        const int u = item >> 3;
+        const int s = __shfl_sync(kFull, my_changed, (u >> 1) & 31);
+        uint32_t c[4] = {0, 0, 0, 0};
+        unsigned valid = 0;
+        if (u < units) valid = delta_line_candidates(t, (u & 1) ? after : before, changed, s, item & 7, c);
+        const uint32_t flags = (u & 1) ? 0u : kTaskSub;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) n_tasks = enqueue(ws, n_tasks, (valid >> i) & 1, c[i] | flags, lane);
+    }
+    /* square items: lane = unit */
+    const int s = __shfl_sync(kFull, my_changed, (lane >> 1) & 31);
+    const BoardView& b = (lane & 1) ? after : before;
+    const int piece = lane < units ? b.mailbox[s] : kNoPiece;
+    const uint32_t sub = (lane & 1) ? 0u : kSubFlag;
+    const unsigned occupied = __ballot_sync(kFull, piece != kNoPiece);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if ((rebuild >> c) & 1) continue;
+        if (piece != kNoPiece) {
+            const int at = __popc(occupied & ((1u << lane) - 1));
+            if (at < kPsqDeltaCap) ws.psq_delta[c][at] = psq_index(t, c, piece, s, after.king[c]) | sub;
+        }
+        n_psq_delta[c] = __popc(occupied);
+    }
+    const bool pawn = piece != kNoPiece && (piece >> 1) == kPawn;
+    const uint64_t partners = pawn ? delta_pawn_partners(b, changed, s) : 0;
+    return enqueue_pawn_pairs(ws, n_tasks, b.mailbox, s, piece & 1, partners, (lane & 1) ? 0u : kTaskSub, lane);
+}
+
+/* Index the queued tasks, one (task, perspective) per lane, and compact the existing features into the
+ * row lists.  Kings of the current board orient both boards' features: a perspective whose king changed
+ * side or bucket is rebuilt, not updated (threats.cpp:170-221). */
+__device__ __forceinline__ void process_tasks(
+    const FeatureTables& t, const BoardView& b, int rebuild, int n_tasks, int lane, WarpScratch& ws, int (&n_full)[2],
+    int (&n_dadd)[2], int (&n_dsub)[2]) {
+    const int c = lane & 1;
+    const unsigned mine = (c ? 0xAAAAAAAAu : 0x55555555u) & ((1u << lane) - 1); /* earlier lanes of my perspective */
+    const bool rebuilt = (rebuild >> c) & 1;
+#pragma unroll 1
+    for (int base = 0; base < n_tasks; base += 16) {
+        const int i = base + (lane >> 1);
+        uint32_t task = 0;
+        int32_t idx = -1;
+        if (i < n_tasks) {
+            task = ws.tasks[i];
+            if (((task & kTaskFull) != 0) == rebuilt) {
+                const int sq0 = task & 0xFF, sq1 = (task >> 8) & 0xFF, p0 = (task >> 16) & 0xF, p1 = (task >> 24) & 0xF;
+                const int ksq = c ? b.king[1] : b.king[0];
+                idx = (task & kTaskPawnPair) ? static_cast<int32_t>(pp_index(c, ksq, p0, sq0, p1, sq1))
+                                             : threat_index(t, c, ksq, p0, sq0, p1, sq1);
+            }
+        }
+        const bool valid = idx >= 0;
+        const bool full = (task & kTaskFull) != 0, sub = (task & kTaskSub) != 0;
+        const unsigned mf = __ballot_sync(kFull, valid && full);
+        const unsigned ma = __ballot_sync(kFull, valid && !full && !sub);
+        const unsigned ms = __ballot_sync(kFull, valid && !full && sub);
+        if (valid) {
+            if (full) {
+                const int at = (c ? n_full[1] : n_full[0]) + __popc(mf & mine);
+                if (at < kThrListCap) ws.thr_add[c][at] = static_cast<uint16_t>(idx);
+            } else if (!sub) {
+                const int at = (c ? n_dadd[1] : n_dadd[0]) + __popc(ma & mine);
+                if (at < kThrDeltaCap) ws.thr_delta[c][at] = static_cast<uint32_t>(idx);
+            } else {
+                const int at = (c ? n_dsub[1] : n_dsub[0]) + __popc(ms & mine);
+                if (at < kThrDeltaCap) ws.thr_delta[c][kThrDeltaCap - 1 - at] = static_cast<uint32_t>(idx);
+            }
+        }
+        n_full[0] += __popc(mf & 0x55555555u), n_full[1] += __popc(mf & 0xAAAAAAAAu);
+        n_dadd[0] += __popc(ma & 0x55555555u), n_dadd[1] += __popc(ma & 0xAAAAAAAAu);
+        n_dsub[0] += __popc(ms & 0x55555555u), n_dsub[1] += __popc(ms & 0xAAAAAAAAu);
+    }
 }
 
 /*
  * Fill the warp's feature lists for the step `before` -> `d` (before == nullptr: no predecessor).
  *   perspectives in the returned mask are rebuilt from scratch: psq_add = all pieces + bias row,
  *     thr_add = every threat / pawn-pair feature of the board (nnue_state.cpp:309-354, 440-449)
- *   the others are updated: psq_delta / thr_delta = signed delta rows (sp_delta.h;
- *     replaces nnue.cpp:490-599, nnue_state.cpp:34-87, 163-307)
+ *   the others are updated: psq_delta / thr_delta = delta rows (sp_delta.h; replaces
+ *     nnue.cpp:490-599, nnue_state.cpp:34-87, 163-307)
  * A perspective is rebuilt when its king changes input bucket or board half (psq.h:264-283,
  * nnue_state.h:118-128), when more than kMaxChanged squares differ, or when a delta list overflows.
  * Returns -1 if a full list exceeds the reference's bound of 256 entries.
@@ -175,56 +343,45 @@ __device__ __forceinline__ int build_lists(
         if (__popcll(changed) > kMaxChanged) rebuild = 3;
     }
     for (;;) {
-        if (lane < 2) ws.n_thr_add[lane] = ws.n_thr_delta[lane] = ws.n_psq_add[lane] = ws.n_psq_delta[lane] = 0;
-        __syncwarp();
-        if (rebuild != 3) {
-            auto emit = [&](int c, int kind, int sign, uint32_t idx) {
-                if ((rebuild >> c) & 1) return;
-                const uint32_t entry = sign > 0 ? idx : idx | kSubFlag;
-                if (kind == 0) push(ws.psq_delta[c], &ws.n_psq_delta[c], kPsqDeltaCap, entry);
-                else push(ws.thr_delta[c], &ws.n_thr_delta[c], kThrDeltaCap, entry);
-            };
-            /* lane j < |D| finds the j-th changed square once; items fetch theirs by shuffle */
-            const int n_changed = __popcll(changed);
-            const int my_changed = lane < n_changed ? nth_piece_square(changed, lane) : 0;
-            /* line items: lane = unit * 8 + k, uniform code in every lane */
-            const int units = 2 * n_changed;
-#pragma unroll 1
-            for (int base = 0; base < units * kLineItemsPerUnit; base += 32) {
-                const int item = base + lane;
-                const int u = item >> 3;
-                const int s = __shfl_sync(kFull, my_changed, (u >> 1) & 31);
-                if (u < units) delta_line_item(t, (u & 1) ? d.view : *before, (u & 1) ? 1 : -1, changed, s, item & 7, emit);
-            }
-            const int s = __shfl_sync(kFull, my_changed, (lane >> 1) & 31);
-            if (lane < units) delta_square_item(t, (lane & 1) ? d.view : *before, (lane & 1) ? 1 : -1, changed, s, emit);
+        int n_tasks = 0;
+        int n_full[2] = {0, 0}, n_dadd[2] = {0, 0}, n_dsub[2] = {0, 0}, n_psq_delta[2] = {0, 0};
+        if (rebuild != 3) n_tasks = enqueue_delta(t, *before, d.view, changed, rebuild, lane, ws, n_tasks, n_psq_delta);
+        if (n_tasks > kTaskCap - 32) { /* far too many candidates for an update: rebuild instead */
+            rebuild = 3;
+            __syncwarp();
+            continue;
         }
-        if (rebuild && lane < d.n_pieces) {
-            /* lane-per-piece enumeration of the whole board */
-            const int sq = nth_piece_square(d.view.occ, lane);
-            const int piece = d.view.mailbox[sq];
-            if (rebuild & 1) ws.psq_add[kBlack][lane] = static_cast<uint16_t>(psq_index(t, kBlack, piece, sq, d.view.king[kBlack]));
-            if (rebuild & 2) ws.psq_add[kWhite][lane] = static_cast<uint16_t>(psq_index(t, kWhite, piece, sq, d.view.king[kWhite]));
-            square_threat_features(t, d.view, sq, [&](int c, uint32_t idx) {
-                if ((rebuild >> c) & 1) push(ws.thr_add[c], &ws.n_thr_add[c], kThrListCap, idx);
-            });
-        }
-        __syncwarp();
-        if (lane < 2 && ((rebuild >> lane) & 1)) {
-            ws.psq_add[lane][d.n_pieces] = kPsqBiasRow;
-            ws.n_psq_add[lane] = d.n_pieces + 1;
-        }
-        __syncwarp();
-        int overflow = 0;
+        auto flush = [&](int queued) {
+            __syncwarp();
+            process_tasks(t, d.view, rebuild, queued, lane, ws, n_full, n_dadd, n_dsub);
+            __syncwarp();
+            return 0;
+        };
+        if (rebuild) n_tasks = enqueue_board(t, d.view, d.n_pieces, rebuild, lane, ws, n_tasks, flush);
+        flush(n_tasks);
+        int overflow = 0, too_long = 0;
+#pragma unroll
         for (int c = 0; c < 2; ++c) {
-            if (ws.n_thr_add[c] > kThrListCap || ws.n_psq_add[c] > kPsqListCap || ws.n_thr_delta[c] > kThrDeltaCap
-                || ws.n_psq_delta[c] > kPsqDeltaCap)
-                overflow |= 1 << c;
+            if (n_full[c] > kThrListCap) too_long |= 1 << c;
+            if (n_dadd[c] + n_dsub[c] > kThrDeltaCap || n_psq_delta[c] > kPsqDeltaCap) overflow |= 1 << c;
         }
-        if (!overflow) return rebuild;
-        if (overflow & rebuild) return -1; /* a from-scratch list does not fit: the reference's own limit */
-        rebuild = 3;                       /* an over-long delta: fall back to rebuilding */
+        if (too_long) return -1; /* a from-scratch list does not fit: the reference's own limit */
+        if (overflow) {
+            rebuild = 3; /* an over-long delta: fall back to rebuilding */
+            __syncwarp();
+            continue;
+        }
+        if (lane < 2) {
+            const bool fresh = (rebuild >> lane) & 1;
+            if (fresh) ws.psq_add[lane][d.n_pieces] = kPsqBiasRow;
+            ws.n_psq_add[lane] = fresh ? d.n_pieces + 1 : 0;
+            ws.n_thr_add[lane] = lane ? n_full[1] : n_full[0];
+            ws.n_thr_dadd[lane] = lane ? n_dadd[1] : n_dadd[0];
+            ws.n_thr_dsub[lane] = lane ? n_dsub[1] : n_dsub[0];
+            ws.n_psq_delta[lane] = lane ? n_psq_delta[1] : n_psq_delta[0];
+        }
         __syncwarp();
+        return rebuild;
     }
 }
 
@@ -237,7 +394,6 @@ __device__ __forceinline__ int build_lists(
  * fall out of one AND / one PRMT, and the device PSQ rows are stored in the same order, so both
  * kinds of row are added with VIADD.16x2 (__vadd2: wrapping, no carry between the halves). */
 
-__device__ __forceinline__ uint32_t even_bytes(uint32_t w) { return w & 0x00FF00FFu; }
 __device__ __forceinline__ uint32_t odd_bytes(uint32_t w) { return __byte_perm(w, 0, 0x4341); }
 
 __device__ __forceinline__ void load_psq_row(const DeviceNet& net, uint32_t row, int lane, uint4 (&c)[4]) {
@@ -325,10 +481,12 @@ __device__ __noinline__ void rebuild_perspective_cold(
     for (int i = 0; i < 16; ++i) out[i] = v[i];
 }
 
-/* Advance one perspective by its signed delta lists.  A subtracted row is added complemented:
- * PSQ words ~w = -w - 1 per int16, biased threat bytes ~b = (-s) + 127, so one accumulator serves both
- * signs and the constant offsets (+1 per subtracted PSQ row, 128 per added and 127 per subtracted
- * threat row, zero-row top-ups counting as added) are removed once at the end. */
+/* Advance one perspective by its delta lists.
+ * PSQ rows: one signed list; a subtracted row is added complemented (~w = -w - 1 per int16).
+ * Threat rows: added and subtracted rows are fetched in lock-step (equal row counts, so their +128
+ * biases cancel) and summed as on the rebuild path -- whole words in s, odd bytes in o, even bytes
+ * recovered as s - (o << 8) -- then the subtracted sums are added complemented.  All the "-1" of the
+ * complements are repaid by one constant at the end. */
 __device__ __forceinline__ void update_perspective(const DeviceNet& net, const WarpScratch& ws, int c, int lane, uint32_t (&v)[16]) {
     const int n_psq = ws.n_psq_delta[c];
     int psq_subs = 0;
@@ -353,36 +511,35 @@ __device__ __forceinline__ void update_perspective(const DeviceNet& net, const W
                 v[k * 4 + 3] = __vadd2(v[k * 4 + 3], rows[j][k].w ^ mask[j]);
             }
     }
-    const int n_thr = ws.n_thr_delta[c];
-    int thr_rows = 0, thr_subs = 0;
+    const int n_add = ws.n_thr_dadd[c], n_sub = ws.n_thr_dsub[c];
+    uint32_t sa[8], oa[8], ss[8], os[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sa[i] = oa[i] = ss[i] = os[i] = 0;
 #pragma unroll 1
-    for (int i = 0; i < n_thr; i += kThrGroupDelta) {
-        uint4 rows[kThrGroupDelta][2];
-        uint32_t mask[kThrGroupDelta];
+    for (int i = 0; i < max(n_add, n_sub); i += kThrGroupDelta) {
+        uint4 ra[kThrGroupDelta][2], rs[kThrGroupDelta][2];
 #pragma unroll
         for (int j = 0; j < kThrGroupDelta; ++j) {
-            const uint32_t e = i + j < n_thr ? ws.thr_delta[c][i + j] : static_cast<uint32_t>(kThrZeroRow);
-            mask[j] = static_cast<uint32_t>(static_cast<int32_t>(e) >> 31);
-            thr_subs += mask[j] & 1;
-            load_thr_row(net, e & ~kSubFlag, lane, rows[j]);
+            load_thr_row(net, i + j < n_add ? ws.thr_delta[c][i + j] : static_cast<uint32_t>(kThrZeroRow), lane, ra[j]);
+            load_thr_row(net, i + j < n_sub ? ws.thr_delta[c][kThrDeltaCap - 1 - (i + j)] : static_cast<uint32_t>(kThrZeroRow), lane, rs[j]);
         }
 #pragma unroll
-        for (int j = 0; j < kThrGroupDelta; ++j)
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const uint32_t w[4] = {rows[j][u].x ^ mask[j], rows[j][u].y ^ mask[j], rows[j][u].z ^ mask[j], rows[j][u].w ^ mask[j]};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    v[(2 * u) * 4 + t] = __vadd2(v[(2 * u) * 4 + t], even_bytes(w[t]));
-                    v[(2 * u + 1) * 4 + t] = __vadd2(v[(2 * u + 1) * 4 + t], odd_bytes(w[t]));
-                }
-            }
-        thr_rows += kThrGroupDelta;
+        for (int j = 0; j < kThrGroupDelta; ++j) {
+            add_thr_wide(sa, oa, ra[j]);
+            add_thr_wide(ss, os, rs[j]);
+        }
     }
-    const int offset = psq_subs - 128 * (thr_rows - thr_subs) - 127 * thr_subs;
-    const uint32_t corr = (static_cast<uint32_t>(offset) & 0xFFFFu) * 0x10001u;
+    const uint32_t repay = (static_cast<uint32_t>(psq_subs + 1) & 0xFFFFu) * 0x10001u; /* +1: the complemented threat sums */
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __vadd2(v[i], corr);
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint32_t even_a = sa[u * 4 + t] - (oa[u * 4 + t] << 8), even_s = ss[u * 4 + t] - (os[u * 4 + t] << 8);
+            uint32_t& ve = v[(2 * u) * 4 + t];
+            uint32_t& vo = v[(2 * u + 1) * 4 + t];
+            ve = __vadd2(__vadd2(__vadd2(ve, even_a), ~even_s), repay);
+            vo = __vadd2(__vadd2(__vadd2(vo, oa[u * 4 + t]), ~os[u * 4 + t]), repay);
+        }
 }
 
 /* activateFt, multilayer.h:92-152, on packed pairs: out = (clamp(a,0,255) * clamp(d,0,255)) >> 9.

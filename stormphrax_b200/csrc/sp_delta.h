@@ -107,18 +107,18 @@ SP_HD void emit_threat(const FeatureTables& t, const B& b, int sign, int attacke
     if (fw >= 0) emit(kWhite, 1, sign, static_cast<uint32_t>(fw));
 }
 
-/* Line item k of unit (s, b).  Up to four (attacker, victim) candidates are collected first and
- * emitted by ONE copy of the indexing code (keeps the kernels' instruction footprint small). */
-template <typename B, typename Emit>
-SP_HD void delta_line_item(const FeatureTables& t, const B& b, int sign, uint64_t changed, int s, int k, Emit&& emit) {
-    /* candidate i: attacker squares/pieces packed as asq | vsq << 8 | attacker << 16 | victim << 24 */
-    /* fixed slots (0: piece -> ahead / x-ray, 1: ahead -> piece, 2: knight out, 3: knight in) so the
-     * candidates stay in registers */
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+/* A threat candidate: asq | vsq << 8 | attacker << 16 | victim << 24 (bits 20-23 and 28-31 stay free
+ * for the kernels' task flags). */
+SP_HD uint32_t pack_candidate(int attacker, int asq, int victim, int vsq) {
+    return static_cast<uint32_t>(asq | vsq << 8 | attacker << 16 | victim << 24);
+}
+
+/* Line item k of unit (s, b): up to four (attacker, victim) candidates in fixed slots
+ * (0: piece -> ahead or x-ray, 1: ahead -> piece, 2: knight out, 3: knight in); returns the mask of
+ * filled slots.  Candidates may still turn out to have no feature (threat_index < 0). */
+template <typename B>
+SP_HD unsigned delta_line_candidates(const FeatureTables& t, const B& b, uint64_t changed, int s, int k, uint32_t (&c)[4]) {
     unsigned valid = 0;
-    auto pack = [](int attacker, int asq, int victim, int vsq) {
-        return static_cast<uint32_t>(asq | vsq << 8 | attacker << 16 | victim << 24);
-    };
     const int piece = b.mailbox[s];
     uint64_t gap_ahead;
     const int ahead = ray_first(t, b.occ, s, k, gap_ahead);
@@ -126,8 +126,8 @@ SP_HD void delta_line_item(const FeatureTables& t, const B& b, int sign, uint64_
         if (ahead != kNoSquare) {
             const int other = b.mailbox[ahead];
             const bool adjacent = gap_ahead == 0;
-            if (attacks_along(piece, k, adjacent)) c0 = pack(piece, s, other, ahead), valid |= 1;
-            if (!((changed >> ahead) & 1) && attacks_along(other, k ^ 4, adjacent)) c1 = pack(other, ahead, piece, s), valid |= 2;
+            if (attacks_along(piece, k, adjacent)) c[0] = pack_candidate(piece, s, other, ahead), valid |= 1;
+            if (!((changed >> ahead) & 1) && attacks_along(other, k ^ 4, adjacent)) c[1] = pack_candidate(other, ahead, piece, s), valid |= 2;
         }
         /* knight offset k: dx = {1,2,2,1,-1,-2,-2,-1}, dy = {2,1,-1,-2,-2,-1,1,2}, stored +2 per nibble */
         const int fx = (s & 7) + static_cast<int>((0x10013443u >> (4 * k)) & 0xF) - 2;
@@ -136,8 +136,8 @@ SP_HD void delta_line_item(const FeatureTables& t, const B& b, int sign, uint64_
             const int o = ry * 8 + fx;
             const int other = b.mailbox[o];
             if (other != kNoPiece) {
-                if ((piece >> 1) == kKnight) c2 = pack(piece, s, other, o), valid |= 4;
-                if ((other >> 1) == kKnight && !((changed >> o) & 1)) c3 = pack(other, o, piece, s), valid |= 8;
+                if ((piece >> 1) == kKnight) c[2] = pack_candidate(piece, s, other, o), valid |= 4;
+                if ((other >> 1) == kKnight && !((changed >> o) & 1)) c[3] = pack_candidate(other, o, piece, s), valid |= 8;
             }
         }
     } else if (ahead != kNoSquare && !((changed >> ahead) & 1)) {
@@ -147,18 +147,28 @@ SP_HD void delta_line_item(const FeatureTables& t, const B& b, int sign, uint64_
         /* a changed square nearer to the attacker would own this pair */
         if (behind != kNoSquare && !((changed >> behind) & 1) && !(gap_behind & changed)) {
             const int attacker = b.mailbox[behind];
-            if (slides_along(attacker, k)) c0 = pack(attacker, behind, b.mailbox[ahead], ahead), valid |= 1;
+            if (slides_along(attacker, k)) c[0] = pack_candidate(attacker, behind, b.mailbox[ahead], ahead), valid |= 1;
         }
     }
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
+    return valid;
+}
+
+template <typename B, typename Emit>
+SP_HD void delta_line_item(const FeatureTables& t, const B& b, int sign, uint64_t changed, int s, int k, Emit&& emit) {
+    uint32_t c[4] = {0, 0, 0, 0};
+    const unsigned valid = delta_line_candidates(t, b, changed, s, k, c);
     for (int i = 0; i < 4; ++i) {
         if (!((valid >> i) & 1)) continue;
-        const uint32_t c = i == 0 ? c0 : (i == 1 ? c1 : (i == 2 ? c2 : c3));
-        emit_threat(t, b, sign, static_cast<int>((c >> 16) & 0xFF), static_cast<int>(c & 0xFF), static_cast<int>(c >> 24),
-                    static_cast<int>((c >> 8) & 0xFF), emit);
+        emit_threat(t, b, sign, static_cast<int>((c[i] >> 16) & 0xF), static_cast<int>(c[i] & 0xFF), static_cast<int>((c[i] >> 24) & 0xF),
+                    static_cast<int>((c[i] >> 8) & 0xFF), emit);
     }
+}
+
+/* Partners of a pawn on s for the pawn-pair features of unit (s, b): every other pawn within one file,
+ * except changed pawns on lower squares (the pair then belongs to that lower square's unit). */
+template <typename B>
+SP_HD uint64_t delta_pawn_partners(const B& b, uint64_t changed, int s) {
+    return (b.pawns[0] | b.pawns[1]) & pp_mask(s) & ~bit(s) & ~(changed & squares_below(s));
 }
 
 /* Square item of unit (s, b): PSQ row and pawn pairs. */
@@ -169,8 +179,7 @@ SP_HD void delta_square_item(const FeatureTables& t, const B& b, int sign, uint6
     emit(kBlack, 0, sign, psq_index(t, kBlack, piece, s, b.king[kBlack]));
     emit(kWhite, 0, sign, psq_index(t, kWhite, piece, s, b.king[kWhite]));
     if ((piece >> 1) != kPawn) return;
-    uint64_t partners = (b.pawns[0] | b.pawns[1]) & pp_mask(s) & ~bit(s);
-    partners &= ~(changed & squares_below(s)); /* a pair of two changed pawns belongs to the lower square */
+    uint64_t partners = delta_pawn_partners(b, changed, s);
     while (partners) {
         const int o = lsb64(partners);
         partners &= partners - 1;
