@@ -47,20 +47,25 @@ constexpr int kPsqListCap = 40;    /* 32 pieces + bias row */
 constexpr int kPsqDeltaCap = 16;
 constexpr int kThrDeltaCap = 96;   /* added rows grow from the front, subtracted rows from the back */
 constexpr int kThrListCap = SP_MAX_THREAT_INDICES;
-constexpr int kTaskCap = 256;
+constexpr int kTaskCap = 128;
 constexpr uint32_t kSubFlag = 0x80000000u;      /* PSQ delta list entry: subtract this row */
 constexpr uint32_t kTaskPawnPair = 1u << 31;    /* task = pawn pair (else attacker -> victim candidate) */
 constexpr uint32_t kTaskSub = 1u << 30;         /* feature of the predecessor board: subtract */
 constexpr uint32_t kTaskFull = 1u << 29;        /* from a whole-board enumeration: for rebuilt perspectives */
 constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr uint32_t kPsqVecs = 128, kThrVecs = 64; /* uint4 per row */
+constexpr uint32_t kPsqZeroOff = kPsqZeroRow * kPsqVecs, kPsqBiasOff = kPsqBiasRow * kPsqVecs, kThrZeroOff = kThrZeroRow * kThrVecs;
 
 /* Per-warp shared memory. */
 struct WarpScratch {
+    /* Row lists hold uint4 offsets into the weight tables (row * 128 for PSQ, row * 64 for threat rows)
+     * and are padded with the zero row to a whole number of load batches, so the accumulate loops fetch
+     * four entries with one LDS.128 and form an address with one IMAD.WIDE. */
+    __align__(16) uint32_t thr_add[2][kThrListCap];      /* rebuild: every threat / pawn-pair row of the board */
+    __align__(16) uint32_t thr_delta[2][kThrDeltaCap];   /* update: added rows [0, n_add), subtracted rows [cap - n_sub, cap) */
+    __align__(16) uint32_t psq_add[2][kPsqListCap];      /* rebuild: one row per piece + the bias row */
+    __align__(16) uint32_t psq_delta[2][kPsqDeltaCap];   /* update: kSubFlag = subtract */
     uint32_t tasks[kTaskCap];              /* (attacker, victim) candidates and pawn pairs awaiting indexing */
-    uint16_t thr_add[2][kThrListCap];      /* rebuild: every threat / pawn-pair row of the board */
-    uint32_t thr_delta[2][kThrDeltaCap];   /* update: added rows [0, n_add), subtracted rows [cap - n_sub, cap) */
-    uint16_t psq_add[2][kPsqListCap];      /* rebuild: one row per piece + the bias row */
-    uint32_t psq_delta[2][kPsqDeltaCap];   /* update: kSubFlag = subtract */
     uint8_t mailbox[2][64];                /* two boards: the one being evaluated and its predecessor */
     int n_thr_add[2];
     int n_thr_dadd[2];
@@ -194,8 +199,8 @@ __device__ __forceinline__ int enqueue_board(
     const int piece = has ? b.mailbox[sq] : kNoPiece;
     const int type = piece >> 1;
     if (has) {
-        if (rebuild & 1) ws.psq_add[kBlack][lane] = static_cast<uint16_t>(psq_index(t, kBlack, piece, sq, b.king[kBlack]));
-        if (rebuild & 2) ws.psq_add[kWhite][lane] = static_cast<uint16_t>(psq_index(t, kWhite, piece, sq, b.king[kWhite]));
+        if (rebuild & 1) ws.psq_add[kBlack][lane] = psq_index(t, kBlack, piece, sq, b.king[kBlack]) * kPsqVecs;
+        if (rebuild & 2) ws.psq_add[kWhite][lane] = psq_index(t, kWhite, piece, sq, b.king[kWhite]) * kPsqVecs;
     }
     const bool attacker = has && type != kKing;
 #pragma unroll 1
@@ -266,7 +271,7 @@ __device__ __forceinline__ int enqueue_delta(
         if ((rebuild >> c) & 1) continue;
         if (piece != kNoPiece) {
             const int at = __popc(occupied & ((1u << lane) - 1));
-            if (at < kPsqDeltaCap) ws.psq_delta[c][at] = psq_index(t, c, piece, s, after.king[c]) | sub;
+            if (at < kPsqDeltaCap) ws.psq_delta[c][at] = psq_index(t, c, piece, s, after.king[c]) * kPsqVecs | sub;
         }
         n_psq_delta[c] = __popc(occupied);
     }
@@ -306,13 +311,13 @@ __device__ __forceinline__ void process_tasks(
         if (valid) {
             if (full) {
                 const int at = (c ? n_full[1] : n_full[0]) + __popc(mf & mine);
-                if (at < kThrListCap) ws.thr_add[c][at] = static_cast<uint16_t>(idx);
+                if (at < kThrListCap) ws.thr_add[c][at] = static_cast<uint32_t>(idx) * kThrVecs;
             } else if (!sub) {
                 const int at = (c ? n_dadd[1] : n_dadd[0]) + __popc(ma & mine);
-                if (at < kThrDeltaCap) ws.thr_delta[c][at] = static_cast<uint32_t>(idx);
+                if (at < kThrDeltaCap) ws.thr_delta[c][at] = static_cast<uint32_t>(idx) * kThrVecs;
             } else {
                 const int at = (c ? n_dsub[1] : n_dsub[0]) + __popc(ms & mine);
-                if (at < kThrDeltaCap) ws.thr_delta[c][kThrDeltaCap - 1 - at] = static_cast<uint32_t>(idx);
+                if (at < kThrDeltaCap) ws.thr_delta[c][kThrDeltaCap - 1 - at] = static_cast<uint32_t>(idx) * kThrVecs;
             }
         }
         n_full[0] += __popc(mf & 0x55555555u), n_full[1] += __popc(mf & 0xAAAAAAAAu);
@@ -363,7 +368,9 @@ __device__ __forceinline__ int build_lists(
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             if (n_full[c] > kThrListCap) too_long |= 1 << c;
-            if (n_dadd[c] + n_dsub[c] > kThrDeltaCap || n_psq_delta[c] > kPsqDeltaCap) overflow |= 1 << c;
+            if (2 * ((max(n_dadd[c], n_dsub[c]) + kThrGroupDelta - 1) / kThrGroupDelta * kThrGroupDelta) > kThrDeltaCap
+                || n_psq_delta[c] > kPsqDeltaCap)
+                overflow |= 1 << c;
         }
         if (too_long) return -1; /* a from-scratch list does not fit: the reference's own limit */
         if (overflow) {
@@ -371,14 +378,25 @@ __device__ __forceinline__ int build_lists(
             __syncwarp();
             continue;
         }
-        if (lane < 2) {
-            const bool fresh = (rebuild >> lane) & 1;
-            if (fresh) ws.psq_add[lane][d.n_pieces] = kPsqBiasRow;
-            ws.n_psq_add[lane] = fresh ? d.n_pieces + 1 : 0;
-            ws.n_thr_add[lane] = lane ? n_full[1] : n_full[0];
-            ws.n_thr_dadd[lane] = lane ? n_dadd[1] : n_dadd[0];
-            ws.n_thr_dsub[lane] = lane ? n_dsub[1] : n_dsub[0];
-            ws.n_psq_delta[lane] = lane ? n_psq_delta[1] : n_psq_delta[0];
+        /* top the lists up with the zero row to whole load batches and publish the padded lengths */
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if ((rebuild >> c) & 1) {
+                const int n_psq = d.n_pieces + 1, n_psq_pad = (n_psq + kPsqGroup - 1) / kPsqGroup * kPsqGroup;
+                const int n_thr_pad = (n_full[c] + kThrGroupFull - 1) / kThrGroupFull * kThrGroupFull;
+                if (lane == 0) ws.psq_add[c][d.n_pieces] = kPsqBiasOff;
+                if (lane > 0 && d.n_pieces + lane < n_psq_pad) ws.psq_add[c][d.n_pieces + lane] = kPsqZeroOff;
+                if (n_full[c] + lane < n_thr_pad) ws.thr_add[c][n_full[c] + lane] = kThrZeroOff;
+                if (lane == 0) ws.n_psq_add[c] = n_psq_pad, ws.n_thr_add[c] = n_thr_pad;
+            } else {
+                const int n_psq_pad = (n_psq_delta[c] + kPsqGroupDelta - 1) / kPsqGroupDelta * kPsqGroupDelta;
+                const int n_thr_pad = (max(n_dadd[c], n_dsub[c]) + kThrGroupDelta - 1) / kThrGroupDelta * kThrGroupDelta;
+                if (n_psq_delta[c] + lane < n_psq_pad) ws.psq_delta[c][n_psq_delta[c] + lane] = kPsqZeroOff;
+                /* both signs are fetched in lock-step: pad each up to the common length */
+                for (int i = n_dadd[c] + lane; i < n_thr_pad; i += 32) ws.thr_delta[c][i] = kThrZeroOff;
+                for (int i = n_dsub[c] + lane; i < n_thr_pad; i += 32) ws.thr_delta[c][kThrDeltaCap - 1 - i] = kThrZeroOff;
+                if (lane == 0) ws.n_psq_delta[c] = n_psq_pad, ws.n_thr_dadd[c] = n_thr_pad;
+            }
         }
         __syncwarp();
         return rebuild;
@@ -396,14 +414,15 @@ __device__ __forceinline__ int build_lists(
 
 __device__ __forceinline__ uint32_t odd_bytes(uint32_t w) { return __byte_perm(w, 0, 0x4341); }
 
-__device__ __forceinline__ void load_psq_row(const DeviceNet& net, uint32_t row, int lane, uint4 (&c)[4]) {
-    const uint4* r = net.psq + static_cast<size_t>(row) * 128 + lane;
+/* `base` = table + lane; `off` = uint4 offset of the row (a list entry) */
+__device__ __forceinline__ void load_psq_row(const uint4* base, uint32_t off, uint4 (&c)[4]) {
+    const uint4* r = base + off;
 #pragma unroll
     for (int k = 0; k < 4; ++k) c[k] = __ldg(r + 32 * k);
 }
 
-__device__ __forceinline__ void load_thr_row(const DeviceNet& net, uint32_t row, int lane, uint4 (&c)[2]) {
-    const uint4* r = net.thr + static_cast<size_t>(row) * 64 + lane;
+__device__ __forceinline__ void load_thr_row(const uint4* base, uint32_t off, uint4 (&c)[2]) {
+    const uint4* r = base + off;
     c[0] = __ldg(r);
     c[1] = __ldg(r + 32);
 }
@@ -433,34 +452,44 @@ __device__ __forceinline__ void add_thr_wide(uint32_t (&s)[8], uint32_t (&o)[8],
     }
 }
 
-/* Rebuild one perspective from its full lists: v = bias + sum(PSQ rows) + sum(threat rows). */
+/* Rebuild one perspective from its full lists: v = bias + sum(PSQ rows) + sum(threat rows).
+ * The lists are padded to whole batches (build_lists). */
 __device__ __forceinline__ void rebuild_perspective(
-    const DeviceNet& net, const uint16_t* psq_list, int n_psq, const uint16_t* thr_list, int n_thr, int lane, uint32_t (&v)[16]) {
+    const DeviceNet& net, const uint32_t* psq_list, int n_psq, const uint32_t* thr_list, int n_thr, int lane, uint32_t (&v)[16]) {
+    static_assert(kPsqGroup == 4 && kThrGroupFull % 4 == 0, "list entries are fetched four at a time");
+    const uint4* psq_base = net.psq + lane;
+    const uint4* thr_base = net.thr + lane;
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = 0;
 #pragma unroll 1
     for (int i = 0; i < n_psq; i += kPsqGroup) {
+        const uint4 e = *reinterpret_cast<const uint4*>(psq_list + i);
+        const uint32_t off[4] = {e.x, e.y, e.z, e.w};
         uint4 c[kPsqGroup][4];
 #pragma unroll
-        for (int j = 0; j < kPsqGroup; ++j) load_psq_row(net, i + j < n_psq ? psq_list[i + j] : static_cast<uint32_t>(kPsqZeroRow), lane, c[j]);
+        for (int j = 0; j < kPsqGroup; ++j) load_psq_row(psq_base, off[j], c[j]);
 #pragma unroll
         for (int j = 0; j < kPsqGroup; ++j) add_psq(v, c[j]);
     }
     uint32_t s[8], o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = o[i] = 0;
-    int rows = 0;
 #pragma unroll 1
     for (int i = 0; i < n_thr; i += kThrGroupFull) {
         uint4 c[kThrGroupFull][2];
 #pragma unroll
-        for (int j = 0; j < kThrGroupFull; ++j) load_thr_row(net, i + j < n_thr ? thr_list[i + j] : static_cast<uint32_t>(kThrZeroRow), lane, c[j]);
+        for (int q = 0; q < kThrGroupFull / 4; ++q) {
+            const uint4 e = *reinterpret_cast<const uint4*>(thr_list + i + 4 * q);
+            load_thr_row(thr_base, e.x, c[4 * q + 0]);
+            load_thr_row(thr_base, e.y, c[4 * q + 1]);
+            load_thr_row(thr_base, e.z, c[4 * q + 2]);
+            load_thr_row(thr_base, e.w, c[4 * q + 3]);
+        }
 #pragma unroll
         for (int j = 0; j < kThrGroupFull; ++j) add_thr_wide(s, o, c[j]);
-        rows += kThrGroupFull;
     }
     /* every row (zero-row top-ups included) carried +128 per element */
-    const uint32_t corr = (static_cast<uint32_t>(-128 * rows) & 0xFFFFu) * 0x10001u;
+    const uint32_t corr = (static_cast<uint32_t>(-128 * n_thr) & 0xFFFFu) * 0x10001u;
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
@@ -474,7 +503,7 @@ __device__ __forceinline__ void rebuild_perspective(
 /* Out-of-line copy for the kernels where a rebuild is the rare path (king crossed a bucket
  * boundary): keeps their hot loop small enough for the instruction cache. */
 __device__ __noinline__ void rebuild_perspective_cold(
-    const DeviceNet& net, const uint16_t* psq_list, int n_psq, const uint16_t* thr_list, int n_thr, int lane, uint32_t* out) {
+    const DeviceNet& net, const uint32_t* psq_list, int n_psq, const uint32_t* thr_list, int n_thr, int lane, uint32_t* out) {
     uint32_t v[16];
     rebuild_perspective(net, psq_list, n_psq, thr_list, n_thr, lane, v);
 #pragma unroll
@@ -488,18 +517,22 @@ __device__ __noinline__ void rebuild_perspective_cold(
  * recovered as s - (o << 8) -- then the subtracted sums are added complemented.  All the "-1" of the
  * complements are repaid by one constant at the end. */
 __device__ __forceinline__ void update_perspective(const DeviceNet& net, const WarpScratch& ws, int c, int lane, uint32_t (&v)[16]) {
-    const int n_psq = ws.n_psq_delta[c];
+    static_assert(kPsqGroupDelta == 4 && kThrGroupDelta == 4, "list entries are fetched four at a time");
+    const uint4* psq_base = net.psq + lane;
+    const uint4* thr_base = net.thr + lane;
+    const int n_psq = ws.n_psq_delta[c]; /* padded */
     int psq_subs = 0;
 #pragma unroll 1
     for (int i = 0; i < n_psq; i += kPsqGroupDelta) {
+        const uint4 e4 = *reinterpret_cast<const uint4*>(ws.psq_delta[c] + i);
+        const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
         uint4 rows[kPsqGroupDelta][4];
         uint32_t mask[kPsqGroupDelta];
 #pragma unroll
         for (int j = 0; j < kPsqGroupDelta; ++j) {
-            const uint32_t e = i + j < n_psq ? ws.psq_delta[c][i + j] : static_cast<uint32_t>(kPsqZeroRow);
-            mask[j] = static_cast<uint32_t>(static_cast<int32_t>(e) >> 31);
-            psq_subs += mask[j] & 1;
-            load_psq_row(net, e & ~kSubFlag, lane, rows[j]);
+            mask[j] = static_cast<uint32_t>(static_cast<int32_t>(e[j]) >> 31);
+            psq_subs += e[j] >> 31;
+            load_psq_row(psq_base, e[j] & ~kSubFlag, rows[j]);
         }
 #pragma unroll
         for (int j = 0; j < kPsqGroupDelta; ++j)
@@ -511,18 +544,19 @@ __device__ __forceinline__ void update_perspective(const DeviceNet& net, const W
                 v[k * 4 + 3] = __vadd2(v[k * 4 + 3], rows[j][k].w ^ mask[j]);
             }
     }
-    const int n_add = ws.n_thr_dadd[c], n_sub = ws.n_thr_dsub[c];
+    const int n_thr = ws.n_thr_dadd[c]; /* common padded length of the added and the subtracted list */
     uint32_t sa[8], oa[8], ss[8], os[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) sa[i] = oa[i] = ss[i] = os[i] = 0;
 #pragma unroll 1
-    for (int i = 0; i < max(n_add, n_sub); i += kThrGroupDelta) {
+    for (int i = 0; i < n_thr; i += kThrGroupDelta) {
+        const uint4 ea = *reinterpret_cast<const uint4*>(ws.thr_delta[c] + i);
+        const uint4 es = *reinterpret_cast<const uint4*>(ws.thr_delta[c] + kThrDeltaCap - kThrGroupDelta - i); /* stored backwards */
         uint4 ra[kThrGroupDelta][2], rs[kThrGroupDelta][2];
-#pragma unroll
-        for (int j = 0; j < kThrGroupDelta; ++j) {
-            load_thr_row(net, i + j < n_add ? ws.thr_delta[c][i + j] : static_cast<uint32_t>(kThrZeroRow), lane, ra[j]);
-            load_thr_row(net, i + j < n_sub ? ws.thr_delta[c][kThrDeltaCap - 1 - (i + j)] : static_cast<uint32_t>(kThrZeroRow), lane, rs[j]);
-        }
+        load_thr_row(thr_base, ea.x, ra[0]), load_thr_row(thr_base, ea.y, ra[1]);
+        load_thr_row(thr_base, ea.z, ra[2]), load_thr_row(thr_base, ea.w, ra[3]);
+        load_thr_row(thr_base, es.x, rs[0]), load_thr_row(thr_base, es.y, rs[1]);
+        load_thr_row(thr_base, es.z, rs[2]), load_thr_row(thr_base, es.w, rs[3]);
 #pragma unroll
         for (int j = 0; j < kThrGroupDelta; ++j) {
             add_thr_wide(sa, oa, ra[j]);
