@@ -32,8 +32,8 @@ struct SpNnue {
 
     /* scratch for one chunk of positions, double-buffered: the head of chunk i runs on `aux` while the
      * feature transformer of chunk i + 1 runs on the caller's stream */
-    size_t chunk = 32768;
-    uint32_t games_chunk = 4736; /* playout walker: games per launch (2 per resident warp) */
+    size_t chunk = 65536;
+    uint32_t games_chunk = 7104; /* playout walker: games per launch (3 per resident warp) */
     uint8_t* d_act2[2] = {nullptr, nullptr};
     uint8_t* d_bucket2[2] = {nullptr, nullptr};
     uint8_t* d_act = nullptr;    /* = d_act2[0] */

@@ -33,12 +33,22 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef SP_THR_GROUP
 #define SP_THR_GROUP 8
 #endif
+#ifndef SP_PSQ_INFLIGHT
+#define SP_PSQ_INFLIGHT 2 /* PSQ rows whose loads are in flight together (4 x LDG.128 each) */
+#endif
+#ifndef SP_THR_INFLIGHT
+#define SP_THR_INFLIGHT 4 /* threat rows in flight together (2 x LDG.128 each) */
+#endif
+#ifndef SP_ENQ_UNROLL
+#define SP_ENQ_UNROLL 1 /* unroll of the 8-round board enumeration (more ILP, more code) */
+#endif
 #ifndef SP_FULL_MIN_BLOCKS
-#define SP_FULL_MIN_BLOCKS 2
+#define SP_FULL_MIN_BLOCKS 4
 #endif
 #ifndef SP_GAMES_MIN_BLOCKS
 #define SP_GAMES_MIN_BLOCKS 2
 #endif
+constexpr int kEnqUnroll = SP_ENQ_UNROLL;
 constexpr int kPsqGroup = SP_PSQ_GROUP;      /* PSQ rows fetched per batch on the rebuild path (4 x LDG.128 each per lane) */
 constexpr int kThrGroupFull = SP_THR_GROUP;  /* threat rows per batch on the rebuild path (2 x LDG.128 each per lane) */
 constexpr int kPsqGroupDelta = 4;  /* delta rows per batch on the incremental path (16 x LDG.128) */
@@ -203,7 +213,7 @@ __device__ __forceinline__ int enqueue_board(
         if (rebuild & 2) ws.psq_add[kWhite][lane] = psq_index(t, kWhite, piece, sq, b.king[kWhite]) * kPsqVecs;
     }
     const bool attacker = has && type != kKing;
-#pragma unroll 1
+#pragma unroll kEnqUnroll
     for (int k = 0; k < 8; ++k) {
         int target = kNoSquare;
         if (attacker) {
@@ -465,28 +475,34 @@ __device__ __forceinline__ void rebuild_perspective(
     for (int i = 0; i < n_psq; i += kPsqGroup) {
         const uint4 e = *reinterpret_cast<const uint4*>(psq_list + i);
         const uint32_t off[4] = {e.x, e.y, e.z, e.w};
-        uint4 c[kPsqGroup][4];
 #pragma unroll
-        for (int j = 0; j < kPsqGroup; ++j) load_psq_row(psq_base, off[j], c[j]);
+        for (int h = 0; h < kPsqGroup; h += SP_PSQ_INFLIGHT) {
+            uint4 c[SP_PSQ_INFLIGHT][4];
 #pragma unroll
-        for (int j = 0; j < kPsqGroup; ++j) add_psq(v, c[j]);
+            for (int j = 0; j < SP_PSQ_INFLIGHT; ++j) load_psq_row(psq_base, off[h + j], c[j]);
+#pragma unroll
+            for (int j = 0; j < SP_PSQ_INFLIGHT; ++j) add_psq(v, c[j]);
+        }
     }
     uint32_t s[8], o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = o[i] = 0;
 #pragma unroll 1
     for (int i = 0; i < n_thr; i += kThrGroupFull) {
-        uint4 c[kThrGroupFull][2];
 #pragma unroll
-        for (int q = 0; q < kThrGroupFull / 4; ++q) {
-            const uint4 e = *reinterpret_cast<const uint4*>(thr_list + i + 4 * q);
-            load_thr_row(thr_base, e.x, c[4 * q + 0]);
-            load_thr_row(thr_base, e.y, c[4 * q + 1]);
-            load_thr_row(thr_base, e.z, c[4 * q + 2]);
-            load_thr_row(thr_base, e.w, c[4 * q + 3]);
+        for (int h = 0; h < kThrGroupFull; h += SP_THR_INFLIGHT) {
+            uint4 c[SP_THR_INFLIGHT][2];
+#pragma unroll
+            for (int q = 0; q < SP_THR_INFLIGHT / 4; ++q) {
+                const uint4 e = *reinterpret_cast<const uint4*>(thr_list + i + h + 4 * q);
+                load_thr_row(thr_base, e.x, c[4 * q + 0]);
+                load_thr_row(thr_base, e.y, c[4 * q + 1]);
+                load_thr_row(thr_base, e.z, c[4 * q + 2]);
+                load_thr_row(thr_base, e.w, c[4 * q + 3]);
+            }
+#pragma unroll
+            for (int j = 0; j < SP_THR_INFLIGHT; ++j) add_thr_wide(s, o, c[j]);
         }
-#pragma unroll
-        for (int j = 0; j < kThrGroupFull; ++j) add_thr_wide(s, o, c[j]);
     }
     /* every row (zero-row top-ups included) carried +128 per element */
     const uint32_t corr = (static_cast<uint32_t>(-128 * n_thr) & 0xFFFFu) * 0x10001u;
