@@ -39,7 +39,9 @@ struct SpNnue {
     uint8_t* d_act = nullptr;    /* = d_act2[0] */
     uint8_t* d_bucket = nullptr; /* = d_bucket2[0] */
     cudaStream_t aux = nullptr;
-    cudaEvent_t ev_ft[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr}, ev_join = nullptr;
+    cudaStream_t h2d = nullptr, d2h = nullptr; /* host-pointer entry points: copies overlap the kernels chunk by chunk */
+    cudaEvent_t ev_ft[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr}, ev_join = nullptr, ev_start = nullptr;
+    std::vector<cudaEvent_t> ev_chunk; /* one "inputs of chunk i have landed" event per chunk */
     bool overlap = true;
     /* whole-stream scratch of the playout walker (one activation row per board) */
     uint8_t* d_act_big = nullptr;
@@ -234,12 +236,44 @@ struct Timed {
 /* boards (device) -> out (device), in chunks that keep the activation scratch L2-sized.  The dense
  * head of chunk i (latency-bound, low occupancy) runs on the auxiliary stream underneath the feature
  * transformer of chunk i + 1; everything is ordered with events, the host never waits. */
-int eval_full_device(SpNnue* ctx, const SpPackedBoard* d_boards, size_t n, int32_t* d_out, cudaStream_t stream) {
+/* Host side of a chunked call: where chunk i's boards come from and where its results go. */
+struct HostIo {
+    const SpPackedBoard* boards;
+    int32_t* out;
+};
+
+int chunk_event(SpNnue* ctx, size_t i, cudaEvent_t* ev) {
+    while (ctx->ev_chunk.size() <= i) {
+        cudaEvent_t e = nullptr;
+        SP_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_chunk.push_back(e);
+    }
+    *ev = ctx->ev_chunk[i];
+    return SP_OK;
+}
+
+int eval_full_device(
+    SpNnue* ctx, const SpPackedBoard* d_boards, size_t n, int32_t* d_out, cudaStream_t stream, const HostIo* io = nullptr) {
     const bool overlap = ctx->overlap && n > ctx->chunk;
+    if (io) {
+        /* all uploads are queued up front on their own stream; chunk i's kernels wait for upload i only */
+        SP_CUDA(ctx, cudaEventRecord(ctx->ev_start, stream));
+        SP_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d, ctx->ev_start, 0));
+        SP_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->ev_start, 0));
+        size_t i = 0;
+        for (size_t off = 0; off < n; off += ctx->chunk, ++i) {
+            const size_t m = std::min(ctx->chunk, n - off);
+            cudaEvent_t ev;
+            if (const int rc = chunk_event(ctx, i, &ev)) return rc;
+            SP_CUDA(ctx, cudaMemcpyAsync(const_cast<SpPackedBoard*>(d_boards) + off, io->boards + off, m * sizeof(SpPackedBoard), cudaMemcpyHostToDevice, ctx->h2d));
+            SP_CUDA(ctx, cudaEventRecord(ev, ctx->h2d));
+        }
+    }
     size_t i = 0;
     for (size_t off = 0; off < n; off += ctx->chunk, ++i) {
         const size_t m = std::min(ctx->chunk, n - off);
         const int buf = overlap ? static_cast<int>(i & 1) : 0;
+        if (io) SP_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_chunk[i], 0));
         if (overlap && i >= 2) SP_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_head[buf], 0)); /* scratch is free again */
         {
             Timed timed{ctx, stream, SP_KERNEL_FT_FULL};
@@ -256,10 +290,19 @@ int eval_full_device(SpNnue* ctx, const SpPackedBoard* d_boards, size_t n, int32
             launch_head(ctx->net, ctx->d_act2[buf], ctx->d_bucket2[buf], m, d_out + off, nullptr, ctx->d_status, ctx->sm_count, hs);
         }
         if (overlap) SP_CUDA(ctx, cudaEventRecord(ctx->ev_head[buf], ctx->aux));
+        if (io) { /* results of this chunk go home while the next chunk computes */
+            if (!overlap) SP_CUDA(ctx, cudaEventRecord(ctx->ev_head[buf], hs));
+            SP_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->ev_head[buf], 0));
+            SP_CUDA(ctx, cudaMemcpyAsync(io->out + off, d_out + off, m * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->d2h));
+        }
         ctx->counters[SP_CTR_LAUNCHES] += 2;
     }
     if (overlap) { /* join: later work on `stream` sees every result */
         SP_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux));
+        SP_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_join, 0));
+    }
+    if (io) {
+        SP_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->d2h));
         SP_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_join, 0));
     }
     ctx->counters[SP_CTR_EVALS] += n;
@@ -326,7 +369,10 @@ int sp_nnue_create(const void* net_image, size_t len, int device, SpNnue** out) 
         SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_head[b], cudaEventDisableTiming));
     }
     SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
     SP_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+    SP_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking));
+    SP_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking));
     ctx->d_act = ctx->d_act2[0];
     ctx->d_bucket = ctx->d_bucket2[0];
 
@@ -360,7 +406,11 @@ void sp_nnue_destroy(SpNnue* ctx) {
         if (ctx->ev_head[b]) cudaEventDestroy(ctx->ev_head[b]);
     }
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    for (cudaEvent_t e : ctx->ev_chunk) cudaEventDestroy(e);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    if (ctx->h2d) cudaStreamSynchronize(ctx->h2d), cudaStreamDestroy(ctx->h2d);
+    if (ctx->d2h) cudaStreamSynchronize(ctx->d2h), cudaStreamDestroy(ctx->d2h);
     cudaFree(ctx->d_act_big);
     cudaFree(ctx->d_bucket_big);
     cudaFree(ctx->d_boards);
@@ -433,9 +483,8 @@ int sp_nnue_eval_full(SpNnue* ctx, const SpPackedBoard* boards, size_t n, int32_
     if (!boards || !out) return fail(ctx, SP_ERR_INVALID, "null argument");
     DeviceGuard guard{ctx->device};
     if (const int rc = ensure_staging(ctx, n)) return rc;
-    SP_CUDA(ctx, cudaMemcpyAsync(ctx->d_boards, boards, n * sizeof(SpPackedBoard), cudaMemcpyHostToDevice, ctx->stream));
-    if (const int rc = eval_full_device(ctx, ctx->d_boards, n, ctx->d_out, ctx->stream)) return rc;
-    SP_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    const HostIo io{boards, out};
+    if (const int rc = eval_full_device(ctx, ctx->d_boards, n, ctx->d_out, ctx->stream, &io)) return rc;
     return finish(ctx, ctx->stream);
 }
 
