@@ -157,7 +157,9 @@ enum {
     SP_KERNEL_HEAD = 1,     /* activations -> evals (L1 IMMA, L2, L3) */
     SP_KERNEL_FT_SLOTS = 2, /* slot refresh / incremental update */
     SP_KERNEL_FT_GAMES = 3, /* playout walker */
-    SP_NUM_KERNEL_CLASSES = 4
+    SP_KERNEL_EXTRACT = 4,  /* boards -> row lists (split full refresh) */
+    SP_KERNEL_ACCUMULATE = 5, /* row lists -> activations (split full refresh) */
+    SP_NUM_KERNEL_CLASSES = 6
 };
 int sp_nnue_profile(SpNnue* ctx, int enable);
 int sp_nnue_profile_read(SpNnue* ctx, double ms[SP_NUM_KERNEL_CLASSES], uint64_t launches[SP_NUM_KERNEL_CLASSES]);

@@ -43,6 +43,8 @@ struct SpNnue {
     cudaEvent_t ev_ft[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr}, ev_join = nullptr, ev_start = nullptr;
     std::vector<cudaEvent_t> ev_chunk; /* one "inputs of chunk i have landed" event per chunk */
     bool overlap = true;
+    bool split = true;           /* full refresh as extract + accumulate kernels (else the fused ft_full kernel) */
+    void* d_lists[2] = {nullptr, nullptr};
     /* whole-stream scratch of the playout walker (one activation row per board) */
     uint8_t* d_act_big = nullptr;
     uint8_t* d_bucket_big = nullptr;
@@ -275,7 +277,17 @@ int eval_full_device(
         const int buf = overlap ? static_cast<int>(i & 1) : 0;
         if (io) SP_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_chunk[i], 0));
         if (overlap && i >= 2) SP_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_head[buf], 0)); /* scratch is free again */
-        {
+        if (ctx->split) {
+            {
+                Timed timed{ctx, stream, SP_KERNEL_EXTRACT};
+                launch_extract(ctx->net, d_boards + off, m, ctx->d_lists[buf], ctx->d_status, ctx->sm_count, stream);
+            }
+            {
+                Timed timed{ctx, stream, SP_KERNEL_ACCUMULATE};
+                launch_accumulate(ctx->net, ctx->d_lists[buf], m, ctx->d_act2[buf], ctx->d_bucket2[buf], ctx->sm_count, stream);
+            }
+            ctx->counters[SP_CTR_LAUNCHES] += 1;
+        } else {
             Timed timed{ctx, stream, SP_KERNEL_FT_FULL};
             launch_ft_full(ctx->net, d_boards + off, m, ctx->d_act2[buf], ctx->d_bucket2[buf], ctx->d_status, ctx->sm_count, stream);
         }
@@ -362,9 +374,11 @@ int sp_nnue_create(const void* net_image, size_t len, int device, SpNnue** out) 
         if (v >= 1) ctx->games_chunk = static_cast<uint32_t>(v);
     }
     if (const char* env = std::getenv("SP_NNUE_OVERLAP")) ctx->overlap = std::atoi(env) != 0;
+    if (const char* env = std::getenv("SP_NNUE_SPLIT")) ctx->split = std::atoi(env) != 0;
     for (int b = 0; b < 2; ++b) {
         SP_CUDA(nullptr, cudaMalloc(&ctx->d_act2[b], ctx->chunk * SP_L1_SIZE));
         SP_CUDA(nullptr, cudaMalloc(&ctx->d_bucket2[b], ctx->chunk));
+        if (ctx->split) SP_CUDA(nullptr, cudaMalloc(&ctx->d_lists[b], row_list_bytes(ctx->chunk)));
         SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_ft[b], cudaEventDisableTiming));
         SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_head[b], cudaEventDisableTiming));
     }
@@ -402,6 +416,7 @@ void sp_nnue_destroy(SpNnue* ctx) {
     for (int b = 0; b < 2; ++b) {
         cudaFree(ctx->d_act2[b]);
         cudaFree(ctx->d_bucket2[b]);
+        cudaFree(ctx->d_lists[b]);
         if (ctx->ev_ft[b]) cudaEventDestroy(ctx->ev_ft[b]);
         if (ctx->ev_head[b]) cudaEventDestroy(ctx->ev_head[b]);
     }

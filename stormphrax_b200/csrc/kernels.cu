@@ -45,6 +45,9 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef SP_FULL_MIN_BLOCKS
 #define SP_FULL_MIN_BLOCKS 4
 #endif
+#ifndef SP_ACC_MIN_BLOCKS
+#define SP_ACC_MIN_BLOCKS 3
+#endif
 #ifndef SP_GAMES_MIN_BLOCKS
 #define SP_GAMES_MIN_BLOCKS 2
 #endif
@@ -650,6 +653,122 @@ ft_full_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, size_t n
     }
 }
 
+/* ------------------------------------------------------------------ full refresh, split form
+ *
+ * The same work as ft_full_kernel in two kernels, each with the occupancy its phase wants:
+ *   extract_kernel     boards -> row lists (one RowListRecord per position and perspective) in global
+ *                      memory.  Branchy integer code, latency-bound: few registers, many warps.
+ *   accumulate_kernel  row lists -> activations.  One warp per (position, perspective); the next
+ *                      record is staged into shared memory by the TMA engine (cp.async.bulk + mbarrier)
+ *                      while the current one's rows stream in, so the row loop never waits for its
+ *                      own index list. */
+
+struct alignas(16) RowListRecord {
+    uint16_t n_psq, n_thr; /* padded entry counts */
+    uint8_t half;          /* which half of the activation row this perspective fills (0 = side to move) */
+    uint8_t bucket;        /* output bucket, 0xFF = rejected board */
+    uint8_t pad[10];
+    uint32_t psq[kPsqListCap];
+    uint32_t thr[kThrListCap];
+};
+static_assert(sizeof(RowListRecord) == 1200 && sizeof(RowListRecord) % 16 == 0, "bulk copies move whole records");
+
+__global__ void __launch_bounds__(kThreads, 4)
+extract_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, size_t n, RowListRecord* __restrict__ records,
+               DeviceStatus* status) {
+    __shared__ WarpScratch scratch[kWarpsPerCta];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratch& ws = scratch[warp];
+    const FeatureTables& t = *net.tables;
+    const size_t stride = static_cast<size_t>(gridDim.x) * kWarpsPerCta;
+    for (size_t pos = static_cast<size_t>(blockIdx.x) * kWarpsPerCta + warp; pos < n; pos += stride) {
+        const Decoded d = decode_board(boards + pos, lane, ws.mailbox[0]);
+        int err = d.ok ? 0 : kErrBadBoard;
+        if (!err && build_lists(t, nullptr, d, lane, ws) < 0) err = kErrCapacity;
+        if (err && lane == 0) flag_error(status, err);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            RowListRecord& rec = records[2 * pos + c];
+            if (lane == 0) {
+                rec.n_psq = err ? 0 : static_cast<uint16_t>(ws.n_psq_add[c]);
+                rec.n_thr = err ? 0 : static_cast<uint16_t>(ws.n_thr_add[c]);
+                rec.half = c == d.view.stm ? 0 : 1;
+                rec.bucket = err ? 0xFF : static_cast<uint8_t>(output_bucket(d.view.occ));
+            }
+            if (err) continue;
+            for (int i = lane; i < ws.n_psq_add[c]; i += 32) rec.psq[i] = ws.psq_add[c][i];
+            for (int i = lane; i < ws.n_thr_add[c]; i += 32) rec.thr[i] = ws.thr_add[c][i];
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+/* TMA engine: global -> shared bulk copy, completion counted in bytes on the mbarrier */
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+constexpr int kAccWarps = 8;
+
+__global__ void __launch_bounds__(kAccWarps * 32, SP_ACC_MIN_BLOCKS)
+accumulate_kernel(DeviceNet net, const RowListRecord* __restrict__ records, size_t n_items, uint8_t* __restrict__ act,
+                  uint8_t* __restrict__ bucket) {
+    __shared__ RowListRecord staged[kAccWarps][2];
+    __shared__ uint64_t full[kAccWarps][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        mbar_init(&full[warp][0], 1);
+        mbar_init(&full[warp][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const size_t stride = static_cast<size_t>(gridDim.x) * kAccWarps;
+    size_t item = static_cast<size_t>(blockIdx.x) * kAccWarps + warp;
+    if (item < n_items && lane == 0) {
+        mbar_expect_tx(&full[warp][0], sizeof(RowListRecord));
+        bulk_copy_g2s(&staged[warp][0], records + item, sizeof(RowListRecord), &full[warp][0]);
+    }
+    for (uint32_t k = 0; item < n_items; item += stride, ++k) {
+        const int buf = k & 1;
+        const size_t next = item + stride;
+        if (next < n_items && lane == 0) { /* stage the next record while this one is processed */
+            mbar_expect_tx(&full[warp][buf ^ 1], sizeof(RowListRecord));
+            bulk_copy_g2s(&staged[warp][buf ^ 1], records + next, sizeof(RowListRecord), &full[warp][buf ^ 1]);
+        }
+        while (!mbar_try_wait(&full[warp][buf], (k >> 1) & 1)) {}
+        const RowListRecord& rec = staged[warp][buf];
+        const size_t pos = item >> 1;
+        if (rec.bucket != 0xFF) {
+            uint32_t v[16];
+            rebuild_perspective(net, rec.psq, rec.n_psq, rec.thr, rec.n_thr, lane, v);
+            reinterpret_cast<uint4*>(act + pos * SP_L1_SIZE)[rec.half * 32 + lane] = activate(v);
+        }
+        if ((item & 1) == 0 && lane == 0) bucket[pos] = rec.bucket;
+        __syncwarp();
+        /* order this warp's generic-proxy reads of the buffer before the async-proxy write that refills it */
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+}
+
 /* ------------------------------------------------------------------ accumulator slots */
 
 __device__ __forceinline__ void load_slot_acc(const SlotStore& s, uint32_t slot, int c, int lane, uint32_t (&v)[16]) {
@@ -1000,6 +1119,28 @@ void launch_ft_full(
     int sm_count, cudaStream_t stream) {
     if (!n) return;
     ft_full_kernel<<<grid_for(n, kWarpsPerCta, sm_count, SP_FULL_MIN_BLOCKS), kThreads, 0, stream>>>(net, boards, n, act, bucket, status);
+}
+
+size_t row_list_bytes(size_t n_positions) { return n_positions * 2 * sizeof(RowListRecord); }
+
+void launch_ft_full_split(
+    const DeviceNet& net, const SpPackedBoard* boards, size_t n, void* row_lists, uint8_t* act, uint8_t* bucket,
+    DeviceStatus* status, int sm_count, cudaStream_t stream) {
+    if (!n) return;
+    RowListRecord* records = static_cast<RowListRecord*>(row_lists);
+    extract_kernel<<<grid_for(n, kWarpsPerCta, sm_count, 4), kThreads, 0, stream>>>(net, boards, n, records, status);
+    accumulate_kernel<<<grid_for(2 * n, kAccWarps, sm_count, SP_ACC_MIN_BLOCKS), kAccWarps * 32, 0, stream>>>(net, records, 2 * n, act, bucket);
+}
+
+void launch_extract(const DeviceNet& net, const SpPackedBoard* boards, size_t n, void* row_lists, DeviceStatus* status, int sm_count, cudaStream_t stream) {
+    if (!n) return;
+    extract_kernel<<<grid_for(n, kWarpsPerCta, sm_count, 4), kThreads, 0, stream>>>(net, boards, n, static_cast<RowListRecord*>(row_lists), status);
+}
+
+void launch_accumulate(const DeviceNet& net, const void* row_lists, size_t n, uint8_t* act, uint8_t* bucket, int sm_count, cudaStream_t stream) {
+    if (!n) return;
+    accumulate_kernel<<<grid_for(2 * n, kAccWarps, sm_count, SP_ACC_MIN_BLOCKS), kAccWarps * 32, 0, stream>>>(
+        net, static_cast<const RowListRecord*>(row_lists), 2 * n, act, bucket);
 }
 
 void launch_ft_slots(

@@ -68,6 +68,14 @@ void launch_ft_full(
     const DeviceNet& net, const SpPackedBoard* boards, size_t n, uint8_t* act, uint8_t* bucket, DeviceStatus* status,
     int sm_count, cudaStream_t stream);
 
+/* The same in two kernels: boards -> row lists (row_list_bytes(n) of scratch) -> activations. */
+size_t row_list_bytes(size_t n_positions);
+void launch_extract(
+    const DeviceNet& net, const SpPackedBoard* boards, size_t n, void* row_lists, DeviceStatus* status, int sm_count,
+    cudaStream_t stream);
+void launch_accumulate(
+    const DeviceNet& net, const void* row_lists, size_t n, uint8_t* act, uint8_t* bucket, int sm_count, cudaStream_t stream);
+
 /* slot refresh / update. src == nullptr: every dst slot is rebuilt from boards[i].
  * act may be nullptr (no evaluation wanted). */
 void launch_ft_slots(
