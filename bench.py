@@ -213,6 +213,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     boards, moves, starts = make_workload(rank, POSITIONS_PER_GPU)
     n = len(boards)
     ctx = api.Nnue(N.synthetic(NET_SEED).image, local_rank)
+    props = torch.cuda.get_device_properties(local_rank)
     # a real (non-default) stream: the library treats a NULL stream as "use the context's own"
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -312,12 +313,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "share_of_step": k_ms / (k_ms + other_ms) if k_ms + other_ms else None,
             "other_kernels_ms_per_launch": {k: v[0] / max(v[1], 1) for k, v in prof.items() if k != kernel and v[1]},
         }
+        # DRAM traffic per launch from the committed ncu capture of this kernel (profiles/traffic.json)
         traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_path):
             try:
-                roofline["traffic"] = json.load(open(traffic_path)).get(kernel)
+                entry = json.load(open(traffic_path)).get(kernel)
+                roofline["traffic"] = entry["dram_bytes_per_position"] * n * args.steps / max(k_launches, 1)
+                roofline["traffic_source"] = entry["source"]
             except Exception:
                 pass
+        roofline["algorithmic_bytes_per_launch"] = algo_bytes_per_launch
+        # the resource that actually binds these cache-resident kernels: the SM's 128 B/clk L1/LSU data path
+        sm_mhz = clock_summary.get("sm_mhz") or 1965.0
+        onchip_peak = props.multi_processor_count * 128 * sm_mhz * 1e6 / 1e9
+        roofline["onchip"] = {"limit": "L1/LSU data path, 128 B/clk/SM", "peak": onchip_peak, "unit": "GB/s", "frac": achieved / onchip_peak}
         cpu_rate, cpu_info = cpu_arm(boards, moves, starts, args.workload, 12.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

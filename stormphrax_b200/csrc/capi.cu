@@ -43,7 +43,7 @@ struct SpNnue {
     cudaEvent_t ev_ft[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr}, ev_join = nullptr, ev_start = nullptr;
     std::vector<cudaEvent_t> ev_chunk; /* one "inputs of chunk i have landed" event per chunk */
     bool overlap = true;
-    bool split = true;           /* full refresh as extract + accumulate kernels (else the fused ft_full kernel) */
+    bool split = false;          /* full refresh as extract + accumulate kernels instead of the fused ft_full kernel (SP_NNUE_SPLIT=1) */
     void* d_lists[2] = {nullptr, nullptr};
     /* whole-stream scratch of the playout walker (one activation row per board) */
     uint8_t* d_act_big = nullptr;

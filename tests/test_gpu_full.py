@@ -156,3 +156,28 @@ def test_full_size_properties(gpu_ctx, c_oracle):
     start = boards[0].tobytes()
     same = np.array([b.tobytes() == start for b in boards[:: 81][:200]])
     assert same.sum() > 1 and len(set(out[::81][:200][same].tolist())) == 1
+
+
+def test_split_extract_accumulate_path_bit_exact(net, golden, monkeypatch):
+    """SP_NNUE_SPLIT=1: boards -> row lists (extract_kernel) -> TMA-staged accumulate_kernel -> head."""
+    monkeypatch.setenv("SP_NNUE_SPLIT", "1")
+    monkeypatch.setenv("SP_NNUE_CHUNK", "1024")  # several chunks, double-buffered row lists
+    with api.Nnue(net.image, 0) as ctx:
+        assert (ctx.eval_full(golden["boards"]) == golden["evals"]).all()
+        assert (ctx.eval_full(golden["fen_boards"]) == golden["fen_evals"]).all()
+        bad = golden["boards"][:20].copy()
+        bad["occupancy"][3] = 0
+        out = np.zeros(20, dtype=np.int32)
+        with pytest.raises(api.NnueError):
+            ctx.eval_full(bad, out)
+        assert out[3] == INT32_MIN and (np.delete(out, 3) == np.delete(golden["evals"][:20], 3)).all()
+
+
+def test_small_chunks_exercise_the_overlap_pipeline(net, golden, monkeypatch):
+    """Many tiny chunks: double-buffered scratch, auxiliary-stream head, per-chunk uploads/downloads."""
+    monkeypatch.setenv("SP_NNUE_CHUNK", "256")
+    monkeypatch.setenv("SP_NNUE_GAMES_CHUNK", "3")
+    with api.Nnue(net.image, 0) as ctx:
+        for _ in range(3):
+            assert (ctx.eval_full(golden["boards"]) == golden["evals"]).all()
+            assert (ctx.eval_playouts(golden["boards"], golden["starts"]) == golden["evals"]).all()
