@@ -31,7 +31,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Mpositions/sec batched NNUE (bit-exact vs reference CPU path)"
 UNIT = "Mpos/s"
-POSITIONS_PER_GPU = 1 << 20
+POSITIONS_PER_GPU = 1 << 20   # full refresh: BASELINE configs[1]
+PLAYOUTS_PER_GPU = 1 << 16    # incremental: BASELINE configs[2], 65,536 playouts of <= 80 plies (about 5.26 M positions)
 MAX_PLIES = 80
 NET_SEED = 1234
 L2_FLUSH_BYTES = 256 << 20
@@ -50,10 +51,13 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_workload(rank: int, n_positions: int):
-    """Deterministic synthetic positions for this rank: whole games, trimmed to n_positions."""
+def make_workload(rank: int, n_positions: int, workload: str = "full"):
+    """Deterministic synthetic positions for this rank: whole games (playouts), or whole games trimmed
+    to n_positions (full refresh)."""
     from stormphrax_b200 import api
 
+    if workload == "playouts":
+        return api.playouts(42 + 1000003 * rank, PLAYOUTS_PER_GPU, MAX_PLIES)
     n_games = n_positions // 78 + 64  # random playouts rarely end before ply 80
     while True:
         boards, moves, starts = api.playouts(42 + 1000003 * rank, n_games, MAX_PLIES)
@@ -161,7 +165,7 @@ def cpu_arm(boards, moves, starts, workload: str, budget_s: float):
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
-    boards, moves, starts = make_workload(0, POSITIONS_PER_GPU)
+    boards, moves, starts = make_workload(0, POSITIONS_PER_GPU, args.workload)
     budget = min(12.0, 120.0 / max(args.steps, 1))
     rates, info = [], None
     for i in range(args.warmup + args.steps):
@@ -186,8 +190,9 @@ def workload_config(workload: str, **extra):
     cfg = {
         "workload": ("full-refresh NNUE eval of 1,048,576 random legal positions per GPU (BASELINE configs[1])"
                      if workload == "full" else
-                     "incremental NNUE eval along random playouts, 1,048,576 positions per GPU (BASELINE configs[2])"),
-        "positions_per_gpu": POSITIONS_PER_GPU, "max_plies": MAX_PLIES,
+                     "incremental NNUE eval along 65,536 random playouts of <= 80 plies per GPU (BASELINE configs[2])"),
+        "positions_per_gpu": POSITIONS_PER_GPU if workload == "full" else None, "playouts_per_gpu": PLAYOUTS_PER_GPU if workload != "full" else None,
+        "max_plies": MAX_PLIES,
         "network": f"synthetic CBNF, numpy default_rng({NET_SEED}), arch 16x704+64368 -> 1024x2 -> 32 -> 64 -> 1 x8",
         "parallelism": "positions sharded by rank, network replicated, no data-path collective",
         "l2": "L2 flushed (256 MiB write) between timed steps",
@@ -210,7 +215,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     D.init("nccl", local_rank)
 
-    boards, moves, starts = make_workload(rank, POSITIONS_PER_GPU)
+    boards, moves, starts = make_workload(rank, POSITIONS_PER_GPU, args.workload)
     n = len(boards)
     ctx = api.Nnue(N.synthetic(NET_SEED).image, local_rank)
     props = torch.cuda.get_device_properties(local_rank)
@@ -334,6 +339,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "dtype": "int16/int8/int32", "data": "synthetic",
             "config": workload_config(
                 args.workload,
+                positions_this_rank=n,
                 mean_rows_per_perspective={k: v / n / 2 for k, v in counts.items()},
                 playout_stats_per_position=({k: v / n for k, v in st.items()} if args.workload == "playouts" else None),
             ),

@@ -12,7 +12,8 @@ from bench import make_workload
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "both"
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
-    boards, moves, starts = make_workload(0, n)
+    boards, moves, starts = make_workload(0, n, "playouts" if (which == "playouts" and len(sys.argv) <= 2) else "full")
+    n = len(boards)
     ctx = api.Nnue(N.synthetic(1234).image, 0)
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); s = stream.cuda_stream
     d_boards = torch.from_numpy(boards.view(np.uint8).reshape(-1)).cuda()
