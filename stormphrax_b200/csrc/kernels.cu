@@ -972,10 +972,27 @@ __device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, 
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-constexpr int kHeadWarps = 4;
-constexpr int kSkipStride = 65; /* int32 words per row, padded against bank conflicts */
+constexpr int kHeadWarps = 8;
+constexpr int kHeadRows = 256;  /* positions per CTA */
+constexpr int kW1Bytes = SP_L1_SIZE * SP_L2_SIZE;                  /* one bucket's L1 weights: 32 KB */
+constexpr int kW2Words = 2 * SP_L2_SIZE * SP_L3_SIZE;              /* one bucket's L2 weights: 4096 int32 */
+
+struct HeadShared {
+    __align__(16) int8_t w1[kW1Bytes];                      /* current bucket, reference layout [k/4][o][k%4] */
+    __align__(16) int32_t w2[kW2Words];                     /* current bucket, [input][output] */
+    uint32_t skip_dot[kHeadWarps][16];                      /* per row: sum over the L1 outputs of skip * W3 (L3's skip term) */
+    __align__(16) int l2in[kHeadWarps][2 * SP_L2_SIZE][16]; /* skip >> 6, transposed: [input][row] */
+    uint16_t order[kHeadRows + 16 * SP_OUTPUT_BUCKETS];     /* rows grouped by bucket, each group padded to 16 */
+    int count[SP_OUTPUT_BUCKETS];                           /* rows per bucket */
+    int start[SP_OUTPUT_BUCKETS + 1];                       /* first slot of each bucket's group in `order` */
+};
+constexpr uint16_t kNoRow = 0xFFFF;
 
 /*
+ * One CTA = 256 consecutive positions, grouped by output bucket in shared memory so that every
+ * 16-row tile has ONE bucket; per bucket present (normally one or two) the CTA stages that bucket's
+ * L1 and L2 weights (48 KB) in shared memory once and its warps share the tiles.
+ *
  * L1: the contraction index k may be visited in any order as long as A and B agree.  Per 64-wide
  * k-step, lane (g = lane / 4, t = lane % 4) loads 16 contiguous activation bytes of rows g and
  * g + 8 (k = 64 s + 16 t ...) and, for each of the 4 k-quads inside them, 16 contiguous weight
@@ -984,126 +1001,164 @@ constexpr int kSkipStride = 65; /* int32 words per row, padded against bank conf
  * holds outputs 8 t + nt and 8 t + 4 + nt of rows g and g + 8.
  *
  * L2 / L3: lane p owns L2 outputs p and p + 32 for all 16 rows of the tile; per input i it needs two
- * weights (one coalesced 128-byte load per half across the warp) and the 16 rows' inputs (four
- * broadcast LDS.128 from the transposed l2in[i][row] array).  The L3 dot product is closed with one
- * REDUX per row.  Rows of different output buckets are handled by looping over the buckets present
- * in the tile (normally one) and keeping each row's result from its own bucket's pass.
+ * weights (conflict-free LDS) and the 16 rows' inputs (four broadcast LDS.128 from the transposed
+ * l2in[i][row] array).  The L3 dot product is closed with one REDUX per row.
  */
-__global__ void __launch_bounds__(kHeadWarps * 32)
+static_assert(sizeof(HeadShared) * 2 <= 227 * 1024, "two CTAs per SM");
+__global__ void __launch_bounds__(kHeadWarps * 32, 2)
 head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __restrict__ bucket, size_t n,
             int32_t* __restrict__ out, const uint32_t* __restrict__ range, uint32_t range_len) {
-    __shared__ int skip[kHeadWarps][16][kSkipStride];                   /* L1 output incl. the squared half: L3's skip input */
-    __shared__ __align__(16) int l2in[kHeadWarps][2 * SP_L2_SIZE][16];  /* skip >> 6, transposed: [input][row] */
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ __align__(16) unsigned char head_smem[];
+    HeadShared& sh = *reinterpret_cast<HeadShared*>(head_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const size_t tile = static_cast<size_t>(blockIdx.x) * kHeadWarps + warp;
-    size_t base = tile * 16;
+    size_t base = static_cast<size_t>(blockIdx.x) * kHeadRows;
     if (range) { /* positions [range[0], range[range_len]) */
         base += range[0];
         n = range[range_len];
     }
     if (base >= n) return;
-    const size_t last = n - 1;
-    const size_t r0 = min(base + g, last), r1 = min(base + g + 8, last);
-    /* buckets of the 16 rows: lane i < 16 holds row i's */
-    int my_bucket = 0xFF;
-    if (lane < 16 && base + lane < n) my_bucket = bucket[base + lane];
-    const int b0 = __shfl_sync(kFull, my_bucket, g), b1 = __shfl_sync(kFull, my_bucket, g + 8);
-    const unsigned present = __reduce_or_sync(kFull, my_bucket < SP_OUTPUT_BUCKETS ? 1u << my_bucket : 0u);
+    const int rows = static_cast<int>(min(static_cast<size_t>(kHeadRows), n - base));
 
-    const uint4* a_row0 = reinterpret_cast<const uint4*>(act + r0 * SP_L1_SIZE) + t;
-    const uint4* a_row1 = reinterpret_cast<const uint4*>(act + r1 * SP_L1_SIZE) + t;
-
-    for (unsigned todo = present; todo; todo &= todo - 1) {
-        const int b = __ffs(todo) - 1;
-        int c[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) c[i][j] = 0;
-        const uint4* w = reinterpret_cast<const uint4*>(net.l1_w + static_cast<size_t>(b) * SP_L1_SIZE * SP_L2_SIZE) + g;
-#pragma unroll 4
-        for (int s = 0; s < SP_L1_SIZE / 64; ++s) {
-            const uint4 alo = __ldg(a_row0 + s * 4), ahi = __ldg(a_row1 + s * 4);
-            uint4 q[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) q[j] = __ldg(w + static_cast<size_t>(s * 16 + t * 4 + j) * 8);
-            const uint32_t al[4] = {alo.x, alo.y, alo.z, alo.w}, ah[4] = {ahi.x, ahi.y, ahi.z, ahi.w};
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                const uint32_t q0[4] = {q[2 * m].x, q[2 * m].y, q[2 * m].z, q[2 * m].w};
-                const uint32_t q1[4] = {q[2 * m + 1].x, q[2 * m + 1].y, q[2 * m + 1].z, q[2 * m + 1].w};
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) mma_u8s8(c[nt], al[2 * m], ah[2 * m], al[2 * m + 1], ah[2 * m + 1], q0[nt], q1[nt]);
-            }
-        }
-        /* L1 epilogue + dual activation, multilayer.h:219-256 (kShift = -2) */
-#pragma unroll
-        for (int hrow = 0; hrow < 2; ++hrow) {
-            if ((hrow ? b1 : b0) != b) continue;
-            const int r = g + 8 * hrow;
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int o = 8 * t + 4 * cc + nt;
-                    const int x = static_cast<int>(static_cast<uint32_t>(c[nt][hrow * 2 + cc] >> 2)
-                                                   + static_cast<uint32_t>(__ldg(net.l1_b + b * SP_L2_SIZE + o)));
-                    const int cr = min(max(x, 0), 4096);
-                    int sq = static_cast<int>(static_cast<uint32_t>(x) * static_cast<uint32_t>(x)); /* wraps BEFORE the min */
-                    sq = min(sq, 16777216);
-                    skip[warp][r][o] = cr << 6;
-                    skip[warp][r][SP_L2_SIZE + o] = sq >> 6;
-                    l2in[warp][o][r] = cr;                    /* (cr << 6) >> 6 */
-                    l2in[warp][SP_L2_SIZE + o][r] = sq >> 12; /* (sq >> 6) >> 6 */
-                }
-        }
+    /* ---- group the CTA's rows by bucket (counting sort; order within a bucket = position order) */
+    const int my_bucket = tid < rows ? bucket[base + tid] : 0xFF;
+    const bool valid = my_bucket < SP_OUTPUT_BUCKETS;
+    if (tid < SP_OUTPUT_BUCKETS) sh.count[tid] = 0;
+    __syncthreads();
+    int rank_in_warp = 0;
+    if (valid) {
+        const unsigned peers = __match_any_sync(__activemask(), my_bucket);
+        rank_in_warp = __popc(peers & ((1u << lane) - 1));
+        /* the first lane of each peer group reserves the group's slots */
+        int first_slot = 0;
+        const int leader = __ffs(peers) - 1;
+        if (lane == leader) first_slot = atomicAdd(&sh.count[my_bucket], __popc(peers));
+        rank_in_warp += __shfl_sync(peers, first_slot, leader);
     }
-    __syncwarp();
+    __syncthreads();
+    if (tid == 0) {
+        int at = 0;
+        for (int b = 0; b < SP_OUTPUT_BUCKETS; ++b) {
+            sh.start[b] = at;
+            at += (sh.count[b] + 15) & ~15;
+        }
+        sh.start[SP_OUTPUT_BUCKETS] = at;
+    }
+    for (int i = tid; i < kHeadRows + 16 * SP_OUTPUT_BUCKETS; i += kHeadWarps * 32) sh.order[i] = kNoRow;
+    __syncthreads();
+    if (valid) sh.order[sh.start[my_bucket] + rank_in_warp] = static_cast<uint16_t>(tid);
+    if (tid < rows && !valid) out[base + tid] = INT32_MIN; /* rejected board */
+    __syncthreads();
 
-    /* L2 + L3, multilayer.h:261-447 */
-    int32_t result = INT32_MIN;
-    for (unsigned todo = present; todo; todo &= todo - 1) {
-        const int b = __ffs(todo) - 1;
-        uint32_t acc[16][2];
+    for (int b = 0; b < SP_OUTPUT_BUCKETS; ++b) {
+        const int n_tiles = (sh.start[b + 1] - sh.start[b]) >> 4;
+        if (!n_tiles) continue;
+        /* ---- stage this bucket's weights */
         {
-            const uint32_t bias0 = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + lane));
-            const uint32_t bias1 = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + lane + 32));
-#pragma unroll
-            for (int r = 0; r < 16; ++r) acc[r][0] = bias0, acc[r][1] = bias1;
+            const uint4* src1 = reinterpret_cast<const uint4*>(net.l1_w + static_cast<size_t>(b) * kW1Bytes);
+            uint4* dst1 = reinterpret_cast<uint4*>(sh.w1);
+            for (int i = tid; i < kW1Bytes / 16; i += kHeadWarps * 32) dst1[i] = __ldg(src1 + i);
+            const uint4* src2 = reinterpret_cast<const uint4*>(net.l2_w + static_cast<size_t>(b) * kW2Words);
+            uint4* dst2 = reinterpret_cast<uint4*>(sh.w2);
+            for (int i = tid; i < kW2Words / 4; i += kHeadWarps * 32) dst2[i] = __ldg(src2 + i);
         }
-        const int* w2 = net.l2_w + static_cast<size_t>(b) * 2 * SP_L2_SIZE * SP_L3_SIZE + lane;
+        __syncthreads();
+        for (int tile = warp; tile < n_tiles; tile += kHeadWarps) {
+            const uint16_t* ord = sh.order + sh.start[b] + tile * 16;
+            const int row0 = ord[g], row1 = ord[g + 8];
+            /* padding slots read row 0 of the CTA; their results are never written */
+            const uint4* a_row0 = reinterpret_cast<const uint4*>(act + (base + (row0 == kNoRow ? 0 : row0)) * SP_L1_SIZE) + t;
+            const uint4* a_row1 = reinterpret_cast<const uint4*>(act + (base + (row1 == kNoRow ? 0 : row1)) * SP_L1_SIZE) + t;
+            int c[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c[i][j] = 0;
+            const uint4* w = reinterpret_cast<const uint4*>(sh.w1) + g;
 #pragma unroll 4
-        for (int i = 0; i < 2 * SP_L2_SIZE; ++i) {
-            const uint32_t w0 = static_cast<uint32_t>(__ldg(w2 + i * SP_L3_SIZE));
-            const uint32_t w1 = static_cast<uint32_t>(__ldg(w2 + i * SP_L3_SIZE + 32));
-            const int4* in4 = reinterpret_cast<const int4*>(l2in[warp][i]);
+            for (int s = 0; s < SP_L1_SIZE / 64; ++s) {
+                const uint4 alo = __ldg(a_row0 + s * 4), ahi = __ldg(a_row1 + s * 4);
+                uint4 q[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int4 v = in4[q];
-                const uint32_t in[4] = {static_cast<uint32_t>(v.x), static_cast<uint32_t>(v.y), static_cast<uint32_t>(v.z), static_cast<uint32_t>(v.w)};
+                for (int j = 0; j < 4; ++j) q[j] = w[(s * 16 + t * 4 + j) * 8];
+                const uint32_t al[4] = {alo.x, alo.y, alo.z, alo.w}, ah[4] = {ahi.x, ahi.y, ahi.z, ahi.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    acc[q * 4 + e][0] += in[e] * w0;
-                    acc[q * 4 + e][1] += in[e] * w1;
+                for (int m = 0; m < 2; ++m) {
+                    const uint32_t q0[4] = {q[2 * m].x, q[2 * m].y, q[2 * m].z, q[2 * m].w};
+                    const uint32_t q1[4] = {q[2 * m + 1].x, q[2 * m + 1].y, q[2 * m + 1].z, q[2 * m + 1].w};
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) mma_u8s8(c[nt], al[2 * m], ah[2 * m], al[2 * m + 1], ah[2 * m + 1], q0[nt], q1[nt]);
                 }
             }
-        }
-        const uint32_t w3_0 = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + lane));
-        const uint32_t w3_1 = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + lane + 32));
-        const uint32_t bias3 = static_cast<uint32_t>(__ldg(net.l3_b + b));
+            /* L1 epilogue + dual activation, multilayer.h:219-256 (kShift = -2) */
+            /* The L1 outputs also feed L3 directly (skip connection, multilayer.h:353-446).  All sums are
+             * modulo 2^32, so that term is summed here, where the outputs are in registers. */
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const int c0 = min(max(static_cast<int>(acc[r][0]), 0), 262144);
-            const int c1 = min(max(static_cast<int>(acc[r][1]), 0), 262144);
-            const uint32_t part = (static_cast<uint32_t>(c0) + static_cast<uint32_t>(skip[warp][r][lane])) * w3_0
-                                + (static_cast<uint32_t>(c1) + static_cast<uint32_t>(skip[warp][r][lane + 32])) * w3_1;
-            const uint32_t l3 = __reduce_add_sync(kFull, part) + bias3;
-            if (lane == r && my_bucket == b)
-                result = static_cast<int32_t>(static_cast<int64_t>(static_cast<int32_t>(l3)) * 400 / 16777216); /* truncates toward zero */
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int r = g + 8 * hrow;
+                uint32_t dot = 0;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int o = 8 * t + 4 * cc + nt;
+                        const int x = static_cast<int>(static_cast<uint32_t>(c[nt][hrow * 2 + cc] >> 2)
+                                                       + static_cast<uint32_t>(__ldg(net.l1_b + b * SP_L2_SIZE + o)));
+                        const int cr = min(max(x, 0), 4096);
+                        int sq = static_cast<int>(static_cast<uint32_t>(x) * static_cast<uint32_t>(x)); /* wraps BEFORE the min */
+                        sq = min(sq, 16777216);
+                        dot += static_cast<uint32_t>(cr << 6) * static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + o))
+                             + static_cast<uint32_t>(sq >> 6) * static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + SP_L2_SIZE + o));
+                        sh.l2in[warp][o][r] = cr;                    /* (cr << 6) >> 6 */
+                        sh.l2in[warp][SP_L2_SIZE + o][r] = sq >> 12; /* (sq >> 6) >> 6 */
+                    }
+                dot += __shfl_xor_sync(kFull, dot, 1);
+                dot += __shfl_xor_sync(kFull, dot, 2);
+                if (t == 0) sh.skip_dot[warp][r] = dot;
+            }
+            __syncwarp();
+
+            /* L2 + L3, multilayer.h:261-447 */
+            uint32_t acc[16][2];
+            {
+                const uint32_t bias0 = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + lane));
+                const uint32_t bias1 = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + lane + 32));
+#pragma unroll
+                for (int r = 0; r < 16; ++r) acc[r][0] = bias0, acc[r][1] = bias1;
+            }
+#pragma unroll 4
+            for (int i = 0; i < 2 * SP_L2_SIZE; ++i) {
+                const uint32_t w0 = static_cast<uint32_t>(sh.w2[i * SP_L3_SIZE + lane]);
+                const uint32_t w1 = static_cast<uint32_t>(sh.w2[i * SP_L3_SIZE + lane + 32]);
+                const int4* in4 = reinterpret_cast<const int4*>(sh.l2in[warp][i]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int4 v = in4[q];
+                    const uint32_t in[4] = {static_cast<uint32_t>(v.x), static_cast<uint32_t>(v.y), static_cast<uint32_t>(v.z), static_cast<uint32_t>(v.w)};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        acc[q * 4 + e][0] += in[e] * w0;
+                        acc[q * 4 + e][1] += in[e] * w1;
+                    }
+                }
+            }
+            const uint32_t w3_0 = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + lane));
+            const uint32_t w3_1 = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + lane + 32));
+            const uint32_t bias3 = static_cast<uint32_t>(__ldg(net.l3_b + b));
+            int32_t result = 0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int c0 = min(max(static_cast<int>(acc[r][0]), 0), 262144);
+                const int c1 = min(max(static_cast<int>(acc[r][1]), 0), 262144);
+                const uint32_t part = static_cast<uint32_t>(c0) * w3_0 + static_cast<uint32_t>(c1) * w3_1;
+                const uint32_t l3 = __reduce_add_sync(kFull, part) + sh.skip_dot[warp][r] + bias3;
+                if (lane == r) result = static_cast<int32_t>(static_cast<int64_t>(static_cast<int32_t>(l3)) * 400 / 16777216); /* truncates toward zero */
+            }
+            if (lane < 16 && ord[lane] != kNoRow) out[base + ord[lane]] = result;
+            __syncwarp();
         }
+        __syncthreads(); /* the next bucket overwrites the staged weights */
     }
-    if (lane < 16 && base + lane < n) out[base + lane] = result;
 }
 
 int grid_for(size_t n_warp_items, int warps_per_cta, int sm_count, int ctas_per_sm) {
@@ -1168,9 +1223,13 @@ void launch_head(
     const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, const uint32_t* range,
     DeviceStatus*, int, cudaStream_t stream, uint32_t range_len) {
     if (!n) return;
-    const size_t tiles = (n + 15) / 16;
-    const unsigned grid = static_cast<unsigned>((tiles + kHeadWarps - 1) / kHeadWarps);
-    head_kernel<<<grid, kHeadWarps * 32, 0, stream>>>(net, act, bucket, n, out, range, range_len);
+    static bool configured = false; /* opt in to > 48 KB of dynamic shared memory once per process */
+    if (!configured) {
+        cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadShared)));
+        configured = true;
+    }
+    const unsigned grid = static_cast<unsigned>((n + kHeadRows - 1) / kHeadRows);
+    head_kernel<<<grid, kHeadWarps * 32, sizeof(HeadShared), stream>>>(net, act, bucket, n, out, range, range_len);
 }
 
 } // namespace sp::gpu
