@@ -159,7 +159,8 @@ enum {
     SP_KERNEL_FT_GAMES = 3, /* playout walker */
     SP_KERNEL_EXTRACT = 4,  /* boards -> row lists (split full refresh) */
     SP_KERNEL_ACCUMULATE = 5, /* row lists -> activations (split full refresh) */
-    SP_NUM_KERNEL_CLASSES = 6
+    SP_KERNEL_REBUILDS = 6, /* playout walker: planning + computing the rebuilt accumulators ahead of the walk */
+    SP_NUM_KERNEL_CLASSES = 7
 };
 int sp_nnue_profile(SpNnue* ctx, int enable);
 int sp_nnue_profile_read(SpNnue* ctx, double ms[SP_NUM_KERNEL_CLASSES], uint64_t launches[SP_NUM_KERNEL_CLASSES]);

@@ -43,6 +43,9 @@ struct SpNnue {
     cudaEvent_t ev_ft[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr}, ev_join = nullptr, ev_start = nullptr;
     std::vector<cudaEvent_t> ev_chunk; /* one "inputs of chunk i have landed" event per chunk */
     bool overlap = true;
+    bool plan_rebuilds = true;   /* playout walker: rebuilds computed ahead by their own kernel (SP_NNUE_PLAN_REBUILDS=0: inline) */
+    RebuildPlan plan{};          /* scratch of that scheme, sized for the largest stream seen */
+    size_t plan_boards = 0;
     bool split = false;          /* full refresh as extract + accumulate kernels instead of the fused ft_full kernel (SP_NNUE_SPLIT=1) */
     void* d_lists[2] = {nullptr, nullptr};
     /* whole-stream scratch of the playout walker (one activation row per board) */
@@ -375,6 +378,7 @@ int sp_nnue_create(const void* net_image, size_t len, int device, SpNnue** out) 
     }
     if (const char* env = std::getenv("SP_NNUE_OVERLAP")) ctx->overlap = std::atoi(env) != 0;
     if (const char* env = std::getenv("SP_NNUE_SPLIT")) ctx->split = std::atoi(env) != 0;
+    if (const char* env = std::getenv("SP_NNUE_PLAN_REBUILDS")) ctx->plan_rebuilds = std::atoi(env) != 0;
     for (int b = 0; b < 2; ++b) {
         SP_CUDA(nullptr, cudaMalloc(&ctx->d_act2[b], ctx->chunk * SP_L1_SIZE));
         SP_CUDA(nullptr, cudaMalloc(&ctx->d_bucket2[b], ctx->chunk));
@@ -426,6 +430,10 @@ void sp_nnue_destroy(SpNnue* ctx) {
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->h2d) cudaStreamSynchronize(ctx->h2d), cudaStreamDestroy(ctx->h2d);
     if (ctx->d2h) cudaStreamSynchronize(ctx->d2h), cudaStreamDestroy(ctx->d2h);
+    cudaFree(ctx->plan.slot);
+    cudaFree(ctx->plan.items);
+    cudaFree(ctx->plan.acc);
+    cudaFree(ctx->plan.counters);
     cudaFree(ctx->d_act_big);
     cudaFree(ctx->d_bucket_big);
     cudaFree(ctx->d_boards);

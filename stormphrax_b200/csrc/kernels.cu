@@ -19,6 +19,8 @@
  */
 #include "kernels.cuh"
 
+#include <algorithm>
+
 #include "sp_delta.h"
 
 namespace sp::gpu {
@@ -297,11 +299,12 @@ __device__ __forceinline__ int enqueue_delta(
  * row lists.  Kings of the current board orient both boards' features: a perspective whose king changed
  * side or bucket is rebuilt, not updated (threats.cpp:170-221). */
 __device__ __forceinline__ void process_tasks(
-    const FeatureTables& t, const BoardView& b, int rebuild, int n_tasks, int lane, WarpScratch& ws, int (&n_full)[2],
-    int (&n_dadd)[2], int (&n_dsub)[2]) {
+    const FeatureTables& t, const BoardView& b, int rebuild, int external, int n_tasks, int lane, WarpScratch& ws,
+    int (&n_full)[2], int (&n_dadd)[2], int (&n_dsub)[2]) {
     const int c = lane & 1;
     const unsigned mine = (c ? 0xAAAAAAAAu : 0x55555555u) & ((1u << lane) - 1); /* earlier lanes of my perspective */
     const bool rebuilt = (rebuild >> c) & 1;
+    const bool wanted = !((external >> c) & 1);
 #pragma unroll 1
     for (int base = 0; base < n_tasks; base += 16) {
         const int i = base + (lane >> 1);
@@ -309,7 +312,7 @@ __device__ __forceinline__ void process_tasks(
         int32_t idx = -1;
         if (i < n_tasks) {
             task = ws.tasks[i];
-            if (((task & kTaskFull) != 0) == rebuilt) {
+            if (wanted && ((task & kTaskFull) != 0) == rebuilt) {
                 const int sq0 = task & 0xFF, sq1 = (task >> 8) & 0xFF, p0 = (task >> 16) & 0xF, p1 = (task >> 24) & 0xF;
                 const int ksq = c ? b.king[1] : b.king[0];
                 idx = (task & kTaskPawnPair) ? static_cast<int32_t>(pp_index(c, ksq, p0, sq0, p1, sq1))
@@ -348,10 +351,11 @@ __device__ __forceinline__ void process_tasks(
  * A perspective is rebuilt when its king changes input bucket or board half (psq.h:264-283,
  * nnue_state.h:118-128), when more than kMaxChanged squares differ, or when a delta list overflows.
  * Returns -1 if a full list exceeds the reference's bound of 256 entries.
- */
+ * `external`: perspectives whose fresh accumulator comes from elsewhere (RebuildPlan): nothing is
+ * listed for them.  `only`: with no predecessor, the perspectives to rebuild (default both). */
 __device__ __forceinline__ int build_lists(
-    const FeatureTables& t, const BoardView* before, const Decoded& d, int lane, WarpScratch& ws) {
-    int rebuild = 3;
+    const FeatureTables& t, const BoardView* before, const Decoded& d, int lane, WarpScratch& ws, int external = 0, int only = 3) {
+    int rebuild = only & ~external;
     uint64_t changed = 0;
     if (before) {
         const unsigned lo = __ballot_sync(kFull, before->mailbox[lane] != d.view.mailbox[lane]);
@@ -359,19 +363,21 @@ __device__ __forceinline__ int build_lists(
         changed = static_cast<uint64_t>(hi) << 32 | lo;
         rebuild = (needs_refresh(t, *before, d.view, kBlack) ? 1 : 0) | (needs_refresh(t, *before, d.view, kWhite) ? 2 : 0);
         if (__popcll(changed) > kMaxChanged) rebuild = 3;
+        rebuild &= ~external;
     }
     for (;;) {
         int n_tasks = 0;
         int n_full[2] = {0, 0}, n_dadd[2] = {0, 0}, n_dsub[2] = {0, 0}, n_psq_delta[2] = {0, 0};
-        if (rebuild != 3) n_tasks = enqueue_delta(t, *before, d.view, changed, rebuild, lane, ws, n_tasks, n_psq_delta);
+        const int skip = rebuild | external; /* perspectives that take no delta rows */
+        if (before && skip != 3) n_tasks = enqueue_delta(t, *before, d.view, changed, skip, lane, ws, n_tasks, n_psq_delta);
         if (n_tasks > kTaskCap - 32) { /* far too many candidates for an update: rebuild instead */
-            rebuild = 3;
+            rebuild = 3 & ~external;
             __syncwarp();
             continue;
         }
         auto flush = [&](int queued) {
             __syncwarp();
-            process_tasks(t, d.view, rebuild, queued, lane, ws, n_full, n_dadd, n_dsub);
+            process_tasks(t, d.view, rebuild, external, queued, lane, ws, n_full, n_dadd, n_dsub);
             __syncwarp();
             return 0;
         };
@@ -387,13 +393,14 @@ __device__ __forceinline__ int build_lists(
         }
         if (too_long) return -1; /* a from-scratch list does not fit: the reference's own limit */
         if (overflow) {
-            rebuild = 3; /* an over-long delta: fall back to rebuilding */
+            rebuild = 3 & ~external; /* an over-long delta: fall back to rebuilding */
             __syncwarp();
             continue;
         }
         /* top the lists up with the zero row to whole load batches and publish the padded lengths */
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+            if ((external >> c) & 1) continue;
             if ((rebuild >> c) & 1) {
                 const int n_psq = d.n_pieces + 1, n_psq_pad = (n_psq + kPsqGroup - 1) / kPsqGroup * kPsqGroup;
                 const int n_thr_pad = (n_full[c] + kThrGroupFull - 1) / kThrGroupFull * kThrGroupFull;
@@ -885,11 +892,101 @@ slot_activate_kernel(SlotStore slots, const uint32_t* __restrict__ ids, const ui
 
 /* ------------------------------------------------------------------ playout walker */
 
-/* One warp plays through one game: both accumulators stay in registers from ply to ply
- * (datagen form, src/datagen/datagen.cpp:257-262: applyMove + applyImmediately + evaluate). */
+/* King squares of a packed record without decoding the board: nibble i belongs to the i-th occupied
+ * square (marlinformat.h:43-68).  Returns false for a malformed record. */
+__device__ __forceinline__ bool find_kings(const SpPackedBoard* board, int (&king)[2]) {
+    const uint4* p = reinterpret_cast<const uint4*>(board);
+    const uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    const uint64_t occ = static_cast<uint64_t>(lo.y) << 32 | lo.x;
+    const int n = __popcll(occ);
+    if (n < 2 || n > 32) return false;
+    const uint32_t words[4] = {lo.z, lo.w, hi.x, hi.y};
+    int idx[2] = {-1, -1}, found = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        /* a nibble equals 5 (white king) or 13 (black king) iff its low three bits are 101 */
+        uint32_t m = words[w] ^ 0x22222222u; /* low three bits 101 -> 111 */
+        m = m & (m >> 1) & (m >> 2) & 0x11111111u;
+        while (m) {
+            const int nib = (__ffs(m) - 1) >> 2;
+            m &= m - 1;
+            const int i = w * 8 + nib;
+            if (i < n) {
+                idx[(words[w] >> (nib * 4 + 3)) & 1 ? kBlack : kWhite] = i;
+                ++found;
+            }
+        }
+    }
+    if (found != 2 || idx[0] < 0 || idx[1] < 0) return false;
+    king[kBlack] = nth_piece_square(occ, idx[kBlack]);
+    king[kWhite] = nth_piece_square(occ, idx[kWhite]);
+    return true;
+}
+
+struct KingPair {
+    int king[2];
+};
+
+/* One thread per game: which (board, perspective) pairs need a fresh accumulator. */
+__global__ void plan_rebuilds_kernel(DeviceNet net, RebuildPlan plan, const SpPackedBoard* __restrict__ boards,
+                                     const uint32_t* __restrict__ game_start, uint32_t n_games) {
+    const FeatureTables& t = *net.tables;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_games; g += gridDim.x * blockDim.x) {
+        KingPair prev{};
+        bool have_prev = false;
+        for (size_t pos = game_start[g]; pos < game_start[g + 1]; ++pos) {
+            KingPair cur{};
+            const bool ok = find_kings(boards + pos, cur.king);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t slot = kNoRebuildSlot;
+                if (ok && (!have_prev || needs_refresh(t, prev, cur, c))) {
+                    const uint32_t at = atomicAdd(&plan.counters[0], 1u);
+                    if (at < plan.capacity) {
+                        plan.items[at] = static_cast<uint32_t>(pos) * 2 + c;
+                        slot = at;
+                    }
+                }
+                plan.slot[2 * pos + c] = slot;
+            }
+            prev = cur;
+            have_prev = ok; /* after a rejected record the walker restarts the chain by itself */
+        }
+    }
+}
+
+/* One warp per planned item: rebuild that perspective exactly as the full refresh would. */
+__global__ void __launch_bounds__(kThreads, 4)
+run_rebuilds_kernel(DeviceNet net, RebuildPlan plan, const SpPackedBoard* __restrict__ boards, DeviceStatus* status) {
+    __shared__ WarpScratch scratch[kWarpsPerCta];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratch& ws = scratch[warp];
+    const FeatureTables& t = *net.tables;
+    const uint32_t first = plan.counters[1], last = min(plan.counters[0], plan.capacity);
+    const uint32_t stride = gridDim.x * kWarpsPerCta;
+    for (uint32_t i = first + blockIdx.x * kWarpsPerCta + warp; i < last; i += stride) {
+        const uint32_t item = plan.items[i];
+        const int c = item & 1;
+        const Decoded d = decode_board(boards + (item >> 1), lane, ws.mailbox[0]);
+        uint32_t v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = 0;
+        if (d.ok && build_lists(t, nullptr, d, lane, ws, 0, 1 << c) >= 0)
+            rebuild_perspective(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, v);
+        /* a bad record is reported by the walker when it gets there */
+        uint4* out = plan.acc + static_cast<size_t>(i) * 128 + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[32 * k] = make_uint4(v[k * 4 + 0], v[k * 4 + 1], v[k * 4 + 2], v[k * 4 + 3]);
+    }
+}
+
+__global__ void rebuilds_done_kernel(RebuildPlan plan) { plan.counters[1] = min(plan.counters[0], plan.capacity); }
+
+/* One warp plays through one game: both accumulators stay in registers / shared memory from ply to
+ * ply (datagen form, src/datagen/datagen.cpp:257-262: applyMove + applyImmediately + evaluate). */
 __global__ void __launch_bounds__(kThreads, SP_GAMES_MIN_BLOCKS)
 ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const uint32_t* __restrict__ game_start,
-                uint32_t n_games, uint8_t* __restrict__ act, uint8_t* __restrict__ bucket, DeviceStatus* status) {
+                uint32_t n_games, uint8_t* __restrict__ act, uint8_t* __restrict__ bucket, RebuildPlan plan, DeviceStatus* status) {
     __shared__ WarpScratch scratch[kWarpsPerCta];
     __shared__ uint32_t parked[kWarpsPerCta][16][32]; /* one perspective's registers, parked between passes */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -902,24 +999,30 @@ ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const u
         int in_regs = 0; /* which perspective `v` currently holds */
         BoardView prev{};
         bool have_prev = false;
-        /* the next record is fetched one ply ahead so its latency hides behind this ply's work */
+        /* the next record (and its rebuild slots) are fetched one ply ahead so their latency hides behind
+         * this ply's work */
         uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        uint2 slots = make_uint2(kNoRebuildSlot, kNoRebuildSlot);
         if (first < last) {
             const uint4* p = reinterpret_cast<const uint4*>(boards + first);
             lo = __ldg(p), hi = __ldg(p + 1);
+            if (plan.slot) slots = *reinterpret_cast<const uint2*>(plan.slot + 2 * first);
         }
 #pragma unroll 1
         for (size_t pos = first; pos < last; ++pos) {
             const int buf = static_cast<int>(pos - first) & 1;
             const Decoded d = decode_board(lo, hi, lane, ws.mailbox[buf]);
+            const uint2 my_slots = slots;
             if (pos + 1 < last) {
                 const uint4* p = reinterpret_cast<const uint4*>(boards + pos + 1);
                 lo = __ldg(p), hi = __ldg(p + 1);
+                if (plan.slot) slots = *reinterpret_cast<const uint2*>(plan.slot + 2 * (pos + 1));
             }
+            const int external = (my_slots.x != kNoRebuildSlot ? 1 : 0) | (my_slots.y != kNoRebuildSlot ? 2 : 0);
             int err = d.ok ? 0 : kErrBadBoard;
             int rebuild = 3;
             if (!err) {
-                rebuild = build_lists(t, have_prev ? &prev : nullptr, d, lane, ws);
+                rebuild = build_lists(t, have_prev ? &prev : nullptr, d, lane, ws, external);
                 if (rebuild < 0) err = kErrCapacity;
             }
             if (err) {
@@ -936,7 +1039,14 @@ ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const u
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 const int c = in_regs;
-                if ((rebuild >> c) & 1) {
+                if ((external >> c) & 1) {
+                    const uint4* fresh = plan.acc + static_cast<size_t>(c ? my_slots.y : my_slots.x) * 128 + lane;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint4 q = fresh[32 * k];
+                        v[k * 4 + 0] = q.x, v[k * 4 + 1] = q.y, v[k * 4 + 2] = q.z, v[k * 4 + 3] = q.w;
+                    }
+                } else if ((rebuild >> c) & 1) {
                     uint32_t fresh[16];
                     rebuild_perspective_cold(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, fresh);
 #pragma unroll
@@ -1205,11 +1315,26 @@ void launch_ft_slots(
     ft_slots_kernel<<<grid_for(n, kWarpsPerCta, sm_count, 2), kThreads, 0, stream>>>(net, slots, src, dst, boards, n, act, bucket, status);
 }
 
+void launch_plan_rebuilds(
+    const DeviceNet& net, RebuildPlan plan, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, int sm_count,
+    cudaStream_t stream) {
+    if (!n_games) return;
+    const unsigned grid = static_cast<unsigned>(std::min<size_t>((n_games + 127) / 128, static_cast<size_t>(sm_count) * 8));
+    plan_rebuilds_kernel<<<grid, 128, 0, stream>>>(net, plan, boards, game_start, n_games);
+}
+
+void launch_run_rebuilds(
+    const DeviceNet& net, RebuildPlan plan, const SpPackedBoard* boards, DeviceStatus* status, int sm_count, cudaStream_t stream) {
+    run_rebuilds_kernel<<<sm_count * 4, kThreads, 0, stream>>>(net, plan, boards, status);
+    rebuilds_done_kernel<<<1, 1, 0, stream>>>(plan);
+}
+
 void launch_ft_games(
     const DeviceNet& net, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, uint8_t* act,
-    uint8_t* bucket, DeviceStatus* status, int sm_count, cudaStream_t stream) {
+    uint8_t* bucket, RebuildPlan plan, DeviceStatus* status, int sm_count, cudaStream_t stream) {
     if (!n_games) return;
-    ft_games_kernel<<<grid_for(n_games, kWarpsPerCta, sm_count, SP_GAMES_MIN_BLOCKS), kThreads, 0, stream>>>(net, boards, game_start, n_games, act, bucket, status);
+    ft_games_kernel<<<grid_for(n_games, kWarpsPerCta, sm_count, SP_GAMES_MIN_BLOCKS), kThreads, 0, stream>>>(
+        net, boards, game_start, n_games, act, bucket, plan, status);
 }
 
 void launch_slot_activate(
@@ -1223,11 +1348,8 @@ void launch_head(
     const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, const uint32_t* range,
     DeviceStatus*, int, cudaStream_t stream, uint32_t range_len) {
     if (!n) return;
-    static bool configured = false; /* opt in to > 48 KB of dynamic shared memory once per process */
-    if (!configured) {
-        cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadShared)));
-        configured = true;
-    }
+    /* opt in to > 48 KB of dynamic shared memory (a per-device attribute: set it on every launch) */
+    cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadShared)));
     const unsigned grid = static_cast<unsigned>((n + kHeadRows - 1) / kHeadRows);
     head_kernel<<<grid, kHeadWarps * 32, sizeof(HeadShared), stream>>>(net, act, bucket, n, out, range, range_len);
 }

@@ -82,10 +82,31 @@ void launch_ft_slots(
     const DeviceNet& net, SlotStore slots, const uint32_t* src, const uint32_t* dst, const SpPackedBoard* boards,
     size_t n, uint8_t* act, uint8_t* bucket, DeviceStatus* status, int sm_count, cudaStream_t stream);
 
-/* one warp walks one game; act/bucket rows are indexed like boards */
+/* Rebuilds taken out of the playout walker's loop.  A perspective must be rebuilt from scratch at the
+ * first board of a game and whenever its king changes input bucket or board half (about 6 % of
+ * perspective-plies in random playouts); done inside the walker those rare, long steps cost a quarter
+ * of its time.  Instead: launch_plan_rebuilds finds them (king squares only), launch_run_rebuilds
+ * computes their accumulators at full-refresh efficiency into `acc`, and the walker just loads them.
+ * When `acc` is full the remaining ones simply stay with the walker (slot = kNoRebuildSlot). */
+constexpr uint32_t kNoRebuildSlot = 0xFFFFFFFFu;
+struct RebuildPlan {
+    uint32_t* slot;     /* [2 * n_boards]: index into acc for (board, perspective), or kNoRebuildSlot */
+    uint32_t* items;    /* [capacity]: board * 2 + perspective, in reservation order */
+    uint4* acc;         /* [capacity][4][32]: rebuilt accumulators, lane order */
+    uint32_t* counters; /* [0] = items reserved so far (may run past capacity), [1] = items already computed */
+    uint32_t capacity;
+};
+void launch_plan_rebuilds(
+    const DeviceNet& net, RebuildPlan plan, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games,
+    int sm_count, cudaStream_t stream);
+void launch_run_rebuilds(
+    const DeviceNet& net, RebuildPlan plan, const SpPackedBoard* boards, DeviceStatus* status, int sm_count, cudaStream_t stream);
+
+/* one warp walks one game; act/bucket rows are indexed like boards.  plan.slot == nullptr: every
+ * rebuild happens inside the walker. */
 void launch_ft_games(
     const DeviceNet& net, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, uint8_t* act,
-    uint8_t* bucket, DeviceStatus* status, int sm_count, cudaStream_t stream);
+    uint8_t* bucket, RebuildPlan plan, DeviceStatus* status, int sm_count, cudaStream_t stream);
 
 /* slots[i] -> act[i], bucket[i]; stm may be nullptr (use the stored board's side to move) */
 void launch_slot_activate(

@@ -126,3 +126,17 @@ def test_full_size_playouts_equal_full_refresh(gpu_ctx):
     full = gpu_ctx.eval_full(boards)
     inc = gpu_ctx.eval_playouts(boards, starts)
     assert (full == inc).all()
+
+
+@pytest.mark.parametrize("env", [{"SP_NNUE_PLAN_REBUILDS": "0"}, {"SP_NNUE_PLAN_CAP": "7"}, {"SP_NNUE_GAMES_CHUNK": "5"}])
+def test_walker_rebuild_plan_variants(net, golden, monkeypatch, env):
+    """Rebuilds inside the walker, a rebuild plan that overflows after 7 items, and many small chunks
+    sharing one plan: all bit-exact."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    with api.Nnue(net.image, 0) as ctx:
+        for key in ("", "dfrc_"):
+            out = ctx.eval_playouts(golden[key + "boards"], golden[key + "starts"])
+            assert (out == golden[key + "evals"]).all(), (env, key)
+        # a second call reuses the plan scratch
+        assert (ctx.eval_playouts(golden["boards"], golden["starts"]) == golden["evals"]).all()
