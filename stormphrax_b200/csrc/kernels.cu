@@ -927,30 +927,43 @@ struct KingPair {
     int king[2];
 };
 
-/* One thread per game: which (board, perspective) pairs need a fresh accumulator. */
-__global__ void plan_rebuilds_kernel(DeviceNet net, RebuildPlan plan, const SpPackedBoard* __restrict__ boards,
-                                     const uint32_t* __restrict__ game_start, uint32_t n_games) {
+/* One warp per game, one lane per ply: which (board, perspective) pairs need a fresh accumulator. */
+__global__ void __launch_bounds__(256)
+plan_rebuilds_kernel(DeviceNet net, RebuildPlan plan, const SpPackedBoard* __restrict__ boards,
+                     const uint32_t* __restrict__ game_start, uint32_t n_games) {
     const FeatureTables& t = *net.tables;
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_games; g += gridDim.x * blockDim.x) {
-        KingPair prev{};
-        bool have_prev = false;
-        for (size_t pos = game_start[g]; pos < game_start[g + 1]; ++pos) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t g = warp; g < n_games; g += n_warps) {
+        const size_t first = game_start[g], last = game_start[g + 1];
+        KingPair carry{};      /* kings of the board before this round of 32 plies */
+        bool carry_ok = false; /* false at the start of the game: the first board is always rebuilt */
+        for (size_t base = first; base < last; base += 32) {
+            const size_t pos = base + lane;
             KingPair cur{};
-            const bool ok = find_kings(boards + pos, cur.king);
+            const bool ok = pos < last && find_kings(boards + pos, cur.king);
+            KingPair prev;
+            prev.king[0] = __shfl_up_sync(kFull, cur.king[0], 1);
+            prev.king[1] = __shfl_up_sync(kFull, cur.king[1], 1);
+            bool have_prev = __shfl_up_sync(kFull, ok ? 1 : 0, 1) != 0;
+            if (lane == 0) prev = carry, have_prev = carry_ok;
+            if (pos < last) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t slot = kNoRebuildSlot;
-                if (ok && (!have_prev || needs_refresh(t, prev, cur, c))) {
-                    const uint32_t at = atomicAdd(&plan.counters[0], 1u);
-                    if (at < plan.capacity) {
-                        plan.items[at] = static_cast<uint32_t>(pos) * 2 + c;
-                        slot = at;
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t slot = kNoRebuildSlot;
+                    if (ok && (!have_prev || needs_refresh(t, prev, cur, c))) {
+                        const uint32_t at = atomicAdd(&plan.counters[0], 1u);
+                        if (at < plan.capacity) {
+                            plan.items[at] = static_cast<uint32_t>(pos) * 2 + c;
+                            slot = at;
+                        }
                     }
+                    plan.slot[2 * pos + c] = slot;
                 }
-                plan.slot[2 * pos + c] = slot;
             }
-            prev = cur;
-            have_prev = ok; /* after a rejected record the walker restarts the chain by itself */
+            carry.king[0] = __shfl_sync(kFull, cur.king[0], 31);
+            carry.king[1] = __shfl_sync(kFull, cur.king[1], 31);
+            carry_ok = __shfl_sync(kFull, ok ? 1 : 0, 31) != 0; /* after a rejected record the walker restarts the chain by itself */
         }
     }
 }
@@ -1319,8 +1332,8 @@ void launch_plan_rebuilds(
     const DeviceNet& net, RebuildPlan plan, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, int sm_count,
     cudaStream_t stream) {
     if (!n_games) return;
-    const unsigned grid = static_cast<unsigned>(std::min<size_t>((n_games + 127) / 128, static_cast<size_t>(sm_count) * 8));
-    plan_rebuilds_kernel<<<grid, 128, 0, stream>>>(net, plan, boards, game_start, n_games);
+    const unsigned grid = static_cast<unsigned>(std::min<size_t>((n_games + 7) / 8, static_cast<size_t>(sm_count) * 8));
+    plan_rebuilds_kernel<<<grid, 256, 0, stream>>>(net, plan, boards, game_start, n_games);
 }
 
 void launch_run_rebuilds(
