@@ -40,8 +40,7 @@ struct SpNnue {
     uint8_t* d_bucket = nullptr; /* = d_bucket2[0] */
     cudaStream_t aux = nullptr;
     cudaStream_t h2d = nullptr, d2h = nullptr; /* host-pointer entry points: copies overlap the kernels chunk by chunk */
-    cudaEvent_t ev_ft[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr}, ev_rebuilt[2] = {nullptr, nullptr};
-    cudaEvent_t ev_join = nullptr, ev_start = nullptr;
+    cudaEvent_t ev_ft[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr}, ev_join = nullptr, ev_start = nullptr;
     std::vector<cudaEvent_t> ev_chunk; /* one "inputs of chunk i have landed" event per chunk */
     bool overlap = true;
     bool plan_rebuilds = true;   /* playout walker: rebuilds computed ahead by their own kernel (SP_NNUE_PLAN_REBUILDS=0: inline) */
@@ -386,7 +385,6 @@ int sp_nnue_create(const void* net_image, size_t len, int device, SpNnue** out) 
         if (ctx->split) SP_CUDA(nullptr, cudaMalloc(&ctx->d_lists[b], row_list_bytes(ctx->chunk)));
         SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_ft[b], cudaEventDisableTiming));
         SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_head[b], cudaEventDisableTiming));
-        SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_rebuilt[b], cudaEventDisableTiming));
     }
     SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
@@ -425,7 +423,6 @@ void sp_nnue_destroy(SpNnue* ctx) {
         cudaFree(ctx->d_lists[b]);
         if (ctx->ev_ft[b]) cudaEventDestroy(ctx->ev_ft[b]);
         if (ctx->ev_head[b]) cudaEventDestroy(ctx->ev_head[b]);
-        if (ctx->ev_rebuilt[b]) cudaEventDestroy(ctx->ev_rebuilt[b]);
     }
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
