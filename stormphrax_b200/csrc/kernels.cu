@@ -947,19 +947,24 @@ plan_rebuilds_kernel(DeviceNet net, RebuildPlan plan, const SpPackedBoard* __res
             prev.king[1] = __shfl_up_sync(kFull, cur.king[1], 1);
             bool have_prev = __shfl_up_sync(kFull, ok ? 1 : 0, 1) != 0;
             if (lane == 0) prev = carry, have_prev = carry_ok;
+            /* one reservation per round: a game's items sit next to each other in `items`, so the warps
+             * that rebuild them run side by side and share the rows the positions have in common */
+            const bool want0 = ok && (!have_prev || needs_refresh(t, prev, cur, kBlack));
+            const bool want1 = ok && (!have_prev || needs_refresh(t, prev, cur, kWhite));
+            const unsigned m0 = __ballot_sync(kFull, want0), m1 = __ballot_sync(kFull, want1);
+            uint32_t first_slot = 0;
+            if (lane == 0 && (m0 | m1)) first_slot = atomicAdd(&plan.counters[0], static_cast<uint32_t>(__popc(m0) + __popc(m1)));
+            first_slot = __shfl_sync(kFull, first_slot, 0);
             if (pos < last) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t slot = kNoRebuildSlot;
-                    if (ok && (!have_prev || needs_refresh(t, prev, cur, c))) {
-                        const uint32_t at = atomicAdd(&plan.counters[0], 1u);
-                        if (at < plan.capacity) {
-                            plan.items[at] = static_cast<uint32_t>(pos) * 2 + c;
-                            slot = at;
-                        }
-                    }
-                    plan.slot[2 * pos + c] = slot;
+                const unsigned lt = (1u << lane) - 1;
+                uint32_t at = first_slot + __popc(m0 & lt) + __popc(m1 & lt);
+                uint2 slots = make_uint2(kNoRebuildSlot, kNoRebuildSlot);
+                if (want0) {
+                    if (at < plan.capacity) plan.items[at] = static_cast<uint32_t>(pos) * 2, slots.x = at;
+                    ++at;
                 }
+                if (want1 && at < plan.capacity) plan.items[at] = static_cast<uint32_t>(pos) * 2 + 1, slots.y = at;
+                *reinterpret_cast<uint2*>(plan.slot + 2 * pos) = slots;
             }
             carry.king[0] = __shfl_sync(kFull, cur.king[0], 31);
             carry.king[1] = __shfl_sync(kFull, cur.king[1], 31);
