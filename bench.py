@@ -302,11 +302,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             bytes_per_pos = (counts["psq_rows"] * 2048 + (counts["threat_rows"] + counts["pawn_pair_rows"]) * 1024) / n + 2048 + 32 + 4
         else:
             # SURVEY 8(d) incremental formula per perspective: delta rows + read and write of the PSQ and
-            # threat accumulators (2 x 2048 B each way); rebuilt perspectives read their full row lists
+            # threat accumulators (2 x 2048 B each way).  Rebuilt perspectives (first board of a game, king
+            # changed bucket or side) are computed by the separate `rebuilds` kernels, which read their full
+            # row lists and write the accumulator the walker then loads.
             st = api.playout_stats(boards, starts)
-            bytes_per_pos = (st["psq_delta_rows"] * 2048 + st["threat_delta_rows"] * 1024 + st["rebuild_psq_rows"] * 2048
-                             + st["rebuild_threat_rows"] * 1024 + st["updated_perspectives"] * 2 * 4096
-                             + st["rebuilt_perspectives"] * 4096) / n + 32 + 4
+            bytes_per_pos = (st["psq_delta_rows"] * 2048 + st["threat_delta_rows"] * 1024 + st["updated_perspectives"] * 2 * 4096
+                             + st["rebuilt_perspectives"] * 2 * 4096) / n + 32 + 4
+            rebuild_bytes_per_pos = (st["rebuild_psq_rows"] * 2048 + st["rebuild_threat_rows"] * 1024 + st["rebuilt_perspectives"] * (4096 + 32)) / n
         algo_bytes_per_launch = bytes_per_pos * n * args.steps / max(k_launches, 1)
         avg_launch_ms = k_ms / max(k_launches, 1)
         achieved = algo_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms else 0.0
@@ -328,6 +330,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             except Exception:
                 pass
         roofline["algorithmic_bytes_per_launch"] = algo_bytes_per_launch
+        if args.workload == "playouts":
+            rb_ms, rb_launches = prof.get("rebuilds", (0.0, 0))
+            roofline["rebuilds_kernel"] = {
+                "algorithmic_bytes_per_position": rebuild_bytes_per_pos,
+                "achieved": rebuild_bytes_per_pos * n * args.steps / (rb_ms * 1e-3) / 1e9 if rb_ms else None, "unit": "GB/s",
+                "ms_per_step": rb_ms / args.steps,
+            }
         # the resource that actually binds these cache-resident kernels: the SM's 128 B/clk L1/LSU data path
         sm_mhz = clock_summary.get("sm_mhz") or 1965.0
         onchip_peak = props.multi_processor_count * 128 * sm_mhz * 1e6 / 1e9
