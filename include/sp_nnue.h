@@ -138,6 +138,28 @@ int sp_nnue_forward_device(
 int sp_nnue_activations_device(
     SpNnue* ctx, const SpPackedBoard* d_boards, size_t n, uint8_t* d_act, uint8_t* d_bucket, void* stream);
 
+/* ---------------------------------------------------------------- eval post-processing
+ * Replaces eval::staticEval's adjustStatic (src/eval/eval.cpp:25-28: contempt, clamp to +-24999) followed
+ * by eval::adjustEval (src/eval/eval.cpp:31-67: material scaling, optimism, 50-move damping, optional
+ * correction, clamp) for a batch.  `raw` are the network outputs the eval entry points return.
+ * The reference reads its correction from per-thread history tables (src/correction.h); that state stays
+ * with the caller, which passes the looked-up correction per position (NULL = adjustEval<false>). */
+typedef struct SpAdjustParams {
+    int32_t scaling_value[5];        /* pawn, knight, bishop, rook, queen: src/tunable.h:161-165 */
+    int32_t material_scaling_base;   /* src/tunable.h:167 */
+    int32_t optimism_base;           /* src/tunable.h:168 */
+    int32_t optimism_material_scale; /* src/tunable.h:169 */
+    int32_t contempt[2];             /* eval::Contempt, [black, white] (src/eval/eval.h:31) */
+    int32_t optimism[2];             /* eval::Optimism, [black, white] (src/eval/eval.h:32) */
+} SpAdjustParams;
+void sp_nnue_adjust_defaults(SpAdjustParams* params); /* the reference's default tunables, zero contempt / optimism */
+int sp_nnue_adjust(
+    SpNnue* ctx, const SpPackedBoard* boards, const int32_t* raw, const int32_t* correction, size_t n,
+    const SpAdjustParams* params, int32_t* out);
+int sp_nnue_adjust_device(
+    SpNnue* ctx, const SpPackedBoard* d_boards, const int32_t* d_raw, const int32_t* d_correction, size_t n,
+    const SpAdjustParams* params, int32_t* d_out, void* stream);
+
 /* ---------------------------------------------------------------- introspection
  * Counters since create (uint64 each): what the engine keeps per thread in SearchData
  * (src/thread.h:35-79) and sums at report time.  Multi-GPU runs all-reduce these over NCCL. */

@@ -86,6 +86,7 @@ class Reference:
         L.spref_legal_moves.argtypes = [_vp, _vp]
         L.spref_apply_move.argtypes = [_vp, C.c_uint16, _vp]
         L.spref_board_from_fen.argtypes = [C.c_char_p, _vp]
+        L.spref_adjusted_eval.argtypes = [_vp, C.c_size_t, _vp, _vp, _vp, _vp]
         self._net = None
 
     @staticmethod
@@ -109,6 +110,18 @@ class Reference:
         if rc:
             raise RuntimeError(f"spref_eval_once failed ({rc})")
         return out
+
+    def adjusted_eval(self, boards: np.ndarray, contempt=(0, 0), optimism=(0, 0)):
+        """(raw evaluateOnce, staticEvalOnce + adjustEval<false>) from the reference's own functions."""
+        boards = np.ascontiguousarray(boards, dtype=BOARD_DTYPE)
+        raw = np.empty(boards.size, dtype=np.int32)
+        out = np.empty(boards.size, dtype=np.int32)
+        c = np.asarray(contempt, dtype=np.int32)
+        o = np.asarray(optimism, dtype=np.int32)
+        rc = self.lib.spref_adjusted_eval(_ptr(boards), boards.size, _ptr(c), _ptr(o), _ptr(raw), _ptr(out))
+        if rc:
+            raise RuntimeError(f"spref_adjusted_eval failed ({rc})")
+        return raw, out
 
     def time_eval_once(self, boards: np.ndarray, threads: int, reps: int = 1):
         boards = np.ascontiguousarray(boards, dtype=BOARD_DTYPE)

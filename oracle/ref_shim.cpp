@@ -216,6 +216,30 @@ int spref_eval_once(const SpPackedBoard* boards, size_t n, int32_t* out) {
     return 0;
 }
 
+// The engine's post-processed static eval of n boards, produced by the reference's own functions:
+// eval::staticEvalOnce (contempt + clamp, src/eval/eval.cpp:25-28,109-112) followed by
+// eval::adjustEval<false> (src/eval/eval.cpp:31-67).  raw_out (optional) receives evaluateOnce.
+int spref_adjusted_eval(
+    const SpPackedBoard* boards, size_t n, const int32_t contempt[2], const int32_t optimism[2], int32_t* raw_out, int32_t* out
+) {
+    if (!s_loaded) {
+        return 1;
+    }
+    const eval::Contempt c{contempt[0], contempt[1]};
+    const eval::Optimism o{optimism[0], optimism[1]};
+    for (size_t i = 0; i < n; ++i) {
+        Position pos;
+        if (!toPosition(boards[i], pos)) {
+            return 2;
+        }
+        if (raw_out) {
+            raw_out[i] = eval::NnueState::evaluateOnce(pos, pos.stm());
+        }
+        out[i] = eval::adjustEval<false>(pos, o, {}, nullptr, eval::staticEvalOnce(pos, c));
+    }
+    return 0;
+}
+
 // Timed evaluateOnce: positions are parsed first (untimed), then `threads` std::threads
 // each evaluate a contiguous shard `reps` times. Returns the best wall-clock seconds of one
 // full pass over all n positions (max over threads per rep), or a negative value on error.

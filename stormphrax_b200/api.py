@@ -61,6 +61,9 @@ SIGNATURES = {
     "sp_nnue_eval_playouts_device": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _sz, _vp, _vp]),
     "sp_nnue_forward_device": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "sp_nnue_activations_device": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "sp_nnue_adjust_defaults": (None, [_vp]),
+    "sp_nnue_adjust": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "sp_nnue_adjust_device": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "sp_nnue_counters": (C.c_int, [_vp, _vp]),
     "sp_nnue_read_slot": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
     "sp_host_playouts": (_sz, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp]),
@@ -71,6 +74,29 @@ SIGNATURES = {
     "sp_host_features": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "sp_host_feature_delta": (C.c_int, [_vp, _vp, C.c_int] + [_vp] * 8),
 }
+
+
+
+class AdjustParams(C.Structure):
+    """SpAdjustParams (include/sp_nnue.h): tunables of eval::adjustEval plus contempt / optimism."""
+
+    _fields_ = [
+        ("scaling_value", C.c_int32 * 5),
+        ("material_scaling_base", C.c_int32),
+        ("optimism_base", C.c_int32),
+        ("optimism_material_scale", C.c_int32),
+        ("contempt", C.c_int32 * 2),
+        ("optimism", C.c_int32 * 2),
+    ]
+
+    @classmethod
+    def defaults(cls, contempt=(0, 0), optimism=(0, 0)) -> "AdjustParams":
+        p = cls()
+        lib().sp_nnue_adjust_defaults(C.byref(p))
+        p.contempt[:] = contempt
+        p.optimism[:] = optimism
+        return p
+
 
 _lib = None
 
@@ -190,6 +216,16 @@ class Nnue:
 
     def forward_device(self, d_act, d_bucket, n: int, d_out, stream: int | None = None) -> None:
         self._check(self._lib.sp_nnue_forward_device(self._h, _ptr(d_act), _ptr(d_bucket), n, _ptr(d_out), stream))
+
+    # ---- eval post-processing (adjustStatic + adjustEval)
+    def adjust(self, boards, raw, params: "AdjustParams | None" = None, correction=None) -> np.ndarray:
+        boards = _boards(boards)
+        raw = np.ascontiguousarray(raw, dtype=np.int32)
+        corr = None if correction is None else np.ascontiguousarray(correction, dtype=np.int32)
+        params = params or AdjustParams.defaults()
+        out = np.empty(boards.size, dtype=np.int32)
+        self._check(self._lib.sp_nnue_adjust(self._h, boards.ctypes.data, raw.ctypes.data, _ptr(corr), boards.size, C.addressof(params), out.ctypes.data))
+        return out
 
     # ---- accumulator slots (the NnueState stack, device resident)
     def slots_reserve(self, n_slots: int) -> None:

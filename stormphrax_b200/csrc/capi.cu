@@ -330,9 +330,9 @@ int eval_full_device(
 
 extern "C" {
 
-int sp_nnue_create(const void* net_image, size_t len, int device, SpNnue** out) {
-    if (!out) return fail(nullptr, SP_ERR_INVALID, "out is null");
-    *out = nullptr;
+void sp_nnue_destroy(SpNnue* ctx);
+
+static int create_impl(const void* net_image, size_t len, int device, SpNnue** out) {
     if (!net_image || len < SP_NET_HEADER_BYTES) return fail(nullptr, SP_ERR_BAD_NETWORK, "missing network header");
     const uint8_t* bytes = static_cast<const uint8_t*>(net_image);
     if (const char* why = validate_header(bytes)) return fail(nullptr, SP_ERR_BAD_NETWORK, "%s", why);
@@ -346,8 +346,10 @@ int sp_nnue_create(const void* net_image, size_t len, int device, SpNnue** out) 
     }
     if (device < 0 || device >= count) return fail(nullptr, SP_ERR_NO_DEVICE, "device %d out of range (%d present)", device, count);
 
-    std::unique_ptr<SpNnue> ctx{new (std::nothrow) SpNnue};
+    /* the caller destroys *out if anything below fails, releasing whatever was allocated so far */
+    SpNnue* ctx = new (std::nothrow) SpNnue;
     if (!ctx) return fail(nullptr, SP_ERR_INVALID, "out of host memory");
+    *out = ctx;
     ctx->device = device;
     DeviceGuard guard{device};
     cudaDeviceProp prop{};
@@ -404,8 +406,18 @@ int sp_nnue_create(const void* net_image, size_t len, int device, SpNnue** out) 
     ctx->net.l3_w = reinterpret_cast<const int32_t*>(b + L.l3_w);
     ctx->net.l3_b = reinterpret_cast<const int32_t*>(b + L.l3_b);
     ctx->net.tables = ctx->d_tables;
-    *out = ctx.release();
     return SP_OK;
+}
+
+int sp_nnue_create(const void* net_image, size_t len, int device, SpNnue** out) {
+    if (!out) return fail(nullptr, SP_ERR_INVALID, "out is null");
+    *out = nullptr;
+    const int rc = create_impl(net_image, len, device, out);
+    if (rc != SP_OK && *out) {
+        sp_nnue_destroy(*out);
+        *out = nullptr;
+    }
+    return rc;
 }
 
 void sp_nnue_destroy(SpNnue* ctx) {
@@ -545,6 +557,44 @@ int sp_nnue_forward_device(SpNnue* ctx, const uint8_t* d_act, const uint8_t* d_b
     ctx->counters[SP_CTR_EVALS] += n;
     SP_CUDA(ctx, cudaGetLastError());
     return SP_OK;
+}
+
+void sp_nnue_adjust_defaults(SpAdjustParams* p) {
+    if (!p) return;
+    *p = SpAdjustParams{{48, 442, 461, 637, 1223}, 26000, 2024, 1005, {0, 0}, {0, 0}}; /* src/tunable.h:161-169 */
+}
+
+int sp_nnue_adjust_device(
+    SpNnue* ctx, const SpPackedBoard* d_boards, const int32_t* d_raw, const int32_t* d_correction, size_t n,
+    const SpAdjustParams* params, int32_t* d_out, void* stream) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!n) return SP_OK;
+    if (!d_boards || !d_raw || !d_out || !params) return fail(ctx, SP_ERR_INVALID, "null argument");
+    DeviceGuard guard{ctx->device};
+    launch_adjust(d_boards, d_raw, d_correction, n, *params, d_out, pick(ctx, stream));
+    ctx->counters[SP_CTR_LAUNCHES] += 1;
+    SP_CUDA(ctx, cudaGetLastError());
+    return SP_OK;
+}
+
+int sp_nnue_adjust(
+    SpNnue* ctx, const SpPackedBoard* boards, const int32_t* raw, const int32_t* correction, size_t n,
+    const SpAdjustParams* params, int32_t* out) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!n) return SP_OK;
+    if (!boards || !raw || !out || !params) return fail(ctx, SP_ERR_INVALID, "null argument");
+    DeviceGuard guard{ctx->device};
+    if (const int rc = ensure_staging(ctx, n)) return rc;
+    int32_t* d_raw = reinterpret_cast<int32_t*>(ctx->d_ids);              /* 3 * (cap + 1) words of scratch */
+    int32_t* d_corr = reinterpret_cast<int32_t*>(ctx->d_ids) + ctx->cap + 1;
+    SP_CUDA(ctx, cudaMemcpyAsync(ctx->d_boards, boards, n * sizeof(SpPackedBoard), cudaMemcpyHostToDevice, ctx->stream));
+    SP_CUDA(ctx, cudaMemcpyAsync(d_raw, raw, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (correction) SP_CUDA(ctx, cudaMemcpyAsync(d_corr, correction, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    launch_adjust(ctx->d_boards, d_raw, correction ? d_corr : nullptr, n, *params, ctx->d_out, ctx->stream);
+    ctx->counters[SP_CTR_LAUNCHES] += 1;
+    SP_CUDA(ctx, cudaGetLastError());
+    SP_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx, ctx->stream);
 }
 
 int sp_nnue_counters(SpNnue* ctx, uint64_t out[SP_NUM_COUNTERS]) {

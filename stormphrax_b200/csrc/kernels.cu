@@ -1289,6 +1289,41 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
     }
 }
 
+/* ------------------------------------------------------------------ eval post-processing */
+
+/* adjustStatic + adjustEval, src/eval/eval.cpp:25-67.  All arithmetic is the reference's: int32, C++
+ * division (truncating), std::clamp to +-(kScoreWin - 1). */
+__global__ void adjust_kernel(const SpPackedBoard* __restrict__ boards, const int32_t* __restrict__ raw,
+                              const int32_t* __restrict__ correction, size_t n, SpAdjustParams p, int32_t* __restrict__ out) {
+    constexpr int kLimit = 25000 - 1; /* kScoreWin - 1, src/core.h:708 */
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const uint4* rec = reinterpret_cast<const uint4*>(boards + i);
+        const uint4 lo = __ldg(rec), hi = __ldg(rec + 1);
+        const int n_pieces = __popcll(static_cast<uint64_t>(lo.y) << 32 | lo.x);
+        const int stm = (hi.z & 0x80) ? kBlack : kWhite;
+        const int halfmove = (hi.z >> 8) & 0xFF;
+        const uint32_t words[4] = {lo.z, lo.w, hi.x, hi.y};
+        int material = 0;
+        for (int k = 0; k < n_pieces && k < 32; ++k) {
+            uint32_t type = (words[k >> 3] >> ((k & 7) * 4)) & 7;
+            if (type == 6) type = kRook; /* rook with castling rights */
+            if (type < kKing) material += p.scaling_value[type];
+        }
+        int eval = raw[i];
+        if (eval == INT32_MIN) { /* rejected record: keep the marker */
+            out[i] = eval;
+            continue;
+        }
+        eval = min(max(eval + p.contempt[stm], -kLimit), kLimit);                                 /* adjustStatic */
+        eval = (eval * (p.material_scaling_base + material)
+                + p.optimism[stm] * (p.optimism_base + material * p.optimism_material_scale / 1024))
+             / 32768;
+        eval = eval * (200 - halfmove) / 200;
+        if (correction) eval += correction[i] / 2048;
+        out[i] = min(max(eval, -kLimit), kLimit);
+    }
+}
+
 int grid_for(size_t n_warp_items, int warps_per_cta, int sm_count, int ctas_per_sm) {
     const size_t want = (n_warp_items + warps_per_cta - 1) / warps_per_cta;
     const size_t cap = static_cast<size_t>(sm_count) * ctas_per_sm;
@@ -1370,6 +1405,14 @@ void launch_head(
     cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadShared)));
     const unsigned grid = static_cast<unsigned>((n + kHeadRows - 1) / kHeadRows);
     head_kernel<<<grid, kHeadWarps * 32, sizeof(HeadShared), stream>>>(net, act, bucket, n, out, range, range_len);
+}
+
+void launch_adjust(
+    const SpPackedBoard* boards, const int32_t* raw, const int32_t* correction, size_t n, const SpAdjustParams& params,
+    int32_t* out, cudaStream_t stream) {
+    if (!n) return;
+    const unsigned grid = static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 148 * 16));
+    adjust_kernel<<<grid, 256, 0, stream>>>(boards, raw, correction, n, params, out);
 }
 
 } // namespace sp::gpu

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/sp_nnue.h"
 #include "sp_features.h"
 
 namespace sp::gpu {
@@ -120,6 +121,12 @@ void launch_slot_activate(
 void launch_head(
     const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, const uint32_t* range,
     DeviceStatus* status, int sm_count, cudaStream_t stream, uint32_t range_len = 0);
+
+/* raw network outputs -> adjusted static evals (eval.cpp:25-67); one thread per position.
+ * `correction` may be null. */
+void launch_adjust(
+    const SpPackedBoard* boards, const int32_t* raw, const int32_t* correction, size_t n, const SpAdjustParams& params,
+    int32_t* out, cudaStream_t stream);
 
 } // namespace sp::gpu
 

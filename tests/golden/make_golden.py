@@ -92,6 +92,18 @@ def main() -> None:
         net_seed=np.int64(1234),
     )
 
+    # eval post-processing: staticEvalOnce + adjustEval<false> from the reference, three parameter sets
+    # (boards carry their real halfmove clocks; a few get large ones to exercise the 50-move damping)
+    aboards = np.concatenate([boards[::3], fen_boards]).copy()
+    aboards["halfmove"][::5] = (np.arange(len(aboards[::5])) * 7 % 101).astype(np.uint8)
+    adjust = {"adjust_boards": aboards}
+    for k, (contempt, optimism) in enumerate([((0, 0), (0, 0)), ((25, -25), (0, 0)), ((-40, 40), (120, -95))]):
+        raw, adj = ref.adjusted_eval(aboards, contempt, optimism)
+        adjust["adjust_raw"] = raw
+        adjust[f"adjust_params{k}"] = np.array([*contempt, *optimism], dtype=np.int32)
+        adjust[f"adjust_out{k}"] = adj
+    np.savez_compressed(os.path.join(HERE, "adjust_seed42.npz"), **adjust)
+
     # the stress network (wrapping everywhere) on the same boards
     stress = N.synthetic(99, stress=True)
     ref.load_net(stress.image)

@@ -181,3 +181,25 @@ def test_small_chunks_exercise_the_overlap_pipeline(net, golden, monkeypatch):
         for _ in range(3):
             assert (ctx.eval_full(golden["boards"]) == golden["evals"]).all()
             assert (ctx.eval_playouts(golden["boards"], golden["starts"]) == golden["evals"]).all()
+
+
+def test_adjust_eval_matches_reference_golden(gpu_ctx):
+    """adjustStatic + adjustEval<false> (eval.cpp:25-67) as a device epilogue, against
+    values produced by the reference's own staticEvalOnce / adjustEval."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "adjust_seed42.npz"))
+    boards, raw = g["adjust_boards"], g["adjust_raw"]
+    assert (gpu_ctx.eval_full(boards) == raw).all()
+    for k in range(3):
+        c0, c1, o0, o1 = (int(x) for x in g[f"adjust_params{k}"])
+        params = api.AdjustParams.defaults(contempt=(c0, c1), optimism=(o0, o1))
+        assert (gpu_ctx.adjust(boards, raw, params) == g[f"adjust_out{k}"]).all(), k
+    # caller-supplied correction (the reference reads it from its history tables): + trunc(c / 2048), then clamp
+    rng = np.random.default_rng(1)
+    corr = rng.integers(-300000, 300000, len(boards)).astype(np.int32)
+    base = g["adjust_out0"].astype(np.int64)
+    want = np.clip(base + np.trunc(corr / 2048).astype(np.int64), -24999, 24999)
+    inside = np.abs(base) < 24999  # where the golden value was not clamped, the pre-clamp value is known
+    got = gpu_ctx.adjust(boards, raw, api.AdjustParams.defaults(), correction=corr)
+    assert (got[inside] == want[inside]).all()

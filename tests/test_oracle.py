@@ -88,3 +88,31 @@ def test_synthetic_net_format(net):
     bad[0] = ord("X")
     with pytest.raises(N.NetworkFormatError):
         N.validate_header(bad.tobytes())
+
+
+def _adjust_restatement(boards, raw, contempt, optimism):
+    """numpy restatement of adjustStatic + adjustEval<false> (src/eval/eval.cpp:25-67) with the default
+    tunables (src/tunable.h:161-169); C++ int division truncates toward zero."""
+    tdiv = lambda a, b: np.trunc(a / b).astype(np.int64)
+    value = np.array([48, 442, 461, 637, 1223, 0, 637, 0], dtype=np.int64)  # P N B R Q K castling-rook -
+    out = np.empty(len(boards), dtype=np.int64)
+    for i, b in enumerate(boards):
+        n = bin(int(b["occupancy"])).count("1")
+        nibbles = np.stack([b["pieces"] & 0xF, b["pieces"] >> 4], axis=1).reshape(-1)[:n] & 7
+        material = int(value[nibbles].sum())
+        stm = 0 if b["stm_ep"] & 0x80 else 1
+        e = int(np.clip(int(raw[i]) + contempt[stm], -24999, 24999))
+        e = int(tdiv(e * (26000 + material) + optimism[stm] * (2024 + int(tdiv(material * 1005, 1024))), 32768))
+        e = int(tdiv(e * (200 - int(b["halfmove"])), 200))
+        out[i] = np.clip(e, -24999, 24999)
+    return out
+
+
+def test_adjust_restatement_matches_reference_golden():
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "adjust_seed42.npz"))
+    for k in range(3):
+        c0, c1, o0, o1 = (int(x) for x in g[f"adjust_params{k}"])
+        got = _adjust_restatement(g["adjust_boards"], g["adjust_raw"], (c0, c1), (o0, o1))
+        assert (got == g[f"adjust_out{k}"]).all(), k
