@@ -56,8 +56,8 @@ constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kEnqUnroll = SP_ENQ_UNROLL;
 constexpr int kPsqGroup = SP_PSQ_GROUP;      /* PSQ rows fetched per batch on the rebuild path (4 x LDG.128 each per lane) */
 constexpr int kThrGroupFull = SP_THR_GROUP;  /* threat rows per batch on the rebuild path (2 x LDG.128 each per lane) */
-constexpr int kPsqGroupDelta = 4;  /* delta rows per batch on the incremental path (16 x LDG.128) */
-constexpr int kThrGroupDelta = 4;  /* per sign: 4 added + 4 subtracted rows (16 x LDG.128) */
+constexpr int kPsqGroupDelta = 2;  /* delta rows per batch on the incremental path (8 x LDG.128); lists are short, padding costs */
+constexpr int kThrGroupDelta = 2;  /* per sign: 2 added + 2 subtracted rows (8 x LDG.128) */
 constexpr int kPsqListCap = 40;    /* 32 pieces + bias row */
 constexpr int kPsqDeltaCap = 16;
 constexpr int kThrDeltaCap = 96;   /* added rows grow from the front, subtracted rows from the back */
@@ -543,15 +543,15 @@ __device__ __noinline__ void rebuild_perspective_cold(
  * recovered as s - (o << 8) -- then the subtracted sums are added complemented.  All the "-1" of the
  * complements are repaid by one constant at the end. */
 __device__ __forceinline__ void update_perspective(const DeviceNet& net, const WarpScratch& ws, int c, int lane, uint32_t (&v)[16]) {
-    static_assert(kPsqGroupDelta == 4 && kThrGroupDelta == 4, "list entries are fetched four at a time");
+    static_assert(kPsqGroupDelta == 2 && kThrGroupDelta == 2, "list entries are fetched two at a time");
     const uint4* psq_base = net.psq + lane;
     const uint4* thr_base = net.thr + lane;
     const int n_psq = ws.n_psq_delta[c]; /* padded */
     int psq_subs = 0;
 #pragma unroll 1
     for (int i = 0; i < n_psq; i += kPsqGroupDelta) {
-        const uint4 e4 = *reinterpret_cast<const uint4*>(ws.psq_delta[c] + i);
-        const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
+        const uint2 e2 = *reinterpret_cast<const uint2*>(ws.psq_delta[c] + i);
+        const uint32_t e[2] = {e2.x, e2.y};
         uint4 rows[kPsqGroupDelta][4];
         uint32_t mask[kPsqGroupDelta];
 #pragma unroll
@@ -576,13 +576,11 @@ __device__ __forceinline__ void update_perspective(const DeviceNet& net, const W
     for (int i = 0; i < 8; ++i) sa[i] = oa[i] = ss[i] = os[i] = 0;
 #pragma unroll 1
     for (int i = 0; i < n_thr; i += kThrGroupDelta) {
-        const uint4 ea = *reinterpret_cast<const uint4*>(ws.thr_delta[c] + i);
-        const uint4 es = *reinterpret_cast<const uint4*>(ws.thr_delta[c] + kThrDeltaCap - kThrGroupDelta - i); /* stored backwards */
+        const uint2 ea = *reinterpret_cast<const uint2*>(ws.thr_delta[c] + i);
+        const uint2 es = *reinterpret_cast<const uint2*>(ws.thr_delta[c] + kThrDeltaCap - kThrGroupDelta - i); /* stored backwards */
         uint4 ra[kThrGroupDelta][2], rs[kThrGroupDelta][2];
         load_thr_row(thr_base, ea.x, ra[0]), load_thr_row(thr_base, ea.y, ra[1]);
-        load_thr_row(thr_base, ea.z, ra[2]), load_thr_row(thr_base, ea.w, ra[3]);
         load_thr_row(thr_base, es.x, rs[0]), load_thr_row(thr_base, es.y, rs[1]);
-        load_thr_row(thr_base, es.z, rs[2]), load_thr_row(thr_base, es.w, rs[3]);
 #pragma unroll
         for (int j = 0; j < kThrGroupDelta; ++j) {
             add_thr_wide(sa, oa, ra[j]);

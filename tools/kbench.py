@@ -14,6 +14,8 @@ def main():
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
     boards, moves, starts = make_workload(0, n, "playouts" if (which == "playouts" and len(sys.argv) <= 2) else "full")
     n = len(boards)
+    if os.environ.get("KBENCH_SHUFFLE"):  # full refresh only: destroy the game order (no row sharing between neighbours)
+        boards = boards[np.random.default_rng(0).permutation(n)]
     ctx = api.Nnue(N.synthetic(1234).image, 0)
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); s = stream.cuda_stream
     d_boards = torch.from_numpy(boards.view(np.uint8).reshape(-1)).cuda()
