@@ -56,11 +56,8 @@ constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kEnqUnroll = SP_ENQ_UNROLL;
 constexpr int kPsqGroup = SP_PSQ_GROUP;      /* PSQ rows fetched per batch on the rebuild path (4 x LDG.128 each per lane) */
 constexpr int kThrGroupFull = SP_THR_GROUP;  /* threat rows per batch on the rebuild path (2 x LDG.128 each per lane) */
-#ifndef SP_DELTA_GROUP
-#define SP_DELTA_GROUP 2
-#endif
-constexpr int kPsqGroupDelta = SP_DELTA_GROUP;  /* delta rows per batch on the incremental path (8 x LDG.128); lists are short, padding costs */
-constexpr int kThrGroupDelta = SP_DELTA_GROUP;  /* per sign: 2 added + 2 subtracted rows (8 x LDG.128) */
+constexpr int kPsqGroupDelta = 2;  /* delta rows per batch on the incremental path (8 x LDG.128); lists are short, padding costs */
+constexpr int kThrGroupDelta = 2;  /* per sign: 2 added + 2 subtracted rows (8 x LDG.128) */
 constexpr int kPsqListCap = 40;    /* 32 pieces + bias row */
 constexpr int kPsqDeltaCap = 16;
 constexpr int kThrDeltaCap = 96;   /* added rows grow from the front, subtracted rows from the back */
@@ -354,12 +351,10 @@ __device__ __forceinline__ void process_tasks(
  * A perspective is rebuilt when its king changes input bucket or board half (psq.h:264-283,
  * nnue_state.h:118-128), when more than kMaxChanged squares differ, or when a delta list overflows.
  * Returns -1 if a full list exceeds the reference's bound of 256 entries.
- * `ext_psq` / `ext_thr`: perspectives whose fresh PSQ / threat part comes from elsewhere (RebuildPlan):
- * nothing is listed for those parts.  `only`: with no predecessor, the perspectives to rebuild. */
+ * `external`: perspectives whose fresh accumulator comes from elsewhere (RebuildPlan): nothing is
+ * listed for them.  `only`: with no predecessor, the perspectives to rebuild (default both). */
 __device__ __forceinline__ int build_lists(
-    const FeatureTables& t, const BoardView* before, const Decoded& d, int lane, WarpScratch& ws, int ext_psq = 0, int ext_thr = 0,
-    int only = 3) {
-    const int external = ext_psq | ext_thr; /* never rebuilt here: the missing part is simply updated */
+    const FeatureTables& t, const BoardView* before, const Decoded& d, int lane, WarpScratch& ws, int external = 0, int only = 3) {
     int rebuild = only & ~external;
     uint64_t changed = 0;
     if (before) {
@@ -373,9 +368,8 @@ __device__ __forceinline__ int build_lists(
     for (;;) {
         int n_tasks = 0;
         int n_full[2] = {0, 0}, n_dadd[2] = {0, 0}, n_dsub[2] = {0, 0}, n_psq_delta[2] = {0, 0};
-        const int skip_psq = rebuild | ext_psq, skip_thr = rebuild | ext_thr; /* parts that take no delta rows */
-        if (before && (skip_psq & skip_thr) != 3)
-            n_tasks = enqueue_delta(t, *before, d.view, changed, skip_psq, lane, ws, n_tasks, n_psq_delta);
+        const int skip = rebuild | external; /* perspectives that take no delta rows */
+        if (before && skip != 3) n_tasks = enqueue_delta(t, *before, d.view, changed, skip, lane, ws, n_tasks, n_psq_delta);
         if (n_tasks > kTaskCap - 32) { /* far too many candidates for an update: rebuild instead */
             rebuild = 3 & ~external;
             __syncwarp();
@@ -383,7 +377,7 @@ __device__ __forceinline__ int build_lists(
         }
         auto flush = [&](int queued) {
             __syncwarp();
-            process_tasks(t, d.view, rebuild, ext_thr, queued, lane, ws, n_full, n_dadd, n_dsub);
+            process_tasks(t, d.view, rebuild, external, queued, lane, ws, n_full, n_dadd, n_dsub);
             __syncwarp();
             return 0;
         };
@@ -406,6 +400,7 @@ __device__ __forceinline__ int build_lists(
         /* top the lists up with the zero row to whole load batches and publish the padded lengths */
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+            if ((external >> c) & 1) continue;
             if ((rebuild >> c) & 1) {
                 const int n_psq = d.n_pieces + 1, n_psq_pad = (n_psq + kPsqGroup - 1) / kPsqGroup * kPsqGroup;
                 const int n_thr_pad = (n_full[c] + kThrGroupFull - 1) / kThrGroupFull * kThrGroupFull;
@@ -479,12 +474,13 @@ __device__ __forceinline__ void add_thr_wide(uint32_t (&s)[8], uint32_t (&o)[8],
 
 /* Rebuild one perspective from its full lists: v = bias + sum(PSQ rows) + sum(threat rows).
  * The lists are padded to whole batches (build_lists). */
-/* vp = sum of the listed PSQ rows (the bias row is one of them). */
-__device__ __forceinline__ void rebuild_psq(const DeviceNet& net, const uint32_t* psq_list, int n_psq, int lane, uint32_t (&vp)[16]) {
-    static_assert(kPsqGroup == 4, "list entries are fetched four at a time");
+__device__ __forceinline__ void rebuild_perspective(
+    const DeviceNet& net, const uint32_t* psq_list, int n_psq, const uint32_t* thr_list, int n_thr, int lane, uint32_t (&v)[16]) {
+    static_assert(kPsqGroup == 4 && kThrGroupFull % 4 == 0, "list entries are fetched four at a time");
     const uint4* psq_base = net.psq + lane;
+    const uint4* thr_base = net.thr + lane;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) vp[i] = 0;
+    for (int i = 0; i < 16; ++i) v[i] = 0;
 #pragma unroll 1
     for (int i = 0; i < n_psq; i += kPsqGroup) {
         const uint4 e = *reinterpret_cast<const uint4*>(psq_list + i);
@@ -495,15 +491,9 @@ __device__ __forceinline__ void rebuild_psq(const DeviceNet& net, const uint32_t
 #pragma unroll
             for (int j = 0; j < SP_PSQ_INFLIGHT; ++j) load_psq_row(psq_base, off[h + j], c[j]);
 #pragma unroll
-            for (int j = 0; j < SP_PSQ_INFLIGHT; ++j) add_psq(vp, c[j]);
+            for (int j = 0; j < SP_PSQ_INFLIGHT; ++j) add_psq(v, c[j]);
         }
     }
-}
-
-/* vt += sum of the listed threat rows. */
-__device__ __forceinline__ void rebuild_thr(const DeviceNet& net, const uint32_t* thr_list, int n_thr, int lane, uint32_t (&vt)[16]) {
-    static_assert(kThrGroupFull % 4 == 0, "list entries are fetched four at a time");
-    const uint4* thr_base = net.thr + lane;
     uint32_t s[8], o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = o[i] = 0;
@@ -531,31 +521,19 @@ __device__ __forceinline__ void rebuild_thr(const DeviceNet& net, const uint32_t
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const uint32_t even = s[u * 4 + t] - (o[u * 4 + t] << 8);
-            vt[(2 * u) * 4 + t] = __vadd2(__vadd2(vt[(2 * u) * 4 + t], even), corr);
-            vt[(2 * u + 1) * 4 + t] = __vadd2(__vadd2(vt[(2 * u + 1) * 4 + t], o[u * 4 + t]), corr);
+            v[(2 * u) * 4 + t] = __vadd2(__vadd2(v[(2 * u) * 4 + t], even), corr);
+            v[(2 * u + 1) * 4 + t] = __vadd2(__vadd2(v[(2 * u + 1) * 4 + t], o[u * 4 + t]), corr);
         }
 }
 
-/* Rebuild one perspective from its full lists: v = bias + sum(PSQ rows) + sum(threat rows).
- * The lists are padded to whole batches (build_lists). */
-__device__ __forceinline__ void rebuild_perspective(
-    const DeviceNet& net, const uint32_t* psq_list, int n_psq, const uint32_t* thr_list, int n_thr, int lane, uint32_t (&v)[16]) {
-    rebuild_psq(net, psq_list, n_psq, lane, v);
-    rebuild_thr(net, thr_list, n_thr, lane, v);
-}
-
-/* Out-of-line copy for the kernels where a rebuild is the rare path: keeps their hot loop small enough
- * for the instruction cache.  PSQ and threat parts are returned separately. */
+/* Out-of-line copy for the kernels where a rebuild is the rare path (king crossed a bucket
+ * boundary): keeps their hot loop small enough for the instruction cache. */
 __device__ __noinline__ void rebuild_perspective_cold(
-    const DeviceNet& net, const uint32_t* psq_list, int n_psq, const uint32_t* thr_list, int n_thr, int lane, uint32_t* out_psq,
-    uint32_t* out_thr) {
-    uint32_t vp[16], vt[16];
-    rebuild_psq(net, psq_list, n_psq, lane, vp);
+    const DeviceNet& net, const uint32_t* psq_list, int n_psq, const uint32_t* thr_list, int n_thr, int lane, uint32_t* out) {
+    uint32_t v[16];
+    rebuild_perspective(net, psq_list, n_psq, thr_list, n_thr, lane, v);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) vt[i] = 0;
-    rebuild_thr(net, thr_list, n_thr, lane, vt);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) out_psq[i] = vp[i], out_thr[i] = vt[i];
+    for (int i = 0; i < 16; ++i) out[i] = v[i];
 }
 
 /* Advance one perspective by its delta lists.
@@ -564,20 +542,16 @@ __device__ __noinline__ void rebuild_perspective_cold(
  * biases cancel) and summed as on the rebuild path -- whole words in s, odd bytes in o, even bytes
  * recovered as s - (o << 8) -- then the subtracted sums are added complemented.  All the "-1" of the
  * complements are repaid by one constant at the end. */
-__device__ __forceinline__ void update_psq(const DeviceNet& net, const WarpScratch& ws, int c, int lane, uint32_t (&v)[16]) {
-    static_assert(kPsqGroupDelta == kThrGroupDelta && (kPsqGroupDelta == 1 || kPsqGroupDelta == 2), "list entries are fetched one or two at a time");
+__device__ __forceinline__ void update_perspective(const DeviceNet& net, const WarpScratch& ws, int c, int lane, uint32_t (&v)[16]) {
+    static_assert(kPsqGroupDelta == 2 && kThrGroupDelta == 2, "list entries are fetched two at a time");
     const uint4* psq_base = net.psq + lane;
+    const uint4* thr_base = net.thr + lane;
     const int n_psq = ws.n_psq_delta[c]; /* padded */
     int psq_subs = 0;
 #pragma unroll 1
     for (int i = 0; i < n_psq; i += kPsqGroupDelta) {
-        uint32_t e[2];
-        if (kPsqGroupDelta == 2) {
-            const uint2 e2 = *reinterpret_cast<const uint2*>(ws.psq_delta[c] + i);
-            e[0] = e2.x, e[1] = e2.y;
-        } else {
-            e[0] = ws.psq_delta[c][i], e[1] = 0;
-        }
+        const uint2 e2 = *reinterpret_cast<const uint2*>(ws.psq_delta[c] + i);
+        const uint32_t e[2] = {e2.x, e2.y};
         uint4 rows[kPsqGroupDelta][4];
         uint32_t mask[kPsqGroupDelta];
 #pragma unroll
@@ -596,39 +570,24 @@ __device__ __forceinline__ void update_psq(const DeviceNet& net, const WarpScrat
                 v[k * 4 + 3] = __vadd2(v[k * 4 + 3], rows[j][k].w ^ mask[j]);
             }
     }
-    if (psq_subs) { /* repay the -1 of every complemented row */
-        const uint32_t repay = (static_cast<uint32_t>(psq_subs) & 0xFFFFu) * 0x10001u;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __vadd2(v[i], repay);
-    }
-}
-
-__device__ __forceinline__ void update_thr(const DeviceNet& net, const WarpScratch& ws, int c, int lane, uint32_t (&v)[16]) {
-    const uint4* thr_base = net.thr + lane;
     const int n_thr = ws.n_thr_dadd[c]; /* common padded length of the added and the subtracted list */
-    if (!n_thr) return;
     uint32_t sa[8], oa[8], ss[8], os[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) sa[i] = oa[i] = ss[i] = os[i] = 0;
 #pragma unroll 1
     for (int i = 0; i < n_thr; i += kThrGroupDelta) {
+        const uint2 ea = *reinterpret_cast<const uint2*>(ws.thr_delta[c] + i);
+        const uint2 es = *reinterpret_cast<const uint2*>(ws.thr_delta[c] + kThrDeltaCap - kThrGroupDelta - i); /* stored backwards */
         uint4 ra[kThrGroupDelta][2], rs[kThrGroupDelta][2];
-        if (kThrGroupDelta == 2) {
-            const uint2 ea = *reinterpret_cast<const uint2*>(ws.thr_delta[c] + i);
-            const uint2 es = *reinterpret_cast<const uint2*>(ws.thr_delta[c] + kThrDeltaCap - kThrGroupDelta - i); /* stored backwards */
-            load_thr_row(thr_base, ea.x, ra[0]), load_thr_row(thr_base, ea.y, ra[kThrGroupDelta - 1]);
-            load_thr_row(thr_base, es.x, rs[0]), load_thr_row(thr_base, es.y, rs[kThrGroupDelta - 1]);
-        } else {
-            load_thr_row(thr_base, ws.thr_delta[c][i], ra[0]);
-            load_thr_row(thr_base, ws.thr_delta[c][kThrDeltaCap - 1 - i], rs[0]);
-        }
+        load_thr_row(thr_base, ea.x, ra[0]), load_thr_row(thr_base, ea.y, ra[1]);
+        load_thr_row(thr_base, es.x, rs[0]), load_thr_row(thr_base, es.y, rs[1]);
 #pragma unroll
         for (int j = 0; j < kThrGroupDelta; ++j) {
             add_thr_wide(sa, oa, ra[j]);
             add_thr_wide(ss, os, rs[j]);
         }
     }
-    const uint32_t repay = 0x00010001u; /* the -1 of the complemented subtracted sums */
+    const uint32_t repay = (static_cast<uint32_t>(psq_subs + 1) & 0xFFFFu) * 0x10001u; /* +1: the complemented threat sums */
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
@@ -639,11 +598,6 @@ __device__ __forceinline__ void update_thr(const DeviceNet& net, const WarpScrat
             ve = __vadd2(__vadd2(__vadd2(ve, even_a), ~even_s), repay);
             vo = __vadd2(__vadd2(__vadd2(vo, oa[u * 4 + t]), ~os[u * 4 + t]), repay);
         }
-}
-
-__device__ __forceinline__ void update_perspective(const DeviceNet& net, const WarpScratch& ws, int c, int lane, uint32_t (&v)[16]) {
-    update_psq(net, ws, c, lane, v);
-    update_thr(net, ws, c, lane, v);
 }
 
 /* activateFt, multilayer.h:92-152, on packed pairs: out = (clamp(a,0,255) * clamp(d,0,255)) >> 9.
@@ -880,10 +834,7 @@ ft_slots_kernel(DeviceNet net, SlotStore slots, const uint32_t* __restrict__ src
         for (int c = 0; c < 2; ++c) {
             uint32_t v[16];
             if ((rebuild >> c) & 1) {
-                uint32_t vt[16];
-                rebuild_perspective_cold(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, v, vt);
-#pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] = __vadd2(v[k], vt[k]);
+                rebuild_perspective_cold(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, v);
             } else {
                 load_slot_acc(slots, from, c, lane, v);
                 update_perspective(net, ws, c, lane, v);
@@ -995,15 +946,10 @@ plan_rebuilds_kernel(DeviceNet net, RebuildPlan plan, const SpPackedBoard* __res
             bool have_prev = __shfl_up_sync(kFull, ok ? 1 : 0, 1) != 0;
             if (lane == 0) prev = carry, have_prev = carry_ok;
             /* one reservation per round: a game's items sit next to each other in `items`, so the warps
-             * that rebuild them run side by side and share the rows the positions have in common.
-             * 0 = keep updating, 1 = PSQ part only (bucket changed, same board half), 2 = both parts */
-            int kind[2];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const bool side_flip = ((prev.king[c] & 7) >= 4) != ((cur.king[c] & 7) >= 4);
-                kind[c] = !ok ? 0 : (!have_prev || side_flip) ? 2 : (needs_refresh(t, prev, cur, c) ? 1 : 0);
-            }
-            const unsigned m0 = __ballot_sync(kFull, kind[0] != 0), m1 = __ballot_sync(kFull, kind[1] != 0);
+             * that rebuild them run side by side and share the rows the positions have in common */
+            const bool want0 = ok && (!have_prev || needs_refresh(t, prev, cur, kBlack));
+            const bool want1 = ok && (!have_prev || needs_refresh(t, prev, cur, kWhite));
+            const unsigned m0 = __ballot_sync(kFull, want0), m1 = __ballot_sync(kFull, want1);
             uint32_t first_slot = 0;
             if (lane == 0 && (m0 | m1)) first_slot = atomicAdd(&plan.counters[0], static_cast<uint32_t>(__popc(m0) + __popc(m1)));
             first_slot = __shfl_sync(kFull, first_slot, 0);
@@ -1011,15 +957,11 @@ plan_rebuilds_kernel(DeviceNet net, RebuildPlan plan, const SpPackedBoard* __res
                 const unsigned lt = (1u << lane) - 1;
                 uint32_t at = first_slot + __popc(m0 & lt) + __popc(m1 & lt);
                 uint2 slots = make_uint2(kNoRebuildSlot, kNoRebuildSlot);
-                if (kind[0]) {
-                    const uint32_t flag = kind[0] == 1 ? kRebuildPsqOnly : 0u;
-                    if (at < plan.capacity) plan.items[at] = (static_cast<uint32_t>(pos) * 2) | flag, slots.x = at | flag;
+                if (want0) {
+                    if (at < plan.capacity) plan.items[at] = static_cast<uint32_t>(pos) * 2, slots.x = at;
                     ++at;
                 }
-                if (kind[1] && at < plan.capacity) {
-                    const uint32_t flag = kind[1] == 1 ? kRebuildPsqOnly : 0u;
-                    plan.items[at] = (static_cast<uint32_t>(pos) * 2 + 1) | flag, slots.y = at | flag;
-                }
+                if (want1 && at < plan.capacity) plan.items[at] = static_cast<uint32_t>(pos) * 2 + 1, slots.y = at;
                 *reinterpret_cast<uint2*>(plan.slot + 2 * pos) = slots;
             }
             carry.king[0] = __shfl_sync(kFull, cur.king[0], 31);
@@ -1029,8 +971,7 @@ plan_rebuilds_kernel(DeviceNet net, RebuildPlan plan, const SpPackedBoard* __res
     }
 }
 
-/* One warp per planned item: rebuild that perspective's PSQ part, and -- unless only the king's bucket
- * changed -- its threat part, exactly as the full refresh would. */
+/* One warp per planned item: rebuild that perspective exactly as the full refresh would. */
 __global__ void __launch_bounds__(kThreads, 4)
 run_rebuilds_kernel(DeviceNet net, RebuildPlan plan, const SpPackedBoard* __restrict__ boards, DeviceStatus* status) {
     __shared__ WarpScratch scratch[kWarpsPerCta];
@@ -1041,72 +982,37 @@ run_rebuilds_kernel(DeviceNet net, RebuildPlan plan, const SpPackedBoard* __rest
     const uint32_t stride = gridDim.x * kWarpsPerCta;
     for (uint32_t i = first + blockIdx.x * kWarpsPerCta + warp; i < last; i += stride) {
         const uint32_t item = plan.items[i];
-        const bool psq_only = (item & kRebuildPsqOnly) != 0;
         const int c = item & 1;
-        const Decoded d = decode_board(boards + ((item & ~kRebuildPsqOnly) >> 1), lane, ws.mailbox[0]);
-        uint32_t vp[16], vt[16];
+        const Decoded d = decode_board(boards + (item >> 1), lane, ws.mailbox[0]);
+        uint32_t v[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) vp[k] = vt[k] = 0;
-        /* a bad record leaves zeros; the walker reports it when it gets there */
-        if (d.ok && psq_only) {
-            /* one row per piece + the bias row, topped up with the zero row (nnue_state.cpp:440-449) */
-            const int n_psq = d.n_pieces + 1, n_pad = (n_psq + kPsqGroup - 1) / kPsqGroup * kPsqGroup;
-            __syncwarp();
-            if (lane < d.n_pieces) {
-                const int sq = nth_piece_square(d.view.occ, lane);
-                ws.psq_add[c][lane] = psq_index(t, c, d.view.mailbox[sq], sq, c ? d.view.king[1] : d.view.king[0]) * kPsqVecs;
-            }
-            if (lane == 0) ws.psq_add[c][d.n_pieces] = kPsqBiasOff;
-            if (lane > 0 && d.n_pieces + lane < n_pad) ws.psq_add[c][d.n_pieces + lane] = kPsqZeroOff;
-            __syncwarp();
-            rebuild_psq(net, ws.psq_add[c], n_pad, lane, vp);
-        } else if (d.ok && build_lists(t, nullptr, d, lane, ws, 0, 0, 1 << c) >= 0) {
-            rebuild_psq(net, ws.psq_add[c], ws.n_psq_add[c], lane, vp);
-            rebuild_thr(net, ws.thr_add[c], ws.n_thr_add[c], lane, vt);
-        }
-        uint4* out = plan.acc + static_cast<size_t>(i) * kRebuildAccVecs + lane;
+        for (int k = 0; k < 16; ++k) v[k] = 0;
+        if (d.ok && build_lists(t, nullptr, d, lane, ws, 0, 1 << c) >= 0)
+            rebuild_perspective(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, v);
+        /* a bad record is reported by the walker when it gets there */
+        uint4* out = plan.acc + static_cast<size_t>(i) * 128 + lane;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) out[32 * k] = make_uint4(vp[k * 4 + 0], vp[k * 4 + 1], vp[k * 4 + 2], vp[k * 4 + 3]);
-        if (!psq_only) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) out[128 + 32 * k] = make_uint4(vt[k * 4 + 0], vt[k * 4 + 1], vt[k * 4 + 2], vt[k * 4 + 3]);
-        }
-        __syncwarp();
+        for (int k = 0; k < 4; ++k) out[32 * k] = make_uint4(v[k * 4 + 0], v[k * 4 + 1], v[k * 4 + 2], v[k * 4 + 3]);
     }
 }
 
 __global__ void rebuilds_done_kernel(RebuildPlan plan) { plan.counters[1] = min(plan.counters[0], plan.capacity); }
 
-struct GamesShared {
-    WarpScratch scratch[kWarpsPerCta];
-    uint32_t parked[kWarpsPerCta][2][16][32]; /* one perspective's PSQ and threat registers, parked between passes */
-};
-
-__device__ __forceinline__ void load_acc(const uint4* p, uint32_t (&v)[16]) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint4 q = p[32 * k];
-        v[k * 4 + 0] = q.x, v[k * 4 + 1] = q.y, v[k * 4 + 2] = q.z, v[k * 4 + 3] = q.w;
-    }
-}
-
-/* One warp plays through one game (datagen form, src/datagen/datagen.cpp:257-262: applyMove +
- * applyImmediately + evaluate).  Like the reference's UpdatableAccumulator (nnue_state.h:47-66) it keeps
- * the PSQ and the threat part of each perspective apart; the perspective being advanced lives in
- * registers, the other one is parked in shared memory. */
+/* One warp plays through one game: both accumulators stay in registers / shared memory from ply to
+ * ply (datagen form, src/datagen/datagen.cpp:257-262: applyMove + applyImmediately + evaluate). */
 __global__ void __launch_bounds__(kThreads, SP_GAMES_MIN_BLOCKS)
 ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const uint32_t* __restrict__ game_start,
                 uint32_t n_games, uint8_t* __restrict__ act, uint8_t* __restrict__ bucket, RebuildPlan plan, DeviceStatus* status) {
-    extern __shared__ __align__(16) unsigned char games_smem[];
-    GamesShared& sh = *reinterpret_cast<GamesShared*>(games_smem);
+    __shared__ WarpScratch scratch[kWarpsPerCta];
+    __shared__ uint32_t parked[kWarpsPerCta][16][32]; /* one perspective's registers, parked between passes */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpScratch& ws = sh.scratch[warp];
+    WarpScratch& ws = scratch[warp];
     const FeatureTables& t = *net.tables;
     const uint32_t stride = gridDim.x * kWarpsPerCta;
     for (uint32_t g = blockIdx.x * kWarpsPerCta + warp; g < n_games; g += stride) {
         const size_t first = game_start[g], last = game_start[g + 1];
-        uint32_t vp[16], vt[16];
-        int in_regs = 0; /* which perspective the registers currently hold */
+        uint32_t v[16];
+        int in_regs = 0; /* which perspective `v` currently holds */
         BoardView prev{};
         bool have_prev = false;
         /* the next record (and its rebuild slots) are fetched one ply ahead so their latency hides behind
@@ -1128,13 +1034,11 @@ ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const u
                 lo = __ldg(p), hi = __ldg(p + 1);
                 if (plan.slot) slots = *reinterpret_cast<const uint2*>(plan.slot + 2 * (pos + 1));
             }
-            /* parts that arrive rebuilt from the plan */
-            const int ext_psq = (my_slots.x != kNoRebuildSlot ? 1 : 0) | (my_slots.y != kNoRebuildSlot ? 2 : 0);
-            const int ext_thr = ((my_slots.x & kRebuildPsqOnly) ? 0 : (ext_psq & 1)) | ((my_slots.y & kRebuildPsqOnly) ? 0 : (ext_psq & 2));
+            const int external = (my_slots.x != kNoRebuildSlot ? 1 : 0) | (my_slots.y != kNoRebuildSlot ? 2 : 0);
             int err = d.ok ? 0 : kErrBadBoard;
             int rebuild = 3;
             if (!err) {
-                rebuild = build_lists(t, have_prev ? &prev : nullptr, d, lane, ws, ext_psq, ext_thr);
+                rebuild = build_lists(t, have_prev ? &prev : nullptr, d, lane, ws, external);
                 if (rebuild < 0) err = kErrCapacity;
             }
             if (err) {
@@ -1145,35 +1049,35 @@ ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const u
                 have_prev = false; /* the next good board restarts the chain */
                 continue;
             }
-            /* One copy of the loop body: the two perspectives swap places once per ply and the order
-             * alternates, so that each ply starts with the perspective that is already in registers. */
+            /* One copy of the loop body.  `v` holds the perspective being advanced, the other one is
+             * parked in shared memory; they swap once per ply and the order alternates, so that each
+             * ply starts with the perspective that is already in registers. */
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 const int c = in_regs;
-                if ((rebuild >> c) & 1) {
-                    uint32_t fresh_p[16], fresh_t[16];
-                    rebuild_perspective_cold(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, fresh_p, fresh_t);
+                if ((external >> c) & 1) {
+                    const uint4* fresh = plan.acc + static_cast<size_t>(c ? my_slots.y : my_slots.x) * 128 + lane;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) vp[i] = fresh_p[i], vt[i] = fresh_t[i];
+                    for (int k = 0; k < 4; ++k) {
+                        const uint4 q = fresh[32 * k];
+                        v[k * 4 + 0] = q.x, v[k * 4 + 1] = q.y, v[k * 4 + 2] = q.z, v[k * 4 + 3] = q.w;
+                    }
+                } else if ((rebuild >> c) & 1) {
+                    uint32_t fresh[16];
+                    rebuild_perspective_cold(net, ws.psq_add[c], ws.n_psq_add[c], ws.thr_add[c], ws.n_thr_add[c], lane, fresh);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fresh[i];
                 } else {
-                    const uint32_t slot = (c ? my_slots.y : my_slots.x) & ~kRebuildPsqOnly;
-                    const uint4* fresh = plan.acc + static_cast<size_t>(slot) * kRebuildAccVecs + lane;
-                    if ((ext_psq >> c) & 1) load_acc(fresh, vp);
-                    else update_psq(net, ws, c, lane, vp);
-                    if ((ext_thr >> c) & 1) load_acc(fresh + 128, vt);
-                    else update_thr(net, ws, c, lane, vt);
+                    update_perspective(net, ws, c, lane, v);
                 }
-                uint32_t v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __vadd2(vp[i], vt[i]); /* only the wrapped sum reaches the network */
                 const int half = c == d.view.stm ? 0 : 1;
                 reinterpret_cast<uint4*>(act + pos * SP_L1_SIZE)[half * 32 + lane] = activate(v);
                 if (pass == 0) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const uint32_t other_p = sh.parked[warp][0][i][lane], other_t = sh.parked[warp][1][i][lane];
-                        sh.parked[warp][0][i][lane] = vp[i], sh.parked[warp][1][i][lane] = vt[i];
-                        vp[i] = other_p, vt[i] = other_t;
+                        const uint32_t other = parked[warp][i][lane];
+                        parked[warp][i][lane] = v[i];
+                        v[i] = other;
                     }
                     in_regs ^= 1;
                 }
@@ -1480,9 +1384,7 @@ void launch_ft_games(
     const DeviceNet& net, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, uint8_t* act,
     uint8_t* bucket, RebuildPlan plan, DeviceStatus* status, int sm_count, cudaStream_t stream) {
     if (!n_games) return;
-    /* opt in to > 48 KB of dynamic shared memory (a per-device attribute: set it on every launch) */
-    cudaFuncSetAttribute(ft_games_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(GamesShared)));
-    ft_games_kernel<<<grid_for(n_games, kWarpsPerCta, sm_count, SP_GAMES_MIN_BLOCKS), kThreads, sizeof(GamesShared), stream>>>(
+    ft_games_kernel<<<grid_for(n_games, kWarpsPerCta, sm_count, SP_GAMES_MIN_BLOCKS), kThreads, 0, stream>>>(
         net, boards, game_start, n_games, act, bucket, plan, status);
 }
 

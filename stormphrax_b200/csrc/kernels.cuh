@@ -88,17 +88,12 @@ void launch_ft_slots(
  * perspective-plies in random playouts); done inside the walker those rare, long steps cost a quarter
  * of its time.  Instead: launch_plan_rebuilds finds them (king squares only), launch_run_rebuilds
  * computes their accumulators at full-refresh efficiency into `acc`, and the walker just loads them.
- * The walker keeps the PSQ and the threat part of an accumulator apart (as the reference does,
- * nnue_state.h:47-66): a king that changes input bucket but not board half -- three rebuilds out of four
- * -- invalidates only the PSQ part, which is rebuilt from ~28 rows with no threat enumeration at all.
  * When `acc` is full the remaining ones simply stay with the walker (slot = kNoRebuildSlot). */
 constexpr uint32_t kNoRebuildSlot = 0xFFFFFFFFu;
-constexpr uint32_t kRebuildPsqOnly = 0x80000000u; /* slot / item flag: only the PSQ part is fresh */
-constexpr uint32_t kRebuildAccVecs = 256;         /* uint4 per plan slot: PSQ part [0, 128), threat part [128, 256) */
 struct RebuildPlan {
-    uint32_t* slot;     /* [2 * n_boards]: slot index (| kRebuildPsqOnly) for (board, perspective), or kNoRebuildSlot */
-    uint32_t* items;    /* [capacity]: board * 2 + perspective (| kRebuildPsqOnly), in reservation order */
-    uint4* acc;         /* [capacity][kRebuildAccVecs]: rebuilt accumulator parts, lane order */
+    uint32_t* slot;     /* [2 * n_boards]: index into acc for (board, perspective), or kNoRebuildSlot */
+    uint32_t* items;    /* [capacity]: board * 2 + perspective, in reservation order */
+    uint4* acc;         /* [capacity][4][32]: rebuilt accumulators, lane order */
     uint32_t* counters; /* [0] = items reserved so far (may run past capacity), [1] = items already computed */
     uint32_t capacity;
 };
