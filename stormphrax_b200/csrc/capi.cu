@@ -117,7 +117,7 @@ constexpr size_t align256(size_t x) { return (x + 255) & ~size_t{255}; }
 
 /* Device layout of the network. Offsets into one allocation. */
 struct NetLayout {
-    size_t psq, thr, l1_w, l1_b, l2_w, l2_b, l3_w, l3_b, total;
+    size_t psq, thr, l1_w, l1_b, l2_w, l2_limbs, l2_b, l3_w, l3_b, total;
     NetLayout() {
         size_t o = 0;
         psq = o;  o = align256(o + size_t{kPsqRows} * SP_L1_SIZE * 2);
@@ -125,6 +125,7 @@ struct NetLayout {
         l1_w = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * SP_L1_SIZE * SP_L2_SIZE);
         l1_b = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * SP_L2_SIZE * 4);
         l2_w = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * 2 * SP_L2_SIZE * SP_L3_SIZE * 4);
+        l2_limbs = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * 2 * SP_L2_SIZE * SP_L3_SIZE * 4);
         l2_b = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * SP_L3_SIZE * 4);
         l3_w = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * SP_L3_SIZE * 4);
         l3_b = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * 4);
@@ -162,6 +163,18 @@ void build_device_image(const uint8_t* payload, const NetLayout& L, uint8_t* img
     take(L.l1_w, size_t{SP_OUTPUT_BUCKETS} * SP_L1_SIZE * SP_L2_SIZE);
     take(L.l1_b, size_t{SP_OUTPUT_BUCKETS} * SP_L2_SIZE * 4);
     take(L.l2_w, size_t{SP_OUTPUT_BUCKETS} * 2 * SP_L2_SIZE * SP_L3_SIZE * 4);
+    /* byte limbs of the int32 L2 weights, laid out as tensor-core B fragments (kernels.cuh: l2_limb_index) */
+    {
+        const uint32_t* w2 = reinterpret_cast<const uint32_t*>(img + L.l2_w);
+        uint8_t* limbs = img + L.l2_limbs;
+        for (int b = 0; b < SP_OUTPUT_BUCKETS; ++b)
+            for (int k = 0; k < 2 * SP_L2_SIZE; ++k)
+                for (int o = 0; o < SP_L3_SIZE; ++o) {
+                    const uint32_t w = w2[(static_cast<size_t>(b) * 2 * SP_L2_SIZE + k) * SP_L3_SIZE + o];
+                    for (int limb = 0; limb < 4; ++limb)
+                        limbs[(static_cast<size_t>(b) * 4096 + l2_limb_index(limb, k >> 2, o)) * 4 + (k & 3)] = static_cast<uint8_t>(w >> (8 * limb));
+                }
+    }
     take(L.l2_b, size_t{SP_OUTPUT_BUCKETS} * SP_L3_SIZE * 4);
     take(L.l3_w, size_t{SP_OUTPUT_BUCKETS} * SP_L3_SIZE * 4);
     take(L.l3_b, size_t{SP_OUTPUT_BUCKETS} * 4);
@@ -402,6 +415,7 @@ static int create_impl(const void* net_image, size_t len, int device, SpNnue** o
     ctx->net.l1_w = reinterpret_cast<const int8_t*>(b + L.l1_w);
     ctx->net.l1_b = reinterpret_cast<const int32_t*>(b + L.l1_b);
     ctx->net.l2_w = reinterpret_cast<const int32_t*>(b + L.l2_w);
+    ctx->net.l2_limbs = reinterpret_cast<const uint32_t*>(b + L.l2_limbs);
     ctx->net.l2_b = reinterpret_cast<const int32_t*>(b + L.l2_b);
     ctx->net.l3_w = reinterpret_cast<const int32_t*>(b + L.l3_w);
     ctx->net.l3_b = reinterpret_cast<const int32_t*>(b + L.l3_b);

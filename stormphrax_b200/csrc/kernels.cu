@@ -1098,16 +1098,23 @@ __device__ __forceinline__ void mma_u8s8(int (&c)[4], uint32_t a0, uint32_t a1, 
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void mma_u8u8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 constexpr int kHeadWarps = 8;
 constexpr int kHeadRows = 256;  /* positions per CTA */
 constexpr int kW1Bytes = SP_L1_SIZE * SP_L2_SIZE;                  /* one bucket's L1 weights: 32 KB */
 constexpr int kW2Words = 2 * SP_L2_SIZE * SP_L3_SIZE;              /* one bucket's L2 weights: 4096 int32 */
+constexpr int kLimbStride = 80; /* bytes per row of a limb plane: 64 inputs + padding so A-fragment reads hit 32 banks */
 
 struct HeadShared {
     __align__(16) int8_t w1[kW1Bytes];                      /* current bucket, reference layout [k/4][o][k%4] */
-    __align__(16) int32_t w2[kW2Words];                     /* current bucket, [input][output] */
-    uint32_t skip_dot[kHeadWarps][16];                      /* per row: sum over the L1 outputs of skip * W3 (L3's skip term) */
-    __align__(16) int l2in[kHeadWarps][2 * SP_L2_SIZE][16]; /* skip >> 6, transposed: [input][row] */
+    __align__(16) uint32_t w2[kW2Words];                    /* current bucket: byte limbs as B fragments (l2_limb_index) */
+    __align__(16) uint8_t l2in[kHeadWarps][4][16][kLimbStride]; /* L2 inputs (skip >> 6) as four byte limbs: [limb][row][input] */
     uint16_t order[kHeadRows + 16 * SP_OUTPUT_BUCKETS];     /* rows grouped by bucket, each group padded to 16 */
     int count[SP_OUTPUT_BUCKETS];                           /* rows per bucket */
     int start[SP_OUTPUT_BUCKETS + 1];                       /* first slot of each bucket's group in `order` */
@@ -1126,9 +1133,8 @@ constexpr uint16_t kNoRow = 0xFFFF;
  * column g of n-tile nt is therefore output o = 4 g + nt, and the C fragment of lane (g, t)
  * holds outputs 8 t + nt and 8 t + 4 + nt of rows g and g + 8.
  *
- * L2 / L3: lane p owns L2 outputs p and p + 32 for all 16 rows of the tile; per input i it needs two
- * weights (conflict-free LDS) and the 16 rows' inputs (four broadcast LDS.128 from the transposed
- * l2in[i][row] array).  The L3 dot product is closed with one REDUX per row.
+ * L2 (int32 weights, multilayer.h:261-343) also runs on the tensor cores, as ten byte-limb contractions
+ * that are recombined modulo 2^32; L3 is a 64-term dot product closed with two shuffles.
  */
 static_assert(sizeof(HeadShared) * 2 <= 227 * 1024, "two CTAs per SM");
 __global__ void __launch_bounds__(kHeadWarps * 32, 2)
@@ -1184,7 +1190,7 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
             const uint4* src1 = reinterpret_cast<const uint4*>(net.l1_w + static_cast<size_t>(b) * kW1Bytes);
             uint4* dst1 = reinterpret_cast<uint4*>(sh.w1);
             for (int i = tid; i < kW1Bytes / 16; i += kHeadWarps * 32) dst1[i] = __ldg(src1 + i);
-            const uint4* src2 = reinterpret_cast<const uint4*>(net.l2_w + static_cast<size_t>(b) * kW2Words);
+            const uint4* src2 = reinterpret_cast<const uint4*>(net.l2_limbs + static_cast<size_t>(b) * kW2Words);
             uint4* dst2 = reinterpret_cast<uint4*>(sh.w2);
             for (int i = tid; i < kW2Words / 4; i += kHeadWarps * 32) dst2[i] = __ldg(src2 + i);
         }
@@ -1201,32 +1207,56 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
 #pragma unroll
                 for (int j = 0; j < 4; ++j) c[i][j] = 0;
             const uint4* w = reinterpret_cast<const uint4*>(sh.w1) + g;
-#pragma unroll 4
-            for (int s = 0; s < SP_L1_SIZE / 64; ++s) {
-                const uint4 alo = __ldg(a_row0 + s * 4), ahi = __ldg(a_row1 + s * 4);
-                uint4 q[4];
+            /* Activation rows come from global memory (L2 or HBM): the loads of the next four k-steps are
+             * issued before the MMAs of the current four, so only the first group's latency is exposed. */
+            constexpr int kGroup = 4, kGroups = SP_L1_SIZE / 64 / kGroup;
+            uint4 a_next[kGroup][2];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) q[j] = w[(s * 16 + t * 4 + j) * 8];
-                const uint32_t al[4] = {alo.x, alo.y, alo.z, alo.w}, ah[4] = {ahi.x, ahi.y, ahi.z, ahi.w};
+            for (int i = 0; i < kGroup; ++i) a_next[i][0] = __ldg(a_row0 + i * 4), a_next[i][1] = __ldg(a_row1 + i * 4);
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    const uint32_t q0[4] = {q[2 * m].x, q[2 * m].y, q[2 * m].z, q[2 * m].w};
-                    const uint32_t q1[4] = {q[2 * m + 1].x, q[2 * m + 1].y, q[2 * m + 1].z, q[2 * m + 1].w};
+            for (int grp = 0; grp < kGroups; ++grp) {
+                uint4 a_cur[kGroup][2];
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) mma_u8s8(c[nt], al[2 * m], ah[2 * m], al[2 * m + 1], ah[2 * m + 1], q0[nt], q1[nt]);
+                for (int i = 0; i < kGroup; ++i) a_cur[i][0] = a_next[i][0], a_cur[i][1] = a_next[i][1];
+                if (grp + 1 < kGroups) {
+#pragma unroll
+                    for (int i = 0; i < kGroup; ++i) {
+                        a_next[i][0] = __ldg(a_row0 + ((grp + 1) * kGroup + i) * 4);
+                        a_next[i][1] = __ldg(a_row1 + ((grp + 1) * kGroup + i) * 4);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < kGroup; ++i) {
+                    const int s = grp * kGroup + i;
+                    uint4 q[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) q[j] = w[(s * 16 + t * 4 + j) * 8];
+                    const uint32_t al[4] = {a_cur[i][0].x, a_cur[i][0].y, a_cur[i][0].z, a_cur[i][0].w};
+                    const uint32_t ah[4] = {a_cur[i][1].x, a_cur[i][1].y, a_cur[i][1].z, a_cur[i][1].w};
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        const uint32_t q0[4] = {q[2 * m].x, q[2 * m].y, q[2 * m].z, q[2 * m].w};
+                        const uint32_t q1[4] = {q[2 * m + 1].x, q[2 * m + 1].y, q[2 * m + 1].z, q[2 * m + 1].w};
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) mma_u8s8(c[nt], al[2 * m], ah[2 * m], al[2 * m + 1], ah[2 * m + 1], q0[nt], q1[nt]);
+                    }
                 }
             }
-            /* L1 epilogue + dual activation, multilayer.h:219-256 (kShift = -2) */
-            /* The L1 outputs also feed L3 directly (skip connection, multilayer.h:353-446).  All sums are
-             * modulo 2^32, so that term is summed here, where the outputs are in registers. */
+            /* L1 epilogue + dual activation, multilayer.h:219-256 (kShift = -2).
+             * The L1 outputs also feed L3 directly (skip connection, multilayer.h:353-446).  All sums are
+             * modulo 2^32, so that term is summed here, where the outputs are in registers.
+             * The L2 inputs (skip >> 6, range [-2^19, 4096]: the wrapped square may be negative) leave as
+             * four unsigned byte limbs of their 32-bit two's complement, ready to be IMMA A fragments. */
+            uint32_t skip_dot[2];
 #pragma unroll
             for (int hrow = 0; hrow < 2; ++hrow) {
                 const int r = g + 8 * hrow;
                 uint32_t dot = 0;
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
+                for (int cc = 0; cc < 2; ++cc) {
+                    uint32_t cr_limbs[4] = {0, 0, 0, 0}, sq_limbs[4] = {0, 0, 0, 0};
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
+                    for (int nt = 0; nt < 4; ++nt) {
                         const int o = 8 * t + 4 * cc + nt;
                         const int x = static_cast<int>(static_cast<uint32_t>(c[nt][hrow * 2 + cc] >> 2)
                                                        + static_cast<uint32_t>(__ldg(net.l1_b + b * SP_L2_SIZE + o)));
@@ -1235,52 +1265,88 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
                         sq = min(sq, 16777216);
                         dot += static_cast<uint32_t>(cr << 6) * static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + o))
                              + static_cast<uint32_t>(sq >> 6) * static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + SP_L2_SIZE + o));
-                        sh.l2in[warp][o][r] = cr;                    /* (cr << 6) >> 6 */
-                        sh.l2in[warp][SP_L2_SIZE + o][r] = sq >> 12; /* (sq >> 6) >> 6 */
+                        const uint32_t in_cr = static_cast<uint32_t>(cr);       /* (cr << 6) >> 6 */
+                        const uint32_t in_sq = static_cast<uint32_t>(sq >> 12); /* (sq >> 6) >> 6, arithmetic */
+#pragma unroll
+                        for (int limb = 0; limb < 4; ++limb) {
+                            cr_limbs[limb] |= ((in_cr >> (8 * limb)) & 0xFFu) << (8 * nt);
+                            sq_limbs[limb] |= ((in_sq >> (8 * limb)) & 0xFFu) << (8 * nt);
+                        }
                     }
+                    /* inputs 8t + 4cc .. + 3 (CReLU half) and 32 + 8t + 4cc .. + 3 (squared half) of row r */
+#pragma unroll
+                    for (int limb = 0; limb < 4; ++limb) {
+                        *reinterpret_cast<uint32_t*>(&sh.l2in[warp][limb][r][8 * t + 4 * cc]) = cr_limbs[limb];
+                        *reinterpret_cast<uint32_t*>(&sh.l2in[warp][limb][r][SP_L2_SIZE + 8 * t + 4 * cc]) = sq_limbs[limb];
+                    }
+                }
                 dot += __shfl_xor_sync(kFull, dot, 1);
                 dot += __shfl_xor_sync(kFull, dot, 2);
-                if (t == 0) sh.skip_dot[warp][r] = dot;
+                skip_dot[hrow] = dot;
             }
             __syncwarp();
 
-            /* L2 + L3, multilayer.h:261-447 */
-            uint32_t acc[16][2];
-            {
-                const uint32_t bias0 = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + lane));
-                const uint32_t bias1 = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + lane + 32));
+            /* L2 on the tensor cores, multilayer.h:261-343: out = bias + sum_k in[k] * W2[k][o] (mod 2^32).
+             * With in = sum_i a_i 2^(8i) and W2 = sum_j w_j 2^(8j) (unsigned byte limbs), the product modulo
+             * 2^32 is sum over i + j <= 3 of (a_i w_j) << 8 (i + j): ten u8 x u8 -> s32 contractions of
+             * length 64, each exact (64 * 255 * 255 < 2^31).  Lane (g, t) ends up with outputs
+             * o = 8 nt + 2 t, + 1 of rows g and g + 8. */
+            uint32_t l2[8][4];
 #pragma unroll
-                for (int r = 0; r < 16; ++r) acc[r][0] = bias0, acc[r][1] = bias1;
+            for (int nt = 0; nt < 8; ++nt) {
+                const uint32_t b0v = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + nt * 8 + 2 * t));
+                const uint32_t b1v = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + nt * 8 + 2 * t + 1));
+                l2[nt][0] = b0v, l2[nt][1] = b1v, l2[nt][2] = b0v, l2[nt][3] = b1v;
             }
-#pragma unroll 4
-            for (int i = 0; i < 2 * SP_L2_SIZE; ++i) {
-                const uint32_t w0 = static_cast<uint32_t>(sh.w2[i * SP_L3_SIZE + lane]);
-                const uint32_t w1 = static_cast<uint32_t>(sh.w2[i * SP_L3_SIZE + lane + 32]);
-                const int4* in4 = reinterpret_cast<const int4*>(sh.l2in[warp][i]);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int4 v = in4[q];
-                    const uint32_t in[4] = {static_cast<uint32_t>(v.x), static_cast<uint32_t>(v.y), static_cast<uint32_t>(v.z), static_cast<uint32_t>(v.w)};
+            for (int shift = 0; shift < 4; ++shift) {
+                int part[8][4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        acc[q * 4 + e][0] += in[e] * w0;
-                        acc[q * 4 + e][1] += in[e] * w1;
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) part[nt][k] = 0;
+#pragma unroll
+                for (int i = 0; i <= shift; ++i) { /* input limb i with weight limb shift - i */
+                    const int j = shift - i;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(&sh.l2in[warp][i][g][ks * 32 + 4 * t]);
+                        const uint32_t a1 = *reinterpret_cast<const uint32_t*>(&sh.l2in[warp][i][g + 8][ks * 32 + 4 * t]);
+                        const uint32_t a2 = *reinterpret_cast<const uint32_t*>(&sh.l2in[warp][i][g][ks * 32 + 16 + 4 * t]);
+                        const uint32_t a3 = *reinterpret_cast<const uint32_t*>(&sh.l2in[warp][i][g + 8][ks * 32 + 16 + 4 * t]);
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) {
+                            const uint32_t* wl = sh.w2 + ((j * 8 + nt) * 16 + ks * 8 + t) * 8 + g; /* l2_limb_index */
+                            mma_u8u8(part[nt], a0, a1, a2, a3, wl[0], wl[4 * 8]);
+                        }
                     }
                 }
-            }
-            const uint32_t w3_0 = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + lane));
-            const uint32_t w3_1 = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + lane + 32));
-            const uint32_t bias3 = static_cast<uint32_t>(__ldg(net.l3_b + b));
-            int32_t result = 0;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const int c0 = min(max(static_cast<int>(acc[r][0]), 0), 262144);
-                const int c1 = min(max(static_cast<int>(acc[r][1]), 0), 262144);
-                const uint32_t part = static_cast<uint32_t>(c0) * w3_0 + static_cast<uint32_t>(c1) * w3_1;
-                const uint32_t l3 = __reduce_add_sync(kFull, part) + sh.skip_dot[warp][r] + bias3;
-                if (lane == r) result = static_cast<int32_t>(static_cast<int64_t>(static_cast<int32_t>(l3)) * 400 / 16777216); /* truncates toward zero */
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) l2[nt][k] += static_cast<uint32_t>(part[nt][k]) << (8 * shift);
             }
-            if (lane < 16 && ord[lane] != kNoRow) out[base + ord[lane]] = result;
+
+            /* L3 + scale, multilayer.h:345-447, 484-489 */
+            uint32_t dot_lo = 0, dot_hi = 0; /* rows g and g + 8 */
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const uint32_t w3a = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + nt * 8 + 2 * t));
+                const uint32_t w3b = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + nt * 8 + 2 * t + 1));
+                dot_lo += static_cast<uint32_t>(min(max(static_cast<int>(l2[nt][0]), 0), 262144)) * w3a
+                        + static_cast<uint32_t>(min(max(static_cast<int>(l2[nt][1]), 0), 262144)) * w3b;
+                dot_hi += static_cast<uint32_t>(min(max(static_cast<int>(l2[nt][2]), 0), 262144)) * w3a
+                        + static_cast<uint32_t>(min(max(static_cast<int>(l2[nt][3]), 0), 262144)) * w3b;
+            }
+            dot_lo += __shfl_xor_sync(kFull, dot_lo, 1), dot_hi += __shfl_xor_sync(kFull, dot_hi, 1);
+            dot_lo += __shfl_xor_sync(kFull, dot_lo, 2), dot_hi += __shfl_xor_sync(kFull, dot_hi, 2);
+            if (t == 0) {
+                const uint32_t bias3 = static_cast<uint32_t>(__ldg(net.l3_b + b));
+                const int32_t l3_lo = static_cast<int32_t>(dot_lo + skip_dot[0] + bias3), l3_hi = static_cast<int32_t>(dot_hi + skip_dot[1] + bias3);
+                /* the final division truncates toward zero */
+                if (row0 != kNoRow) out[base + row0] = static_cast<int32_t>(static_cast<int64_t>(l3_lo) * 400 / 16777216);
+                if (row1 != kNoRow) out[base + row1] = static_cast<int32_t>(static_cast<int64_t>(l3_hi) * 400 / 16777216);
+            }
             __syncwarp();
         }
         __syncthreads(); /* the next bucket overwrites the staged weights */

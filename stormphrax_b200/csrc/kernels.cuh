@@ -29,6 +29,7 @@ struct DeviceNet {
     const int8_t* l1_w; /* [8][256][32][4] reference order (multilayer.h:180-196) */
     const int32_t* l1_b;
     const int32_t* l2_w; /* [8][64][64] */
+    const uint32_t* l2_limbs; /* [8][4 limbs][8 n-tiles][16 k-quads][8]: byte limbs of l2_w as IMMA B fragments (l2_limb_index) */
     const int32_t* l2_b;
     const int32_t* l3_w; /* [8][64] */
     const int32_t* l3_b;
@@ -63,6 +64,11 @@ struct DeviceStatus {
 inline int lane_order_element(int k, int lane, int e) {
     return (k >= 2 ? 512 : 0) + lane * 16 + 4 * (e >> 1) + (k & 1) + 2 * (e & 1);
 }
+
+/* Word index, inside one bucket's 4096-word block, of the B-fragment word that holds byte limb `limb` of
+ * the L2 weights W2[k][o] for k = 4 kq .. 4 kq + 3 (one byte each, k ascending).  Within an n-tile the 32
+ * lanes (k-quad t, column g) of one IMMA read 32 consecutive words: no bank conflicts. */
+inline int l2_limb_index(int limb, int kq, int o) { return ((limb * 8 + (o >> 3)) * 16 + kq) * 8 + (o & 7); }
 
 /* boards[i] -> act[i][1024], bucket[i]; every position rebuilt from scratch */
 void launch_ft_full(
