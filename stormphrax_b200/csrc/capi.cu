@@ -43,6 +43,7 @@ struct SpNnue {
     cudaEvent_t ev_ft[2] = {nullptr, nullptr}, ev_head[2] = {nullptr, nullptr}, ev_join = nullptr, ev_start = nullptr;
     std::vector<cudaEvent_t> ev_chunk; /* one "inputs of chunk i have landed" event per chunk */
     bool overlap = true;
+    HeadSort head_sort{};        /* scratch of the dense head's bucket grouping, grown on demand */
     bool plan_rebuilds = true;   /* playout walker: rebuilds computed ahead by their own kernel (SP_NNUE_PLAN_REBUILDS=0: inline) */
     RebuildPlan plan{};          /* scratch of that scheme, sized for the largest stream seen */
     size_t plan_boards = 0;
@@ -223,6 +224,20 @@ struct DeviceGuard {
 
 cudaStream_t pick(SpNnue* ctx, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : ctx->stream; }
 
+/* The dense head groups a launch's positions by bucket in this scratch.  Growing it waits for the
+ * device, which only happens when a call is larger than any before. */
+int ensure_head_sort(SpNnue* ctx, size_t n) {
+    const size_t need = n + 16 * SP_OUTPUT_BUCKETS;
+    if (need <= ctx->head_sort.capacity) return SP_OK;
+    SP_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(ctx->head_sort.order);
+    ctx->head_sort.order = nullptr, ctx->head_sort.capacity = 0;
+    if (!ctx->head_sort.counters) SP_CUDA(ctx, cudaMalloc(&ctx->head_sort.counters, kHeadSortCounters * sizeof(uint32_t)));
+    SP_CUDA(ctx, cudaMalloc(&ctx->head_sort.order, need * sizeof(uint32_t)));
+    ctx->head_sort.capacity = need;
+    return SP_OK;
+}
+
 cudaEvent_t take_event(SpNnue* ctx) {
     if (!ctx->event_pool.empty()) {
         cudaEvent_t e = ctx->event_pool.back();
@@ -272,6 +287,7 @@ int chunk_event(SpNnue* ctx, size_t i, cudaEvent_t* ev) {
 
 int eval_full_device(
     SpNnue* ctx, const SpPackedBoard* d_boards, size_t n, int32_t* d_out, cudaStream_t stream, const HostIo* io = nullptr) {
+    if (const int rc = ensure_head_sort(ctx, std::min(n, ctx->chunk))) return rc;
     const bool overlap = ctx->overlap && n > ctx->chunk;
     if (io) {
         /* all uploads are queued up front on their own stream; chunk i's kernels wait for upload i only */
@@ -315,7 +331,8 @@ int eval_full_device(
         }
         {
             Timed timed{ctx, hs, SP_KERNEL_HEAD};
-            launch_head(ctx->net, ctx->d_act2[buf], ctx->d_bucket2[buf], m, d_out + off, nullptr, ctx->d_status, ctx->sm_count, hs);
+            launch_head(ctx->net, ctx->d_act2[buf], ctx->d_bucket2[buf], m, d_out + off, nullptr, ctx->head_sort, ctx->sm_count, hs);
+            ctx->counters[SP_CTR_LAUNCHES] += 3;
         }
         if (overlap) SP_CUDA(ctx, cudaEventRecord(ctx->ev_head[buf], ctx->aux));
         if (io) { /* results of this chunk go home while the next chunk computes */
@@ -456,6 +473,8 @@ void sp_nnue_destroy(SpNnue* ctx) {
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->h2d) cudaStreamSynchronize(ctx->h2d), cudaStreamDestroy(ctx->h2d);
     if (ctx->d2h) cudaStreamSynchronize(ctx->d2h), cudaStreamDestroy(ctx->d2h);
+    cudaFree(ctx->head_sort.order);
+    cudaFree(ctx->head_sort.counters);
     cudaFree(ctx->plan.slot);
     cudaFree(ctx->plan.items);
     cudaFree(ctx->plan.acc);
@@ -566,8 +585,9 @@ int sp_nnue_forward_device(SpNnue* ctx, const uint8_t* d_act, const uint8_t* d_b
     if (!d_act || !d_bucket || !d_out) return fail(ctx, SP_ERR_INVALID, "null argument");
     if (reinterpret_cast<uintptr_t>(d_act) & 15) return fail(ctx, SP_ERR_INVALID, "d_act must be 16-byte aligned");
     DeviceGuard guard{ctx->device};
-    launch_head(ctx->net, d_act, d_bucket, n, d_out, nullptr, ctx->d_status, ctx->sm_count, pick(ctx, stream));
-    ctx->counters[SP_CTR_LAUNCHES] += 1;
+    if (const int rc = ensure_head_sort(ctx, n)) return rc;
+    launch_head(ctx->net, d_act, d_bucket, n, d_out, nullptr, ctx->head_sort, ctx->sm_count, pick(ctx, stream));
+    ctx->counters[SP_CTR_LAUNCHES] += 4;
     ctx->counters[SP_CTR_EVALS] += n;
     SP_CUDA(ctx, cudaGetLastError());
     return SP_OK;

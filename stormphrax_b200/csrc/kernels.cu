@@ -1115,16 +1115,70 @@ struct HeadShared {
     __align__(16) int8_t w1[kW1Bytes];                      /* current bucket, reference layout [k/4][o][k%4] */
     __align__(16) uint32_t w2[kW2Words];                    /* current bucket: byte limbs as B fragments (l2_limb_index) */
     __align__(16) uint8_t l2in[kHeadWarps][4][16][kLimbStride]; /* L2 inputs (skip >> 6) as four byte limbs: [limb][row][input] */
-    uint16_t order[kHeadRows + 16 * SP_OUTPUT_BUCKETS];     /* rows grouped by bucket, each group padded to 16 */
-    int count[SP_OUTPUT_BUCKETS];                           /* rows per bucket */
-    int start[SP_OUTPUT_BUCKETS + 1];                       /* first slot of each bucket's group in `order` */
+    uint32_t rows[kHeadRows];                               /* this CTA's slice of the bucket-grouped order */
+    uint8_t tile_bucket[kHeadRows / 16];                    /* bucket of each 16-row tile (0xFF = empty tile) */
 };
-constexpr uint16_t kNoRow = 0xFFFF;
+
+/* ---- counting sort of a launch's positions by output bucket (three tiny kernels) */
+__device__ __forceinline__ void head_span(const uint32_t* range, uint32_t range_len, size_t& first, size_t& n) {
+    first = 0;
+    if (range) { /* positions [range[0], range[range_len]) */
+        first = range[0];
+        n = range[range_len] - first;
+    }
+}
+
+__global__ void head_hist_kernel(const uint8_t* __restrict__ bucket, size_t n, const uint32_t* __restrict__ range, uint32_t range_len,
+                                 HeadSort sort) {
+    __shared__ unsigned hist[SP_OUTPUT_BUCKETS];
+    size_t first;
+    head_span(range, range_len, first, n);
+    if (threadIdx.x < SP_OUTPUT_BUCKETS) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int b = bucket[first + i];
+        if (b < SP_OUTPUT_BUCKETS) atomicAdd(&hist[b], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < SP_OUTPUT_BUCKETS && hist[threadIdx.x]) atomicAdd(&sort.counters[threadIdx.x], hist[threadIdx.x]);
+}
+
+__global__ void head_scan_kernel(HeadSort sort) {
+    uint32_t at = 0;
+    for (int b = 0; b < SP_OUTPUT_BUCKETS; ++b) {
+        sort.counters[16 + b] = at;
+        at += (sort.counters[b] + 15u) & ~15u; /* whole tiles per bucket */
+    }
+    sort.counters[16 + SP_OUTPUT_BUCKETS] = at;
+}
+
+__global__ void head_scatter_kernel(const uint8_t* __restrict__ bucket, size_t n, const uint32_t* __restrict__ range, uint32_t range_len,
+                                    HeadSort sort, int32_t* __restrict__ out) {
+    size_t first;
+    head_span(range, range_len, first, n);
+    const int lane = threadIdx.x & 31;
+    const size_t n_round = (n + 31) & ~size_t{31}; /* whole warps stay together for the match */
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_round; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int b = i < n ? bucket[first + i] : 0xFE;
+        const unsigned peers = __match_any_sync(kFull, b);
+        if (b < SP_OUTPUT_BUCKETS) {
+            /* one reservation per bucket per warp */
+            const int leader = __ffs(peers) - 1;
+            uint32_t slot = 0;
+            if (lane == leader) slot = atomicAdd(&sort.counters[8 + b], static_cast<uint32_t>(__popc(peers)));
+            slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1));
+            sort.order[sort.counters[16 + b] + slot] = static_cast<uint32_t>(first + i);
+        } else if (i < n) {
+            out[first + i] = INT32_MIN; /* rejected board */
+        }
+    }
+}
+constexpr uint32_t kNoRow = kHeadNoRow;
 
 /*
- * One CTA = 256 consecutive positions, grouped by output bucket in shared memory so that every
- * 16-row tile has ONE bucket; per bucket present (normally one or two) the CTA stages that bucket's
- * L1 and L2 weights (48 KB) in shared memory once and its warps share the tiles.
+ * One CTA = 256 rows of the bucket-grouped order: sixteen 16-row tiles, two per warp, that (except
+ * where two groups meet) all belong to ONE bucket, whose L1 and L2 weights (48 KB) are staged in shared
+ * memory once.
  *
  * L1: the contraction index k may be visited in any order as long as A and B agree.  Per 64-wide
  * k-step, lane (g = lane / 4, t = lane % 4) loads 16 contiguous activation bytes of rows g and
@@ -1138,53 +1192,31 @@ constexpr uint16_t kNoRow = 0xFFFF;
  */
 static_assert(sizeof(HeadShared) * 2 <= 227 * 1024, "two CTAs per SM");
 __global__ void __launch_bounds__(kHeadWarps * 32, 2)
-head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __restrict__ bucket, size_t n,
-            int32_t* __restrict__ out, const uint32_t* __restrict__ range, uint32_t range_len) {
+head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __restrict__ bucket, int32_t* __restrict__ out, HeadSort sort) {
     extern __shared__ __align__(16) unsigned char head_smem[];
     HeadShared& sh = *reinterpret_cast<HeadShared*>(head_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    size_t base = static_cast<size_t>(blockIdx.x) * kHeadRows;
-    if (range) { /* positions [range[0], range[range_len]) */
-        base += range[0];
-        n = range[range_len];
-    }
-    if (base >= n) return;
-    const int rows = static_cast<int>(min(static_cast<size_t>(kHeadRows), n - base));
+    const uint32_t total = sort.counters[16 + SP_OUTPUT_BUCKETS]; /* padded: a multiple of 16 */
+    const uint32_t slice = blockIdx.x * kHeadRows;
+    if (slice >= total) return;
+    constexpr size_t base = 0; /* `rows` holds absolute position indices */
 
-    /* ---- group the CTA's rows by bucket (counting sort; order within a bucket = position order) */
-    const int my_bucket = tid < rows ? bucket[base + tid] : 0xFF;
-    const bool valid = my_bucket < SP_OUTPUT_BUCKETS;
-    if (tid < SP_OUTPUT_BUCKETS) sh.count[tid] = 0;
+    sh.rows[tid] = slice + tid < total ? sort.order[slice + tid] : kNoRow;
     __syncthreads();
-    int rank_in_warp = 0;
-    if (valid) {
-        const unsigned peers = __match_any_sync(__activemask(), my_bucket);
-        rank_in_warp = __popc(peers & ((1u << lane) - 1));
-        /* the first lane of each peer group reserves the group's slots */
-        int first_slot = 0;
-        const int leader = __ffs(peers) - 1;
-        if (lane == leader) first_slot = atomicAdd(&sh.count[my_bucket], __popc(peers));
-        rank_in_warp += __shfl_sync(peers, first_slot, leader);
+    if (tid < kHeadRows / 16) {
+        /* a group is padded at its end only, so a tile's first row tells its bucket */
+        const uint32_t first = sh.rows[tid * 16];
+        sh.tile_bucket[tid] = first == kNoRow ? 0xFF : bucket[first];
     }
     __syncthreads();
-    if (tid == 0) {
-        int at = 0;
-        for (int b = 0; b < SP_OUTPUT_BUCKETS; ++b) {
-            sh.start[b] = at;
-            at += (sh.count[b] + 15) & ~15;
-        }
-        sh.start[SP_OUTPUT_BUCKETS] = at;
-    }
-    for (int i = tid; i < kHeadRows + 16 * SP_OUTPUT_BUCKETS; i += kHeadWarps * 32) sh.order[i] = kNoRow;
-    __syncthreads();
-    if (valid) sh.order[sh.start[my_bucket] + rank_in_warp] = static_cast<uint16_t>(tid);
-    if (tid < rows && !valid) out[base + tid] = INT32_MIN; /* rejected board */
-    __syncthreads();
+    unsigned present = 0;
+#pragma unroll
+    for (int i = 0; i < kHeadRows / 16; ++i)
+        if (sh.tile_bucket[i] < SP_OUTPUT_BUCKETS) present |= 1u << sh.tile_bucket[i];
 
-    for (int b = 0; b < SP_OUTPUT_BUCKETS; ++b) {
-        const int n_tiles = (sh.start[b + 1] - sh.start[b]) >> 4;
-        if (!n_tiles) continue;
+    for (unsigned todo = present; todo; todo &= todo - 1) {
+        const int b = __ffs(todo) - 1;
         /* ---- stage this bucket's weights */
         {
             const uint4* src1 = reinterpret_cast<const uint4*>(net.l1_w + static_cast<size_t>(b) * kW1Bytes);
@@ -1195,12 +1227,13 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
             for (int i = tid; i < kW2Words / 4; i += kHeadWarps * 32) dst2[i] = __ldg(src2 + i);
         }
         __syncthreads();
-        for (int tile = warp; tile < n_tiles; tile += kHeadWarps) {
-            const uint16_t* ord = sh.order + sh.start[b] + tile * 16;
-            const int row0 = ord[g], row1 = ord[g + 8];
-            /* padding slots read row 0 of the CTA; their results are never written */
-            const uint4* a_row0 = reinterpret_cast<const uint4*>(act + (base + (row0 == kNoRow ? 0 : row0)) * SP_L1_SIZE) + t;
-            const uint4* a_row1 = reinterpret_cast<const uint4*>(act + (base + (row1 == kNoRow ? 0 : row1)) * SP_L1_SIZE) + t;
+        for (int tile = warp; tile < kHeadRows / 16; tile += kHeadWarps) {
+            if (sh.tile_bucket[tile] != b) continue;
+            const uint32_t* ord = sh.rows + tile * 16;
+            const uint32_t row0 = ord[g], row1 = ord[g + 8];
+            /* padding slots read the tile's first row; their results are never written */
+            const uint4* a_row0 = reinterpret_cast<const uint4*>(act + (base + (row0 == kNoRow ? ord[0] : row0)) * SP_L1_SIZE) + t;
+            const uint4* a_row1 = reinterpret_cast<const uint4*>(act + (base + (row1 == kNoRow ? ord[0] : row1)) * SP_L1_SIZE) + t;
             int c[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -1462,13 +1495,20 @@ void launch_slot_activate(
 }
 
 void launch_head(
-    const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, const uint32_t* range,
-    DeviceStatus*, int, cudaStream_t stream, uint32_t range_len) {
+    const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, const uint32_t* range, HeadSort sort,
+    int sm_count, cudaStream_t stream, uint32_t range_len) {
     if (!n) return;
+    const size_t slots = std::min(sort.capacity, n + 16 * SP_OUTPUT_BUCKETS); /* n bounds the rows of this launch */
+    cudaMemsetAsync(sort.counters, 0, kHeadSortCounters * sizeof(uint32_t), stream);
+    cudaMemsetAsync(sort.order, 0xFF, slots * sizeof(uint32_t), stream);
+    const unsigned sort_grid = static_cast<unsigned>(std::min<size_t>((n + 1023) / 1024, static_cast<size_t>(sm_count) * 4));
+    head_hist_kernel<<<sort_grid, 256, 0, stream>>>(bucket, n, range, range_len, sort);
+    head_scan_kernel<<<1, 1, 0, stream>>>(sort);
+    head_scatter_kernel<<<sort_grid, 256, 0, stream>>>(bucket, n, range, range_len, sort, out);
     /* opt in to > 48 KB of dynamic shared memory (a per-device attribute: set it on every launch) */
     cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadShared)));
-    const unsigned grid = static_cast<unsigned>((n + kHeadRows - 1) / kHeadRows);
-    head_kernel<<<grid, kHeadWarps * 32, sizeof(HeadShared), stream>>>(net, act, bucket, n, out, range, range_len);
+    const unsigned grid = static_cast<unsigned>((slots + kHeadRows - 1) / kHeadRows);
+    head_kernel<<<grid, kHeadWarps * 32, sizeof(HeadShared), stream>>>(net, act, bucket, out, sort);
 }
 
 void launch_adjust(

@@ -120,13 +120,23 @@ void launch_slot_activate(
     SlotStore slots, const uint32_t* slot_ids, const uint8_t* stm, size_t n, uint8_t* act, uint8_t* bucket,
     DeviceStatus* status, int sm_count, cudaStream_t stream);
 
-/* act[i], bucket[i] -> out[i] : L1 (int8 IMMA) + L2 + L3 + scale.  bucket[i] > 7 marks a
- * position whose board was rejected: out[i] = INT32_MIN.
+/* Scratch of the dense head: the launch's positions grouped by output bucket (counting sort), so that
+ * every CTA works on rows of one bucket with that bucket's weights staged in shared memory once. */
+struct HeadSort {
+    uint32_t* order;    /* [capacity]: position indices grouped by bucket, each group padded to 16 with kHeadNoRow */
+    uint32_t* counters; /* [0..7] rows per bucket, [8..15] scatter cursors, [16..24] group starts (24 = padded total) */
+    size_t capacity;    /* entries in `order`: at least n + 16 * 8 */
+};
+constexpr uint32_t kHeadNoRow = 0xFFFFFFFFu;
+constexpr int kHeadSortCounters = 32;
+
+/* act[i], bucket[i] -> out[i] : L1 (int8 IMMA) + L2 (byte-limb IMMA) + L3 + scale.  bucket[i] > 7 marks
+ * a position whose board was rejected: out[i] = INT32_MIN.
  * range == nullptr: positions [0, n).  Otherwise positions [range[0], range[range_len]) read on the
- * device (a span of a game_start array) and n is only an upper bound of their count for the grid. */
+ * device (a span of a game_start array) and n is only an upper bound of their count for the grids. */
 void launch_head(
     const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, const uint32_t* range,
-    DeviceStatus* status, int sm_count, cudaStream_t stream, uint32_t range_len = 0);
+    HeadSort sort, int sm_count, cudaStream_t stream, uint32_t range_len = 0);
 
 /* raw network outputs -> adjusted static evals (eval.cpp:25-67); one thread per position.
  * `correction` may be null. */
