@@ -317,7 +317,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_position": bytes_per_pos, "launches": k_launches, "avg_launch_ms": avg_launch_ms,
-            "share_of_step": k_ms / (k_ms + other_ms) if k_ms + other_ms else None,
+            # fraction of the step's wall time during which this kernel runs; the other kernels overlap it on
+            # a second stream, so their event spans (below) are stretched by sharing the SMs -- the serialised
+            # ncu launch list in profiles/ gives the kernel's share without overlap
+            "share_of_step": (k_ms / args.steps) / ms_per_step if ms_per_step else None,
             "other_kernels_ms_per_launch": {k: v[0] / max(v[1], 1) for k, v in prof.items() if k != kernel and v[1]},
         }
         # DRAM traffic per launch from the committed ncu capture of this kernel (profiles/traffic.json)
