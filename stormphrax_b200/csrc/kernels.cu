@@ -434,17 +434,28 @@ __device__ __forceinline__ int build_lists(
 
 __device__ __forceinline__ uint32_t odd_bytes(uint32_t w) { return __byte_perm(w, 0, 0x4341); }
 
+/* Weight-row loads.  SP_ROW_LOAD selects the cache policy (experiments): 0 = ld.global.nc (default),
+ * 1 = threat rows do not allocate in L1, 2 = no row allocates in L1. */
+#ifndef SP_ROW_LOAD
+#define SP_ROW_LOAD 0
+#endif
+__device__ __forceinline__ uint4 ldg_no_allocate(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
 /* `base` = table + lane; `off` = uint4 offset of the row (a list entry) */
 __device__ __forceinline__ void load_psq_row(const uint4* base, uint32_t off, uint4 (&c)[4]) {
     const uint4* r = base + off;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) c[k] = __ldg(r + 32 * k);
+    for (int k = 0; k < 4; ++k) c[k] = SP_ROW_LOAD >= 2 ? ldg_no_allocate(r + 32 * k) : __ldg(r + 32 * k);
 }
 
 __device__ __forceinline__ void load_thr_row(const uint4* base, uint32_t off, uint4 (&c)[2]) {
     const uint4* r = base + off;
-    c[0] = __ldg(r);
-    c[1] = __ldg(r + 32);
+    c[0] = SP_ROW_LOAD >= 1 ? ldg_no_allocate(r) : __ldg(r);
+    c[1] = SP_ROW_LOAD >= 1 ? ldg_no_allocate(r + 32) : __ldg(r + 32);
 }
 
 __device__ __forceinline__ void add_psq(uint32_t (&v)[16], const uint4 (&c)[4]) {

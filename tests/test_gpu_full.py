@@ -203,3 +203,30 @@ def test_adjust_eval_matches_reference_golden(gpu_ctx):
     inside = np.abs(base) < 24999  # where the golden value was not clamped, the pre-clamp value is known
     got = gpu_ctx.adjust(boards, raw, api.AdjustParams.defaults(), correction=corr)
     assert (got[inside] == want[inside]).all()
+
+
+def test_dense_head_large_mixed_buckets(gpu_ctx, c_oracle):
+    """Config-4 size with rows of all eight buckets interleaved at random plus rejected rows: exercises the
+    bucket grouping (counting sort, group padding, CTAs that straddle two groups) and the byte-limb L2."""
+    import torch
+
+    rng = np.random.default_rng(11)
+    n = (1 << 16) + 17
+    act = rng.integers(0, 128, (n, 1024), dtype=np.uint8)
+    bucket = rng.integers(0, 8, n, dtype=np.uint8)
+    bucket[rng.choice(n, 50, replace=False)] = 0xFF  # boards the FT rejected
+    bucket[:300] = 3                                  # a long single-bucket run
+    d_out = torch.empty(n, dtype=torch.int32, device="cuda")
+    s = _stream()
+    gpu_ctx.forward_device(_dev(act), _dev(bucket), n, d_out, s)
+    gpu_ctx.sync(s)
+    got = d_out.cpu().numpy()
+    assert (got[bucket == 0xFF] == INT32_MIN).all()
+    sample = rng.choice(np.nonzero(bucket != 0xFF)[0], 1500, replace=False)
+    want = np.array([c_oracle.forward(act[i], int(bucket[i])) for i in sample], dtype=np.int32)
+    assert (got[sample] == want).all()
+    # the same rows in another order give the same values (grouping is order-independent)
+    perm = rng.permutation(n)
+    gpu_ctx.forward_device(_dev(act[perm]), _dev(bucket[perm]), n, d_out, s)
+    gpu_ctx.sync(s)
+    assert (d_out.cpu().numpy() == got[perm]).all()
