@@ -189,6 +189,32 @@ int sp_nnue_profile_read(SpNnue* ctx, double ms[SP_NUM_KERNEL_CLASSES], uint64_t
 /* Debug/test access: accumulators of a slot in LOGICAL order, int16[2][1024] (black, white). */
 int sp_nnue_read_slot(SpNnue* ctx, uint32_t slot, int16_t* out_acc, SpPackedBoard* out_board);
 
+/* ---------------------------------------------------------------- batched self-play (datagen)
+ * Replaces the per-thread game loop of src/datagen/datagen.cpp:96-321 (`datagen::run`, :323-400): random
+ * opening plies, search -> applyMove -> NnueState::applyImmediately -> (move, score) until the game is
+ * decided or adjudicated, one viriformat record per game (src/datagen/viriformat.cpp:33-63).  Instead of
+ * one game per thread, `concurrency` games run at once (split over `threads` host threads, each with its
+ * own evaluator context on `device`); their searches are resumable and every static evaluation they ask
+ * for is answered in device batches through the NnueState / EvalBatch mirror.  The search itself is a
+ * stand-in (iterative-deepening alpha-beta, csrc/host/selfplay.h): the reference's search is out of scope.
+ * `out` receives the concatenated records (thread by thread, completion order); *out_len is always set to
+ * the bytes produced (SP_ERR_CAPACITY if they did not fit; out == NULL with out_capacity == 0 only counts). */
+typedef struct SpSelfplayParams {
+    uint32_t concurrency;    /* games in flight, all threads together */
+    uint32_t total_games;    /* games to play, all threads together */
+    uint32_t threads;        /* host threads (0 = 1) */
+    uint32_t depth;          /* iterative deepening stops after this depth ... */
+    uint32_t nodes_per_move; /* ... or once a finished iteration has used this many nodes (datagen.cpp:76 soft limit) */
+    uint32_t max_plies;      /* undecided games are drawn here (0 = 300) */
+    uint64_t seed;
+} SpSelfplayParams;
+typedef struct SpSelfplayStats {
+    uint64_t games, positions, nodes, evals, batches, searches;
+} SpSelfplayStats;
+int sp_selfplay_run(
+    const void* net_image, size_t len, int device, const SpSelfplayParams* params, SpSelfplayStats* stats, uint8_t* out,
+    size_t out_capacity, size_t* out_len);
+
 /* ---------------------------------------------------------------- host utilities (no GPU)
  * Workload generation and CPU execution of the shared feature code, for tests and benchmarks. */
 /* Random legal playouts from the standard start position: game g is seeded from (seed, g); all
@@ -206,6 +232,7 @@ size_t sp_host_playouts(
 int sp_host_board_from_fen(const char* fen, SpPackedBoard* out);
 int sp_host_board_to_fen(const SpPackedBoard* board, char* out, size_t cap);
 int sp_host_legal_moves(const SpPackedBoard* board, SpMove* out /* [256] */);
+int sp_host_in_check(const SpPackedBoard* board); /* 1 / 0, -1 for a malformed record */
 int sp_host_apply_move(const SpPackedBoard* board, SpMove move, SpPackedBoard* out);
 int sp_host_features(const SpPackedBoard* board, int perspective, int kind, uint32_t* out /* [512] */);
 /* Workload statistics for the roofline: out[0] = PSQ rows, out[1] = threat rows, out[2] = pawn-pair

@@ -70,9 +70,11 @@ SIGNATURES = {
     "sp_host_board_from_fen": (C.c_int, [C.c_char_p, _vp]),
     "sp_host_board_to_fen": (C.c_int, [_vp, C.c_char_p, _sz]),
     "sp_host_legal_moves": (C.c_int, [_vp, _vp]),
+    "sp_host_in_check": (C.c_int, [_vp]),
     "sp_host_apply_move": (C.c_int, [_vp, C.c_uint16, _vp]),
     "sp_host_features": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "sp_host_feature_delta": (C.c_int, [_vp, _vp, C.c_int] + [_vp] * 8),
+    "sp_selfplay_run": (C.c_int, [_vp, _sz, C.c_int, _vp, _vp, _vp, _sz, _vp]),
 }
 
 
@@ -325,6 +327,13 @@ def legal_moves(board) -> np.ndarray:
     return out[:n].copy()
 
 
+def in_check(board) -> bool:
+    rc = lib().sp_host_in_check(_boards(board).ctypes.data)
+    if rc < 0:
+        raise ValueError("malformed board record")
+    return bool(rc)
+
+
 def apply_move(board, move: int) -> np.ndarray:
     board = _boards(board).reshape(1)
     out = np.zeros(1, dtype=BOARD_DTYPE)
@@ -380,3 +389,61 @@ def feature_delta(before, after, perspective: int):
     if rc < 0:
         raise NnueError(SP_ERR_BAD_BOARD, "bad board")
     return (rc == 1, *[b[: c.value].copy() for b, c in zip(bufs, counts)])
+
+
+class SelfplayParams(C.Structure):
+    """SpSelfplayParams (include/sp_nnue.h)."""
+
+    _fields_ = [
+        ("concurrency", C.c_uint32),
+        ("total_games", C.c_uint32),
+        ("threads", C.c_uint32),
+        ("depth", C.c_uint32),
+        ("nodes_per_move", C.c_uint32),
+        ("max_plies", C.c_uint32),
+        ("seed", C.c_uint64),
+    ]
+
+
+class SelfplayStats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("games", "positions", "nodes", "evals", "batches", "searches")]
+
+
+def selfplay(net_image, device: int = 0, *, concurrency: int = 1024, total_games: int = 1024, threads: int = 1, depth: int = 3,
+             nodes_per_move: int = 5000, max_plies: int = 300, seed: int = 42, capacity: int | None = None):
+    """Batched self-play on the device (sp_selfplay_run).  Returns (viriformat bytes as uint8 array, stats dict)."""
+    img = np.ascontiguousarray(net_image, dtype=np.uint8)
+    p = SelfplayParams(concurrency, total_games, threads, depth, nodes_per_move, max_plies, seed)
+    st = SelfplayStats()
+    cap = capacity if capacity is not None else total_games * (32 + 4 * (max_plies + 2))
+    out = np.empty(cap, dtype=np.uint8)
+    out_len = C.c_size_t(0)
+    rc = lib().sp_selfplay_run(img.ctypes.data, img.size, device, C.byref(p), C.byref(st), out.ctypes.data, cap, C.byref(out_len))
+    if rc != SP_OK:
+        raise NnueError(rc, (lib().sp_nnue_last_error(None) or b"").decode())
+    return out[: out_len.value].copy(), {k: int(getattr(st, k)) for k, _ in SelfplayStats._fields_}
+
+
+def parse_viriformat(data):
+    """viriformat bytes -> list of (start board record, moves uint16[], scores int16[]) (src/datagen/viriformat.cpp:51-62)."""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    games, at = [], 0
+    while at < len(data):
+        start = data[at : at + 32].view(BOARD_DTYPE)[0].copy()
+        at += 32
+        pairs = data[at:].view("<u2").reshape(-1, 2)
+        end = int(np.flatnonzero((pairs[:, 0] == 0) & (pairs[:, 1] == 0))[0])
+        games.append((start, pairs[:end, 0].copy(), pairs[:end, 1].copy().view("<i2")))
+        at += 4 * (end + 1)
+    return games
+
+
+def viri_to_move(board, viri: int) -> int:
+    """viriformat move (from | to << 6 | promo << 12 | type flags) -> this library's SpMove, by matching the legal moves."""
+    flags = {0x0000: 0, 0xC000: 1, 0x8000: 2, 0x4000: 3}[viri & 0xC000]
+    frm, to, promo = viri & 63, (viri >> 6) & 63, (viri >> 12) & 3
+    want = frm << 10 | to << 4 | (promo << 2 if flags == 1 else 0) | flags
+    moves = legal_moves(board)
+    if want not in moves:
+        raise ValueError(f"viriformat move {viri:#06x} is not legal in {board_to_fen(board)}")
+    return want

@@ -118,7 +118,7 @@ constexpr size_t align256(size_t x) { return (x + 255) & ~size_t{255}; }
 
 /* Device layout of the network. Offsets into one allocation. */
 struct NetLayout {
-    size_t psq, thr, l1_w, l1_b, l2_w, l2_limbs, l2_b, l3_w, l3_b, total;
+    size_t psq, thr, l1_w, l1_b, l2_w, l2_limbs, l2_frags, l2_b, l3_w, l3_b, total;
     NetLayout() {
         size_t o = 0;
         psq = o;  o = align256(o + size_t{kPsqRows} * SP_L1_SIZE * 2);
@@ -127,6 +127,7 @@ struct NetLayout {
         l1_b = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * SP_L2_SIZE * 4);
         l2_w = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * 2 * SP_L2_SIZE * SP_L3_SIZE * 4);
         l2_limbs = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * 2 * SP_L2_SIZE * SP_L3_SIZE * 4);
+        l2_frags = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * 2 * SP_L2_SIZE * SP_L3_SIZE * 4);
         l2_b = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * SP_L3_SIZE * 4);
         l3_w = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * SP_L3_SIZE * 4);
         l3_b = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * 4);
@@ -175,6 +176,19 @@ void build_device_image(const uint8_t* payload, const NetLayout& L, uint8_t* img
                     for (int limb = 0; limb < 4; ++limb)
                         limbs[(static_cast<size_t>(b) * 4096 + l2_limb_index(limb, k >> 2, o)) * 4 + (k & 3)] = static_cast<uint8_t>(w >> (8 * limb));
                 }
+        uint8_t* frags = img + L.l2_frags;
+        for (int b = 0; b < SP_OUTPUT_BUCKETS; ++b)
+            for (int limb = 0; limb < 4; ++limb)
+                for (int nt = 0; nt < 8; ++nt)
+                    for (int ks = 0; ks < 2; ++ks)
+                        for (int lane = 0; lane < 32; ++lane)
+                            for (int reg = 0; reg < 2; ++reg)
+                                for (int m = 0; m < 4; ++m) {
+                                    const int g = lane >> 2, t = lane & 3;
+                                    const int k = 32 * ks + 8 * t + 4 * reg + m, o = 8 * nt + g;
+                                    const uint32_t w = w2[(static_cast<size_t>(b) * 2 * SP_L2_SIZE + k) * SP_L3_SIZE + o];
+                                    frags[(static_cast<size_t>(b) * 4096 + l2_fragment_index(limb, nt, ks, lane, reg)) * 4 + m] = static_cast<uint8_t>(w >> (8 * limb));
+                                }
     }
     take(L.l2_b, size_t{SP_OUTPUT_BUCKETS} * SP_L3_SIZE * 4);
     take(L.l3_w, size_t{SP_OUTPUT_BUCKETS} * SP_L3_SIZE * 4);
@@ -227,7 +241,7 @@ cudaStream_t pick(SpNnue* ctx, void* stream) { return stream ? static_cast<cudaS
 /* The dense head groups a launch's positions by bucket in this scratch.  Growing it waits for the
  * device, which only happens when a call is larger than any before. */
 int ensure_head_sort(SpNnue* ctx, size_t n) {
-    const size_t need = n + 16 * SP_OUTPUT_BUCKETS;
+    const size_t need = n + kHeadGroupPad * SP_OUTPUT_BUCKETS;
     if (need <= ctx->head_sort.capacity) return SP_OK;
     SP_CUDA(ctx, cudaDeviceSynchronize());
     cudaFree(ctx->head_sort.order);
@@ -433,6 +447,7 @@ static int create_impl(const void* net_image, size_t len, int device, SpNnue** o
     ctx->net.l1_b = reinterpret_cast<const int32_t*>(b + L.l1_b);
     ctx->net.l2_w = reinterpret_cast<const int32_t*>(b + L.l2_w);
     ctx->net.l2_limbs = reinterpret_cast<const uint32_t*>(b + L.l2_limbs);
+    ctx->net.l2_frags = reinterpret_cast<const uint32_t*>(b + L.l2_frags);
     ctx->net.l2_b = reinterpret_cast<const int32_t*>(b + L.l2_b);
     ctx->net.l3_w = reinterpret_cast<const int32_t*>(b + L.l3_w);
     ctx->net.l3_b = reinterpret_cast<const int32_t*>(b + L.l3_b);

@@ -59,6 +59,7 @@ void EvalBatch::enqueue(uint32_t srcSlot, uint32_t dstSlot, bool rebuild, const 
         m_dst.push_back(dstSlot);
         m_boards.push_back(board);
     }
+    if (!out) return;
     m_evalSlots.push_back(dstSlot);
     m_stm.push_back(static_cast<uint8_t>(stm));
     m_out.push_back(out);
@@ -83,18 +84,20 @@ int EvalBatch::flush() {
 
 /* ------------------------------------------------------------------ NnueState */
 
-void NnueState::setNetwork(SpNnue* network, uint32_t slotBase) {
+void NnueState::setNetwork(SpNnue* network, uint32_t slotBase, uint32_t depth) {
     m_network = network;
     m_slotBase = slotBase;
     m_top = 0;
-    std::fill(m_clean.begin(), m_clean.end(), 0);
-    if (network) report("NnueState::setNetwork", network, sp_nnue_slots_reserve(network, size_t{slotBase} + kStackDepth));
+    m_clean.assign(depth, 0);
+    m_stale.assign(depth, 0);
+    if (network) report("NnueState::setNetwork", network, sp_nnue_slots_reserve(network, size_t{slotBase} + depth));
 }
 
 /* reset, nnue_state.cpp:539-560: rebuild both perspectives at stack level 0 */
 void NnueState::resetPacked(const SpPackedBoard& board) {
     m_top = 0;
     std::fill(m_clean.begin(), m_clean.end(), 0);
+    std::fill(m_stale.begin(), m_stale.end(), 0);
     const uint32_t s = slot(0);
     m_clean[0] = report("NnueState::reset", m_network, sp_nnue_refresh(m_network, &s, &board, 1));
 }
@@ -103,6 +106,7 @@ void NnueState::resetPacked(const SpPackedBoard& board) {
 BoardObserver NnueState::push() {
     ++m_top;
     m_clean[m_top] = 0;
+    m_stale[m_top] = 0;
     m_ctx = {};
     return BoardObserver{m_ctx};
 }
@@ -128,12 +132,13 @@ void NnueState::applyPacked(const SpPackedBoard& board) {
         rc = sp_nnue_update(m_network, &src, &dst, &board, 1);
     }
     m_clean[m_top] = report("NnueState::applyImmediately", m_network, rc);
+    m_stale[m_top] = 0;
 }
 
 /* evaluate, nnue_state.cpp:598-610 + ensureUpToDate :636-697 */
 i32 NnueState::evaluatePacked(const SpPackedBoard& board, Color stm) {
     const uint32_t dst = slot(m_top);
-    if (!m_clean[m_top]) applyPacked(board);
+    if (!m_clean[m_top] || m_stale[m_top]) applyPacked(board);
     i32 out = 0;
     const uint8_t side = static_cast<uint8_t>(stm);
     report("NnueState::evaluate", m_network, sp_nnue_eval_slots(m_network, &dst, &side, 1, &out));
@@ -142,13 +147,14 @@ i32 NnueState::evaluatePacked(const SpPackedBoard& board, Color stm) {
 
 void NnueState::evaluateAsyncPacked(EvalBatch& batch, const SpPackedBoard& board, Color stm, i32* out) {
     const uint32_t dst = slot(m_top);
-    if (m_clean[m_top]) {
+    if (m_clean[m_top] && !m_stale[m_top]) {
         batch.enqueue(EvalBatch::kNoUpdate, dst, false, board, stm, out); /* already up to date: evaluate only */
         return;
     }
-    const int from = cleanAncestor();
+    const int from = cleanAncestor(); /* may be this very level when it is stale: the slot is updated in place */
     batch.enqueue(from < 0 ? dst : slot(static_cast<uint32_t>(from)), dst, from < 0, board, stm, out);
     m_clean[m_top] = 1; /* valid once the batch is flushed, which must happen before the next dependent call */
+    m_stale[m_top] = 0;
 }
 
 /* evaluateOnce, nnue_state.cpp:612-634: stack-free, from scratch */

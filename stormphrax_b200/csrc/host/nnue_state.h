@@ -70,7 +70,8 @@ public:
 
     explicit EvalBatch(SpNnue* network) : m_network{network} {}
 
-    /* result is written to *out by flush().  A state may have ONE evaluation pending per flush. */
+    /* result is written to *out by flush().  A state may have ONE evaluation pending per flush.
+     * out == nullptr: bring dstSlot up to date without evaluating it. */
     void enqueue(uint32_t srcSlot, uint32_t dstSlot, bool rebuild, const SpPackedBoard& board, Color stm, i32* out);
     [[nodiscard]] size_t pending() const { return m_out.size(); }
     /* Runs everything queued; returns an SpStatus. */
@@ -91,11 +92,13 @@ class NnueState {
 public:
     static constexpr uint32_t kStackDepth = 256; /* nnue_state.h:88 */
 
-    /* Slots [slotBase, slotBase + kStackDepth) of `network` belong to this state. */
+    /* Slots [slotBase, slotBase + depth) of `network` belong to this state.  The reference's stack is 256
+     * deep (kStackDepth); drivers that run tens of thousands of states with a bounded search depth pass
+     * a smaller one (a slot is 4 KB of device memory). */
     NnueState() = default;
-    explicit NnueState(SpNnue* network, uint32_t slotBase = 0) { setNetwork(network, slotBase); }
+    explicit NnueState(SpNnue* network, uint32_t slotBase = 0, uint32_t depth = kStackDepth) { setNetwork(network, slotBase, depth); }
 
-    void setNetwork(SpNnue* network, uint32_t slotBase = 0);
+    void setNetwork(SpNnue* network, uint32_t slotBase = 0, uint32_t depth = kStackDepth);
 
     template <typename Position> void reset(const Position& pos) { resetPacked(pos.pack()); }
 
@@ -113,6 +116,17 @@ public:
     /* queue instead of running: the result lands in *out when batch.flush() is called */
     template <typename Position> void evaluateAsync(EvalBatch& batch, const Position& pos, Color stm, i32* out) {
         evaluateAsyncPacked(batch, pos.pack(), stm, out);
+    }
+
+    /* applyImmediately for batched drivers: the current level moves on to a new position, but the device
+     * work is left to the next evaluate / evaluateAsync at or below this level (the device derives the
+     * delta from the board stored in the slot, however many plies behind it is). */
+    void applyLazily() { m_stale[m_top] = 1; }
+    /* reset for batched drivers: forget everything; the next evaluation rebuilds level 0 from scratch */
+    void invalidate() {
+        m_top = 0;
+        m_clean.assign(m_clean.size(), 0);
+        m_stale.assign(m_stale.size(), 0);
     }
 
     template <typename Position> [[nodiscard]] static i32 evaluateOnce(const Position& pos, Color stm) {
@@ -136,7 +150,8 @@ private:
     uint32_t m_slotBase{0};
     uint32_t m_top{0};
     UpdateContext m_ctx{};
-    std::vector<uint8_t> m_clean = std::vector<uint8_t>(kStackDepth, 0);
+    std::vector<uint8_t> m_clean = std::vector<uint8_t>(kStackDepth, 0); /* slot holds the accumulators of its stored board */
+    std::vector<uint8_t> m_stale = std::vector<uint8_t>(kStackDepth, 0); /* ... but that board is an ancestor of the level's position */
 };
 
 /* ---- eval.h wrappers (src/eval/eval.cpp:25-28, 74-77, 109-112) */

@@ -1,0 +1,60 @@
+/* selfplay.cpp -- extern "C" entry point of the batched self-play driver (selfplay.h). */
+#include "selfplay.h"
+
+#include <atomic>
+#include <string>
+#include <thread>
+
+using namespace sp::host;
+
+extern "C" int sp_selfplay_run(
+    const void* net_image, size_t len, int device, const SpSelfplayParams* params, SpSelfplayStats* stats, uint8_t* out,
+    size_t out_capacity, size_t* out_len) {
+    if (!net_image || !params || !stats || !out_len || (!out && out_capacity)) return SP_ERR_INVALID;
+    const uint32_t threads = std::max<uint32_t>(1, params->threads);
+    /* one evaluator context per host thread: its own stream, scratch and slot store, so the threads' batches
+     * overlap on the device and nothing is shared on the host */
+    std::vector<SpNnue*> contexts(threads, nullptr);
+    int rc = SP_OK;
+    for (uint32_t t = 0; t < threads && rc == SP_OK; ++t) rc = sp_nnue_create(net_image, len, device, &contexts[t]);
+    std::vector<std::vector<uint8_t>> records(threads);
+    std::vector<selfplay::Stats> per_thread(threads);
+    std::atomic<int> failed{0};
+    if (rc == SP_OK) {
+        std::vector<std::thread> pool;
+        for (uint32_t t = 0; t < threads; ++t)
+            pool.emplace_back([&, t] {
+                selfplay::Params p;
+                p.concurrency = std::max<uint32_t>(1, params->concurrency / threads);
+                p.totalGames = params->total_games / threads + (t < params->total_games % threads ? 1 : 0);
+                p.depth = std::min<uint32_t>(std::max<uint32_t>(1, params->depth), selfplay::kMaxPly - 8);
+                p.nodesPerMove = params->nodes_per_move;
+                p.maxPlies = params->max_plies ? params->max_plies : 300;
+                p.seed = params->seed + 0x9E3779B97F4A7C15ULL * (t + 1);
+                if (!p.totalGames) return;
+                selfplay::DeviceEvaluator evaluator{contexts[t], p.concurrency};
+                selfplay::Driver<selfplay::DeviceEvaluator> driver{p, evaluator};
+                if (!driver.run(records[t], per_thread[t])) failed.store(1);
+            });
+        for (auto& th : pool) th.join();
+    }
+    *stats = SpSelfplayStats{};
+    size_t total = 0;
+    for (uint32_t t = 0; t < threads; ++t) {
+        stats->games += per_thread[t].games, stats->positions += per_thread[t].positions, stats->nodes += per_thread[t].nodes;
+        stats->evals += per_thread[t].evals, stats->batches += per_thread[t].batches, stats->searches += per_thread[t].searches;
+        total += records[t].size();
+    }
+    *out_len = total;
+    if (rc == SP_OK && failed.load()) rc = SP_ERR_CUDA;
+    if (rc == SP_OK && total > out_capacity) rc = out ? SP_ERR_CAPACITY : SP_OK; /* out == NULL: size query only */
+    if (rc == SP_OK && out) {
+        size_t at = 0;
+        for (uint32_t t = 0; t < threads; ++t) {
+            std::memcpy(out + at, records[t].data(), records[t].size());
+            at += records[t].size();
+        }
+    }
+    for (SpNnue* ctx : contexts) sp_nnue_destroy(ctx);
+    return rc;
+}

@@ -20,6 +20,8 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "sp_delta.h"
 
@@ -1154,17 +1156,27 @@ __global__ void head_hist_kernel(const uint8_t* __restrict__ bucket, size_t n, c
     if (threadIdx.x < SP_OUTPUT_BUCKETS && hist[threadIdx.x]) atomicAdd(&sort.counters[threadIdx.x], hist[threadIdx.x]);
 }
 
-__global__ void head_scan_kernel(HeadSort sort) {
-    uint32_t at = 0;
-    for (int b = 0; b < SP_OUTPUT_BUCKETS; ++b) {
-        sort.counters[16 + b] = at;
-        at += (sort.counters[b] + 15u) & ~15u; /* whole tiles per bucket */
-    }
-    sort.counters[16 + SP_OUTPUT_BUCKETS] = at;
-}
-
+/* Group starts (each group padded to whole tiles) from the histogram; every block derives them for itself,
+ * block 0 publishes them for the head kernel and fills the padding slots. */
 __global__ void head_scatter_kernel(const uint8_t* __restrict__ bucket, size_t n, const uint32_t* __restrict__ range, uint32_t range_len,
                                     HeadSort sort, int32_t* __restrict__ out) {
+    __shared__ uint32_t start[SP_OUTPUT_BUCKETS + 1];
+    if (threadIdx.x == 0) {
+        uint32_t at = 0;
+        for (int b = 0; b < SP_OUTPUT_BUCKETS; ++b) {
+            start[b] = at;
+            at += (sort.counters[b] + kHeadGroupPad - 1) & ~(kHeadGroupPad - 1);
+        }
+        start[SP_OUTPUT_BUCKETS] = at;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        if (threadIdx.x <= SP_OUTPUT_BUCKETS) sort.counters[16 + threadIdx.x] = start[threadIdx.x];
+        for (uint32_t i = threadIdx.x; i < SP_OUTPUT_BUCKETS * kHeadGroupPad; i += blockDim.x) {
+            const uint32_t b = i / kHeadGroupPad, at = start[b] + sort.counters[b] + i % kHeadGroupPad;
+            if (at < start[b + 1]) sort.order[at] = kHeadNoRow;
+        }
+    }
     size_t first;
     head_span(range, range_len, first, n);
     const int lane = threadIdx.x & 31;
@@ -1178,7 +1190,7 @@ __global__ void head_scatter_kernel(const uint8_t* __restrict__ bucket, size_t n
             uint32_t slot = 0;
             if (lane == leader) slot = atomicAdd(&sort.counters[8 + b], static_cast<uint32_t>(__popc(peers)));
             slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1));
-            sort.order[sort.counters[16 + b] + slot] = static_cast<uint32_t>(first + i);
+            sort.order[start[b] + slot] = static_cast<uint32_t>(first + i);
         } else if (i < n) {
             out[first + i] = INT32_MIN; /* rejected board */
         }
@@ -1397,6 +1409,279 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
     }
 }
 
+/* ------------------------------------------------------------------ dense head, streaming form
+ *
+ * The same arithmetic as head_kernel, organised around the HBM stream (the head is the one kernel of
+ * this library that is bound by it: 1 KB of activations per position, read once).
+ *
+ *   - one persistent CTA per SM works on a contiguous run of 32-row tiles of the bucket-grouped order;
+ *   - a producer warp keeps kHeadStages tiles in flight: every lane issues ONE bulk copy (TMA engine,
+ *     cp.async.bulk global -> shared, 1 KB = one activation row) into a ring of tiles, completion counted
+ *     in bytes on the stage's `full` mbarrier; rows are padded to 1088 B so that the A-fragment reads
+ *     (LDS.128, 8 rows x 4 k-chunks per quarter warp) touch every bank group once;
+ *   - eight consumer warps take tiles round-robin.  A warp owns its tile's 32 rows (two m16 tiles), so
+ *     every weight fragment it fetches from shared memory feeds two IMMAs, and releases the stage
+ *     (`empty` mbarrier) as soon as L1 is done -- the epilogue, L2 and L3 run from registers while the
+ *     TMA engine refills the stage;
+ *   - L1 -> L2 without a shared-memory round trip: the contraction index of an IMMA may be visited in
+ *     any order as long as A and B agree, so L2's k-slots are DEFINED as the order in which L1's C
+ *     fragment leaves the outputs in a lane (lane (g, t) holds outputs 8t .. 8t+7 of rows g and g+8 =
+ *     k-slots 4t..4t+3 and 16+4t..16+4t+3), and the L2 weight limbs are laid out to match at upload
+ *     (l2_fragment_index);
+ *   - L2 by Horner's rule over the limb weight: acc = (acc << 8) + sum_{i+j = s} a_i w_j for s = 3..0,
+ *     the IMMA accumulating straight into acc (s32 accumulation wraps, as everything here must);
+ *     the CReLU half of the inputs is < 2^13, so its limbs 2 and 3 are skipped: 17 instead of 20
+ *     contractions of length 32.
+ */
+#ifndef SP_HEAD_CONSUMERS
+#define SP_HEAD_CONSUMERS 11 /* + the producer = 12 warps, three per scheduler: 168 registers each */
+#endif
+#ifndef SP_HEAD_STAGES
+#define SP_HEAD_STAGES 5
+#endif
+constexpr int kHeadConsumers = SP_HEAD_CONSUMERS;
+constexpr int kStreamThreads = (kHeadConsumers + 1) * 32;
+constexpr int kTileRows = 32;
+constexpr int kTileRowStride = SP_L1_SIZE + 64;
+constexpr int kHeadStages = SP_HEAD_STAGES;
+
+struct HeadStreamShared {
+    __align__(128) uint8_t a[kHeadStages][kTileRows * kTileRowStride];
+    __align__(16) uint4 w1[kW1Bytes / 16]; /* chunk (k-quad q, output quad g) at q * 8 + (g ^ ((q >> 2 & 3) << 1)) */
+    __align__(16) uint2 w2[kW2Words / 2];  /* l2_fragment_index */
+    __align__(8) uint64_t full[kHeadStages];
+    uint64_t empty[kHeadStages];
+    uint32_t rows[kHeadStages][kTileRows];
+};
+static_assert(sizeof(HeadStreamShared) <= 227 * 1024, "one CTA per SM");
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kHeadConsumers * 32) : "memory"); }
+
+__global__ void __launch_bounds__(kStreamThreads, 1)
+head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __restrict__ out, HeadSort sort) {
+    extern __shared__ __align__(16) unsigned char head_smem[];
+    HeadStreamShared& sh = *reinterpret_cast<HeadStreamShared*>(head_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    /* this CTA's run of tiles */
+    const uint32_t n_tiles = sort.counters[16 + SP_OUTPUT_BUCKETS] / kTileRows; /* groups are padded to whole tiles */
+    const uint32_t t0 = static_cast<uint32_t>(static_cast<uint64_t>(n_tiles) * blockIdx.x / gridDim.x);
+    const uint32_t t1 = static_cast<uint32_t>(static_cast<uint64_t>(n_tiles) * (blockIdx.x + 1) / gridDim.x);
+    if (t0 >= t1) return;
+
+    if (tid == 0) {
+        for (int i = 0; i < kHeadStages; ++i) mbar_init(&sh.full[i], 1), mbar_init(&sh.empty[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kHeadConsumers) {
+        /* ---- producer: one bulk copy per lane and tile */
+        for (uint32_t n = 0; n < t1 - t0; ++n) {
+            const int stage = n % kHeadStages;
+            mbar_wait(&sh.empty[stage], ((n / kHeadStages) & 1) ^ 1);
+            const uint32_t row = sort.order[static_cast<size_t>(t0 + n) * kTileRows + lane];
+            sh.rows[stage][lane] = row;
+            const bool valid = row != kHeadNoRow;
+            const uint32_t bytes = __popc(__ballot_sync(kFull, valid)) * SP_L1_SIZE;
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&sh.full[stage], bytes);
+            if (valid) bulk_copy_g2s(&sh.a[stage][lane * kTileRowStride], act + static_cast<size_t>(row) * SP_L1_SIZE, SP_L1_SIZE, &sh.full[stage]);
+        }
+        return;
+    }
+
+    /* ---- consumers */
+    uint32_t cur = t0;
+    while (cur < t1) {
+        /* the bucket of tile `cur` and the end of its group, from the group starts */
+        int b = 0;
+#pragma unroll
+        for (int i = 1; i < SP_OUTPUT_BUCKETS; ++i)
+            if (sort.counters[16 + i] <= cur * kTileRows) b = i;
+        const uint32_t seg_end = min(t1, sort.counters[16 + b + 1] / kTileRows);
+
+        consumers_sync(); /* nobody still reads the previous bucket's weights */
+        {
+            const uint4* src1 = reinterpret_cast<const uint4*>(net.l1_w + static_cast<size_t>(b) * kW1Bytes);
+            for (int i = tid; i < kW1Bytes / 16; i += kHeadConsumers * 32) {
+                const int q = i >> 3, og = i & 7;
+                sh.w1[q * 8 + (og ^ (((q >> 2) & 3) << 1))] = __ldg(src1 + i);
+            }
+            const uint4* src2 = reinterpret_cast<const uint4*>(net.l2_frags + static_cast<size_t>(b) * kW2Words);
+            uint4* dst2 = reinterpret_cast<uint4*>(sh.w2);
+            for (int i = tid; i < kW2Words / 4; i += kHeadConsumers * 32) dst2[i] = __ldg(src2 + i);
+        }
+        consumers_sync();
+
+        for (uint32_t tile = cur + warp; tile < seg_end; tile += kHeadConsumers) {
+            const uint32_t n = tile - t0;
+            const int stage = n % kHeadStages;
+            mbar_wait(&sh.full[stage], (n / kHeadStages) & 1);
+
+            /* ---- L1: 32 rows x 32 outputs, k = 1024 */
+            int c[2][4][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) c[mt][i][j] = 0;
+            const uint8_t* a_base = &sh.a[stage][g * kTileRowStride + 16 * t];
+            const uint4* w_base = sh.w1 + (g ^ (t << 1));
+#pragma unroll 4
+            for (int s = 0; s < SP_L1_SIZE / 64; ++s) {
+                uint4 al[2], ah[2], q[4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    al[mt] = *reinterpret_cast<const uint4*>(a_base + (16 * mt) * kTileRowStride + 64 * s);
+                    ah[mt] = *reinterpret_cast<const uint4*>(a_base + (16 * mt + 8) * kTileRowStride + 64 * s);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) q[j] = w_base[(s * 16 + t * 4 + j) * 8];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const uint32_t q0[4] = {q[2 * m].x, q[2 * m].y, q[2 * m].z, q[2 * m].w};
+                    const uint32_t q1[4] = {q[2 * m + 1].x, q[2 * m + 1].y, q[2 * m + 1].z, q[2 * m + 1].w};
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const uint32_t lo[4] = {al[mt].x, al[mt].y, al[mt].z, al[mt].w};
+                        const uint32_t hi[4] = {ah[mt].x, ah[mt].y, ah[mt].z, ah[mt].w};
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) mma_u8s8(c[mt][nt], lo[2 * m], hi[2 * m], lo[2 * m + 1], hi[2 * m + 1], q0[nt], q1[nt]);
+                    }
+                }
+            }
+            uint32_t row_id[2][2];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) row_id[mt][0] = sh.rows[stage][16 * mt + g], row_id[mt][1] = sh.rows[stage][16 * mt + g + 8];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.empty[stage]); /* the TMA engine may refill the stage */
+
+            /* ---- L1 epilogue (multilayer.h:219-256), skip term of L3, L2 inputs as byte limbs in A-fragment order:
+             * register index hrow + 2 cc = a0..a3 of an IMMA (row g | g+8, k-slots 4t.. | 16+4t..) */
+            uint32_t cr_l[2][2][4], sq_l[2][4][4], skip_dot[2][2];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    uint32_t dot = 0;
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        uint32_t in_cr[4], in_sq[4];
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) {
+                            const int o = 8 * t + 4 * cc + nt;
+                            const int x = static_cast<int>(static_cast<uint32_t>(c[mt][nt][hrow * 2 + cc] >> 2)
+                                                           + static_cast<uint32_t>(__ldg(net.l1_b + b * SP_L2_SIZE + o)));
+                            const int cr = min(max(x, 0), 4096);
+                            int sq = static_cast<int>(static_cast<uint32_t>(x) * static_cast<uint32_t>(x)); /* wraps BEFORE the min */
+                            sq = min(sq, 16777216);
+                            dot += static_cast<uint32_t>(cr << 6) * static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + o))
+                                 + static_cast<uint32_t>(sq >> 6) * static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + SP_L2_SIZE + o));
+                            in_cr[nt] = static_cast<uint32_t>(cr);       /* (cr << 6) >> 6: at most 0x1000 */
+                            in_sq[nt] = static_cast<uint32_t>(sq >> 12); /* (sq >> 6) >> 6, arithmetic */
+                        }
+                        /* 4 x 4 byte transposes: word `limb` = byte `limb` of the four values */
+                        {
+                            const uint32_t lo01 = __byte_perm(in_cr[0], in_cr[1], 0x5140), lo23 = __byte_perm(in_cr[2], in_cr[3], 0x5140);
+                            cr_l[mt][0][hrow + 2 * cc] = __byte_perm(lo01, lo23, 0x5410);
+                            cr_l[mt][1][hrow + 2 * cc] = __byte_perm(lo01, lo23, 0x7632);
+                        }
+                        {
+                            const uint32_t lo01 = __byte_perm(in_sq[0], in_sq[1], 0x5140), lo23 = __byte_perm(in_sq[2], in_sq[3], 0x5140);
+                            const uint32_t hi01 = __byte_perm(in_sq[0], in_sq[1], 0x7362), hi23 = __byte_perm(in_sq[2], in_sq[3], 0x7362);
+                            sq_l[mt][0][hrow + 2 * cc] = __byte_perm(lo01, lo23, 0x5410);
+                            sq_l[mt][1][hrow + 2 * cc] = __byte_perm(lo01, lo23, 0x7632);
+                            sq_l[mt][2][hrow + 2 * cc] = __byte_perm(hi01, hi23, 0x5410);
+                            sq_l[mt][3][hrow + 2 * cc] = __byte_perm(hi01, hi23, 0x7632);
+                        }
+                    }
+                    dot += __shfl_xor_sync(kFull, dot, 1);
+                    dot += __shfl_xor_sync(kFull, dot, 2);
+                    skip_dot[mt][hrow] = dot;
+                }
+
+            /* ---- L2 (multilayer.h:261-343) by Horner over the limb weight; lane (g, t) ends up with outputs
+             * 8 nt + 2t, + 1 of rows g and g + 8 */
+            int acc[2][8][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[mt][nt][k] = 0;
+            const uint2* w2 = sh.w2 + lane;
+#pragma unroll
+            for (int shift = 3; shift >= 0; --shift) {
+                if (shift < 3) {
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) acc[mt][nt][k] = static_cast<int>(static_cast<uint32_t>(acc[mt][nt][k]) << 8);
+                }
+#pragma unroll
+                for (int i = 0; i <= shift; ++i) { /* input limb i with weight limb shift - i */
+                    const int j = shift - i;
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+                        if (i < 2) {
+                            const uint2 wf = w2[((j * 8 + nt) * 2 + 0) * 32];
+#pragma unroll
+                            for (int mt = 0; mt < 2; ++mt)
+                                mma_u8u8(acc[mt][nt], cr_l[mt][i][0], cr_l[mt][i][1], cr_l[mt][i][2], cr_l[mt][i][3], wf.x, wf.y);
+                        }
+                        const uint2 wf = w2[((j * 8 + nt) * 2 + 1) * 32];
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+                            mma_u8u8(acc[mt][nt], sq_l[mt][i][0], sq_l[mt][i][1], sq_l[mt][i][2], sq_l[mt][i][3], wf.x, wf.y);
+                    }
+                }
+            }
+
+            /* ---- L3 + scale, multilayer.h:345-447, 484-489 */
+            uint32_t dot[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const uint32_t b2a = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + nt * 8 + 2 * t));
+                const uint32_t b2b = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + nt * 8 + 2 * t + 1));
+                const uint32_t w3a = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + nt * 8 + 2 * t));
+                const uint32_t w3b = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + nt * 8 + 2 * t + 1));
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int hrow = 0; hrow < 2; ++hrow) {
+                        const int va = static_cast<int>(static_cast<uint32_t>(acc[mt][nt][2 * hrow]) + b2a);
+                        const int vb = static_cast<int>(static_cast<uint32_t>(acc[mt][nt][2 * hrow + 1]) + b2b);
+                        dot[mt][hrow] += static_cast<uint32_t>(min(max(va, 0), 262144)) * w3a + static_cast<uint32_t>(min(max(vb, 0), 262144)) * w3b;
+                    }
+            }
+            const uint32_t bias3 = static_cast<uint32_t>(__ldg(net.l3_b + b));
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    uint32_t d = dot[mt][hrow];
+                    d += __shfl_xor_sync(kFull, d, 1);
+                    d += __shfl_xor_sync(kFull, d, 2);
+                    const int32_t l3 = static_cast<int32_t>(d + skip_dot[mt][hrow] + bias3);
+                    /* the final division truncates toward zero */
+                    if (t == 0 && row_id[mt][hrow] != kHeadNoRow) out[row_id[mt][hrow]] = static_cast<int32_t>(static_cast<int64_t>(l3) * 400 / 16777216);
+                }
+        }
+        cur = seg_end;
+    }
+}
+
 /* ------------------------------------------------------------------ eval post-processing */
 
 /* adjustStatic + adjustEval, src/eval/eval.cpp:25-67.  All arithmetic is the reference's: int32, C++
@@ -1505,21 +1790,34 @@ void launch_slot_activate(
     slot_activate_kernel<<<grid_for(n, kWarpsPerCta, sm_count, 4), kThreads, 0, stream>>>(slots, slot_ids, stm, n, act, bucket, status);
 }
 
+/* SP_NNUE_HEAD=tiles selects the earlier head_kernel (A/B measurements); default is head_stream_kernel. */
+static bool head_uses_tiles() {
+    static const bool tiles = [] {
+        const char* v = std::getenv("SP_NNUE_HEAD");
+        return v && std::strcmp(v, "tiles") == 0;
+    }();
+    return tiles;
+}
+
 void launch_head(
     const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, const uint32_t* range, HeadSort sort,
     int sm_count, cudaStream_t stream, uint32_t range_len) {
     if (!n) return;
-    const size_t slots = std::min(sort.capacity, n + 16 * SP_OUTPUT_BUCKETS); /* n bounds the rows of this launch */
+    const size_t slots = std::min(sort.capacity, n + kHeadGroupPad * SP_OUTPUT_BUCKETS); /* n bounds the rows of this launch */
     cudaMemsetAsync(sort.counters, 0, kHeadSortCounters * sizeof(uint32_t), stream);
-    cudaMemsetAsync(sort.order, 0xFF, slots * sizeof(uint32_t), stream);
     const unsigned sort_grid = static_cast<unsigned>(std::min<size_t>((n + 1023) / 1024, static_cast<size_t>(sm_count) * 4));
     head_hist_kernel<<<sort_grid, 256, 0, stream>>>(bucket, n, range, range_len, sort);
-    head_scan_kernel<<<1, 1, 0, stream>>>(sort);
     head_scatter_kernel<<<sort_grid, 256, 0, stream>>>(bucket, n, range, range_len, sort, out);
     /* opt in to > 48 KB of dynamic shared memory (a per-device attribute: set it on every launch) */
-    cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadShared)));
-    const unsigned grid = static_cast<unsigned>((slots + kHeadRows - 1) / kHeadRows);
-    head_kernel<<<grid, kHeadWarps * 32, sizeof(HeadShared), stream>>>(net, act, bucket, out, sort);
+    if (head_uses_tiles()) {
+        cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadShared)));
+        const unsigned grid = static_cast<unsigned>((slots + kHeadRows - 1) / kHeadRows);
+        head_kernel<<<grid, kHeadWarps * 32, sizeof(HeadShared), stream>>>(net, act, bucket, out, sort);
+    } else {
+        cudaFuncSetAttribute(head_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadStreamShared)));
+        const unsigned grid = static_cast<unsigned>(std::min<size_t>((slots + kTileRows - 1) / kTileRows, static_cast<size_t>(sm_count)));
+        head_stream_kernel<<<grid, kStreamThreads, sizeof(HeadStreamShared), stream>>>(net, act, out, sort);
+    }
 }
 
 void launch_adjust(

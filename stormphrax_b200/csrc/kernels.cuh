@@ -30,6 +30,7 @@ struct DeviceNet {
     const int32_t* l1_b;
     const int32_t* l2_w; /* [8][64][64] */
     const uint32_t* l2_limbs; /* [8][4 limbs][8 n-tiles][16 k-quads][8]: byte limbs of l2_w as IMMA B fragments (l2_limb_index) */
+    const uint32_t* l2_frags; /* [8][4 limbs][8 n-tiles][2 k-halves][32 lanes][2]: the same limbs for head_stream_kernel (l2_fragment_index) */
     const int32_t* l2_b;
     const int32_t* l3_w; /* [8][64] */
     const int32_t* l3_b;
@@ -69,6 +70,14 @@ inline int lane_order_element(int k, int lane, int e) {
  * the L2 weights W2[k][o] for k = 4 kq .. 4 kq + 3 (one byte each, k ascending).  Within an n-tile the 32
  * lanes (k-quad t, column g) of one IMMA read 32 consecutive words: no bank conflicts. */
 inline int l2_limb_index(int limb, int kq, int o) { return ((limb * 8 + (o >> 3)) * 16 + kq) * 8 + (o & 7); }
+
+/* The same limbs in the order head_stream_kernel wants them.  Its L2 contraction visits the inputs in the
+ * order in which the L1 IMMAs leave their outputs in a lane: lane (g, t) of the warp holds outputs
+ * 8t .. 8t + 7 of its rows, so k-slot 4t + m of a 32-wide k-half is input 8t + m and k-slot 16 + 4t + m is
+ * input 8t + 4 + m (m = 0..3).  Word index, inside one bucket's 4096-word block, of the B-fragment register
+ * `reg` (0: k-slots 4t.., 1: k-slots 16 + 4t..) of lane `lane` for (limb, n-tile nt, k-half ks); byte m of
+ * that word is limb `limb` of W2[32 ks + 8t + 4 reg + m][8 nt + g]. */
+inline int l2_fragment_index(int limb, int nt, int ks, int lane, int reg) { return ((((limb * 8 + nt) * 2 + ks) * 32) + lane) * 2 + reg; }
 
 /* boards[i] -> act[i][1024], bucket[i]; every position rebuilt from scratch */
 void launch_ft_full(
@@ -123,11 +132,12 @@ void launch_slot_activate(
 /* Scratch of the dense head: the launch's positions grouped by output bucket (counting sort), so that
  * every CTA works on rows of one bucket with that bucket's weights staged in shared memory once. */
 struct HeadSort {
-    uint32_t* order;    /* [capacity]: position indices grouped by bucket, each group padded to 16 with kHeadNoRow */
+    uint32_t* order;    /* [capacity]: position indices grouped by bucket, each group padded to kHeadGroupPad with kHeadNoRow */
     uint32_t* counters; /* [0..7] rows per bucket, [8..15] scatter cursors, [16..24] group starts (24 = padded total) */
-    size_t capacity;    /* entries in `order`: at least n + 16 * 8 */
+    size_t capacity;    /* entries in `order`: at least n + kHeadGroupPad * 8 */
 };
 constexpr uint32_t kHeadNoRow = 0xFFFFFFFFu;
+constexpr uint32_t kHeadGroupPad = 32; /* rows of a head tile: groups are padded to whole tiles */
 constexpr int kHeadSortCounters = 32;
 
 /* act[i], bucket[i] -> out[i] : L1 (int8 IMMA) + L2 (byte-limb IMMA) + L3 + scale.  bucket[i] > 7 marks

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "sp_nnue.h")).read()
-    declared = set(re.findall(r"\b(sp_(?:nnue|host)_[a-z_0-9]+)\s*\(", header))
+    declared = set(re.findall(r"\b(sp_(?:nnue|host|selfplay)_[a-z_0-9]+)\s*\(", header))
     assert declared, "no declarations found"
     L = api.lib()
     for name in sorted(declared):

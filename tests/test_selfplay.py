@@ -1,0 +1,159 @@
+"""Batched self-play driver (csrc/host/selfplay.h, sp_selfplay_run): SURVEY.md section 8 f3/f4.
+
+CPU: the driver's host logic (resumable search == recursive search, scheduler protocol, viriformat
+records) with a stand-in evaluator that exists in the test only.
+GPU: the real thing through the C-ABI -- every recorded score must be reproduced by re-searching the
+recorded position with the CPU oracle as the evaluator (tests only), which pins every one of the
+millions of batched device evaluations behind those scores to the reference's arithmetic."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from stormphrax_b200 import api, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "stormphrax_b200", "csrc", "host")
+
+
+def test_selfplay_host_logic(tmp_path):
+    exe = str(tmp_path / "test_selfplay_host")
+    subprocess.run(
+        ["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_selfplay_host.cpp"),
+         os.path.join(HOST, "position.cpp")],
+        check=True,
+    )
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    sys.stderr.write(r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout + r.stderr[-2000:]
+    assert "0 failures" in r.stdout
+
+
+def test_viriformat_move_encoding():
+    """from | to << 6 | promo << 12 | type flags (viriformat.cpp:33-49) against hand-built moves."""
+    b = api.board_from_fen("r3k2r/1P6/8/3pP3/8/8/8/R3K2R w KQkq d6 0 1")
+    moves = api.legal_moves(b)
+    by_kind = {}
+    for m in moves:
+        by_kind.setdefault(int(m) & 3, []).append(int(m))
+    assert set(by_kind) == {0, 1, 2, 3}
+    for m in moves:
+        m = int(m)
+        frm, to, kind = m >> 10, (m >> 4) & 63, m & 3
+        viri = frm | to << 6 | ((m >> 2) & 3 if kind == 1 else 0) << 12 | [0x0000, 0xC000, 0x8000, 0x4000][kind]
+        assert api.viri_to_move(b, viri) == m
+
+
+def _research(oracle, board, depth, nodes_per_move):
+    """The stand-in search of selfplay.h, recursively, with the CPU oracle as the static evaluator."""
+    MATE, WIN = 32766, 25000
+    state = {"nodes": 0, "best": 0, "prev": 0}
+
+    def order_key(b, m, root):
+        m = int(m)
+        frm, to, kind = m >> 10, (m >> 4) & 63, m & 3
+        mailbox = oracle_mailbox(b)
+        victim = 0 if kind == 3 else (12 if kind == 2 else mailbox[to])
+        k = 0
+        if victim != 12:
+            k = 16 + 2 * (victim >> 1) - (1 if (mailbox[frm] >> 1) > (victim >> 1) else 0)
+        if kind == 1:
+            k += 8
+        if root and m == state["prev"]:
+            k = 1000
+        return k
+
+    def search(b, depth, alpha, beta, ply):
+        state["nodes"] += 1
+        moves = [int(m) for m in api.legal_moves(b)]
+        in_check = is_check(b)
+        if not moves:
+            return (-MATE + ply) if in_check else 0
+        if ply > 0 and int(b["halfmove"]) >= 100:
+            return 0
+        if in_check and depth == 0 and ply + 1 < 24:
+            depth = 1
+        if not in_check or depth == 0:
+            ev = int(oracle.eval_once(np.array([b], dtype=api.BOARD_DTYPE))[0])
+            ev = max(-WIN + 1, min(WIN - 1, ev))
+            if depth == 0:
+                return ev
+            if ply > 0 and depth <= 2 and ev - 120 * depth >= beta:
+                return ev
+        moves.sort(key=lambda m: -order_key(b, m, ply == 0))  # stable, like std::stable_sort
+        best = -MATE
+        for m in moves:
+            if alpha >= beta:
+                break
+            v = -search(api.apply_move(b, m)[0], depth - 1, -beta, -alpha, ply + 1)
+            if v > best:
+                best = v
+                if ply == 0:
+                    state["best"] = m
+            alpha = max(alpha, v)
+        return best
+
+    score = 0
+    d = 1
+    while True:
+        state["best"] = 0
+        score = search(board, d, -MATE, MATE, 0)
+        state["prev"] = state["best"]
+        if not (d < depth and state["nodes"] < nodes_per_move and abs(score) <= 30000):
+            break
+        d += 1
+    return score, state["prev"]
+
+
+def oracle_mailbox(b):
+    """piece codes (type << 1 | colour, 12 = none) per square from a packed record"""
+    box = [12] * 64
+    occ = int(b["occupancy"])
+    i = 0
+    for sq in range(64):
+        if occ >> sq & 1:
+            nib = (int(b["pieces"][i // 2]) >> (4 * (i & 1))) & 15
+            t = nib & 7
+            t = 3 if t == 6 else t
+            box[sq] = t << 1 | (0 if nib & 8 else 1)
+            i += 1
+    return box
+
+
+def is_check(b):
+    return api.in_check(b)
+
+
+@pytest.mark.gpu
+def test_selfplay_device_records_replay_and_scores_match_oracle(net, c_oracle):
+    data, stats = api.selfplay(net.image, 0, concurrency=256, total_games=320, threads=2, depth=2, nodes_per_move=200, max_plies=60, seed=11)
+    games = api.parse_viriformat(data)
+    assert len(games) == stats["games"] == 320
+    assert sum(len(g[1]) for g in games) == stats["positions"]
+    assert stats["evals"] / stats["batches"] > 64, stats  # leaves really are coalesced
+    rng = np.random.default_rng(5)
+    checked = 0
+    for start, moves, scores in games:
+        assert int(start["wdl"]) in (0, 1, 2)
+        b = start.copy()
+        b["wdl"] = 0
+        for i, (vm, sc) in enumerate(zip(moves, scores)):
+            m = api.viri_to_move(b, int(vm))  # raises if the recorded move is not legal here
+            if rng.random() < 0.02 and checked < 40:
+                score, best = _research(c_oracle, b, 2, 200)
+                white = score if not (int(b["stm_ep"]) & 0x80) else -score
+                assert best == m, (api.board_to_fen(b), hex(best), hex(m))
+                if not (i == len(moves) - 1 and sc == 0):
+                    assert int(sc) == (0 if abs(white) <= 2 else white), (api.board_to_fen(b), int(sc), white)
+                checked += 1
+            b = api.apply_move(b, m)[0]
+    assert checked >= 20
+
+
+@pytest.mark.gpu
+def test_selfplay_is_deterministic_and_thread_count_only_reorders(net):
+    a, sa = api.selfplay(net.image, 0, concurrency=64, total_games=64, threads=1, depth=2, nodes_per_move=100, max_plies=40, seed=3)
+    b, sb = api.selfplay(net.image, 0, concurrency=64, total_games=64, threads=1, depth=2, nodes_per_move=100, max_plies=40, seed=3)
+    assert np.array_equal(a, b) and sa == sb

@@ -25,11 +25,12 @@ def main():
     rand = torch.randint(0, 128, (n_max * 1024,), dtype=torch.uint8, device="cuda")
     peak, _ = measured_peak_hbm()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    print("# Round 1 -- dense head in isolation (BASELINE config 4), 1 x B200\n")
+    print(f"# Round 1 -- dense head in isolation (BASELINE config 4), 1 x B200, SP_NNUE_HEAD={os.environ.get('SP_NNUE_HEAD', 'stream')}\n")
     print("`sp_nnue_forward_device`: u8[M][1024] activations + u8[M] buckets -> i32[M]; L2 flushed before every timed call;")
     print(f"HBM fraction = (1024 + 1 + 4) B/position against the measured {peak:.0f} GB/s; int8 TOP/s counts 2 x 1024 x 32 op/position.\n")
     print("| M | activations | us | Mpos/s | int8 TOP/s | GB/s | HBM frac |\n|---:|---|---:|---:|---:|---:|---:|")
-    for logm in range(10, 21):
+    logms = [int(x) for x in os.environ["SWEEP_LOGM"].split(",")] if os.environ.get("SWEEP_LOGM") else range(10, 21)
+    for logm in logms:
         m = 1 << logm
         for name, src in (("real FT output", real), ("uniform 0..127", rand)):
             for _ in range(3): ctx.forward_device(src, d_bucket, m, d_out, s)
