@@ -215,6 +215,14 @@ int sp_selfplay_run(
     const void* net_image, size_t len, int device, const SpSelfplayParams* params, SpSelfplayStats* stats, uint8_t* out,
     size_t out_capacity, size_t* out_len);
 
+/* One game as a viriformat record through the driver's writer (src/datagen/viriformat.cpp:27-63): returns
+ * the bytes written or -1.  outcome: 0 white loss, 1 draw, 2 white win (src/datagen/common.h:24-28). */
+long sp_host_viriformat(
+    const SpPackedBoard* start, const SpMove* moves, const int16_t* scores, uint32_t n, int outcome, uint8_t* out, size_t cap);
+/* wdl::normalizeScore<false>(score, pos.classicalMaterial()) as the driver's adjudication uses it
+ * (src/wdl.cpp:28-80, src/position.h:515-523). */
+int sp_host_normalize_score(const SpPackedBoard* board, int32_t score, int32_t* material, int32_t* normalized);
+
 /* ---------------------------------------------------------------- host utilities (no GPU)
  * Workload generation and CPU execution of the shared feature code, for tests and benchmarks. */
 /* Random legal playouts from the standard start position: game g is seeded from (seed, g); all

@@ -87,6 +87,9 @@ class Reference:
         L.spref_apply_move.argtypes = [_vp, C.c_uint16, _vp]
         L.spref_board_from_fen.argtypes = [C.c_char_p, _vp]
         L.spref_adjusted_eval.argtypes = [_vp, C.c_size_t, _vp, _vp, _vp, _vp]
+        L.spref_viriformat.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_int, _vp, C.c_size_t]
+        L.spref_viriformat.restype = C.c_long
+        L.spref_normalize_score.argtypes = [_vp, C.c_int32, _vp, _vp]
         self._net = None
 
     @staticmethod
@@ -194,6 +197,25 @@ class Reference:
         if rc:
             raise RuntimeError("spref_apply_move failed")
         return out
+
+    def viriformat(self, start: np.ndarray, moves, scores, outcome: int) -> np.ndarray:
+        """The reference's own Viriformat writer (src/datagen/viriformat.cpp) on one game."""
+        start = np.ascontiguousarray(start, dtype=BOARD_DTYPE).reshape(1)
+        moves = np.ascontiguousarray(moves, dtype=np.uint16)
+        scores = np.ascontiguousarray(scores, dtype=np.int16)
+        out = np.empty(32 + 4 * (len(moves) + 1), dtype=np.uint8)
+        n = self.lib.spref_viriformat(_ptr(start), _ptr(moves), _ptr(scores), len(moves), outcome, _ptr(out), out.size)
+        if n < 0:
+            raise RuntimeError("spref_viriformat failed")
+        return out[:n]
+
+    def normalize_score(self, board: np.ndarray, score: int):
+        """(pos.classicalMaterial(), wdl::normalizeScore<false>(score, material))"""
+        board = np.ascontiguousarray(board, dtype=BOARD_DTYPE).reshape(1)
+        material, norm = C.c_int32(), C.c_int32()
+        if self.lib.spref_normalize_score(_ptr(board), int(score), C.byref(material), C.byref(norm)):
+            raise RuntimeError("spref_normalize_score failed")
+        return material.value, norm.value
 
     def board_from_fen(self, fen: str) -> np.ndarray:
         out = np.zeros(1, dtype=BOARD_DTYPE)

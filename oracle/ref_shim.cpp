@@ -19,11 +19,13 @@
 #include <atomic>
 #include <chrono>
 #include <cstring>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "attacks/attacks.h"
+#include "datagen/viriformat.h"
 #include "eval/eval.h"
 #include "eval/header.h"
 #include "eval/nnue.h"
@@ -36,6 +38,7 @@
 #include "position.h"
 #include "util/align.h"
 #include "util/rng.h"
+#include "wdl.h"
 
 #include "../include/sp_types.h"
 
@@ -550,6 +553,43 @@ int spref_board_from_fen(const char* fen, SpPackedBoard* out) {
         return 1;
     }
     *out = pack(*pos);
+    return 0;
+}
+
+// One game through the reference's own Viriformat writer (src/datagen/viriformat.cpp:27-63): start(),
+// push() per (move, score), writeAllWithOutcome().  Returns the bytes written, or -1.
+long spref_viriformat(
+    const SpPackedBoard* start, const uint16_t* moves, const int16_t* scores, uint32_t n, int outcome, uint8_t* out, size_t cap
+) {
+    opts::mutableOpts().chess960 = true;
+    Position pos;
+    if (!toPosition(*start, pos)) {
+        return -1;
+    }
+    datagen::Viriformat game{};
+    game.start(pos);
+    for (uint32_t i = 0; i < n; ++i) {
+        game.push(false, moveFromRaw(moves[i]), scores[i]);
+    }
+    std::ostringstream stream{std::ios::binary};
+    game.writeAllWithOutcome(stream, static_cast<datagen::Outcome>(outcome));
+    const std::string bytes = stream.str();
+    if (bytes.size() > cap) {
+        return -1;
+    }
+    std::memcpy(out, bytes.data(), bytes.size());
+    return static_cast<long>(bytes.size());
+}
+
+// wdl::normalizeScore<false>(score, pos.classicalMaterial()) (src/wdl.cpp:52-75, src/position.h:515-523)
+int spref_normalize_score(const SpPackedBoard* board, int32_t score, int32_t* material, int32_t* normalized) {
+    opts::mutableOpts().chess960 = true;
+    Position pos;
+    if (!toPosition(*board, pos)) {
+        return 1;
+    }
+    *material = pos.classicalMaterial();
+    *normalized = wdl::normalizeScore<false>(score, *material);
     return 0;
 }
 

@@ -75,6 +75,8 @@ SIGNATURES = {
     "sp_host_features": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "sp_host_feature_delta": (C.c_int, [_vp, _vp, C.c_int] + [_vp] * 8),
     "sp_selfplay_run": (C.c_int, [_vp, _sz, C.c_int, _vp, _vp, _vp, _sz, _vp]),
+    "sp_host_viriformat": (C.c_long, [_vp, _vp, _vp, C.c_uint32, C.c_int, _vp, _sz]),
+    "sp_host_normalize_score": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
 }
 
 
@@ -447,3 +449,24 @@ def viri_to_move(board, viri: int) -> int:
     if want not in moves:
         raise ValueError(f"viriformat move {viri:#06x} is not legal in {board_to_fen(board)}")
     return want
+
+
+def viriformat(start, moves, scores, outcome: int) -> np.ndarray:
+    """One game -> viriformat bytes through the driver's writer (sp_host_viriformat)."""
+    start = _boards(start).reshape(1)
+    moves = np.ascontiguousarray(moves, dtype=np.uint16)
+    scores = np.ascontiguousarray(scores, dtype=np.int16)
+    out = np.empty(32 + 4 * (len(moves) + 1), dtype=np.uint8)
+    n = lib().sp_host_viriformat(start.ctypes.data, moves.ctypes.data, scores.ctypes.data, len(moves), outcome, out.ctypes.data, out.size)
+    if n < 0:
+        raise ValueError("sp_host_viriformat failed")
+    return out[:n]
+
+
+def normalize_score(board, score: int):
+    """(classical material, wdl-normalised score) of a position (sp_host_normalize_score)."""
+    material, norm = C.c_int32(), C.c_int32()
+    rc = lib().sp_host_normalize_score(_boards(board).ctypes.data, int(score), C.byref(material), C.byref(norm))
+    if rc:
+        raise NnueError(rc, "bad board")
+    return material.value, norm.value

@@ -58,3 +58,26 @@ extern "C" int sp_selfplay_run(
     for (SpNnue* ctx : contexts) sp_nnue_destroy(ctx);
     return rc;
 }
+
+/* ---- the record writer and the score normalisation on their own (parity tests against the reference) */
+extern "C" long sp_host_viriformat(
+    const SpPackedBoard* start, const SpMove* moves, const int16_t* scores, uint32_t n, int outcome, uint8_t* out, size_t cap) {
+    Position pos;
+    if (!start || !out || outcome < 0 || outcome > 2 || !Position::fromPacked(*start, pos)) return -1;
+    selfplay::ViriGame game;
+    game.start(pos);
+    for (uint32_t i = 0; i < n; ++i) game.push(Move{moves[i]}, scores[i]);
+    std::vector<uint8_t> bytes;
+    game.writeAllWithOutcome(bytes, static_cast<selfplay::Outcome>(outcome));
+    if (bytes.size() > cap) return -1;
+    std::memcpy(out, bytes.data(), bytes.size());
+    return static_cast<long>(bytes.size());
+}
+
+extern "C" int sp_host_normalize_score(const SpPackedBoard* board, int32_t score, int32_t* material, int32_t* normalized) {
+    Position pos;
+    if (!board || !material || !normalized || !Position::fromPacked(*board, pos)) return SP_ERR_BAD_BOARD;
+    *material = selfplay::classicalMaterial(pos);
+    *normalized = selfplay::normalizeScore(score, *material);
+    return SP_OK;
+}

@@ -47,7 +47,7 @@ constexpr i32 kScoreMate = 32766;  /* src/core.h:706 */
 constexpr i32 kScoreTbWin = 30000; /* src/core.h:707 */
 constexpr int kMaxPly = 24;        /* search stack depth of the stand-in search (depth + extensions) */
 
-inline bool isDecisive(i32 score) { return std::abs(score) > kScoreTbWin; } /* core.h:734-736 */
+inline bool isDecisive(i32 score) { return std::abs(score) > eval::kScoreWin; } /* core.h:722-724 */
 
 /* datagen.cpp:72-90 */
 constexpr i32 kWinAdjMinScore = 1250;
@@ -64,6 +64,9 @@ inline int classicalMaterial(const Position& pos) {
     return __builtin_popcountll(pos.bbType(kPawn)) + 3 * __builtin_popcountll(pos.bbType(kKnight))
          + 3 * __builtin_popcountll(pos.bbType(kBishop)) + 5 * __builtin_popcountll(pos.bbType(kRook))
          + 9 * __builtin_popcountll(pos.bbType(kQueen));
+}
+inline uint32_t plyFromStartpos(const Position& pos) { /* src/position.h:511-513 */
+    return static_cast<uint32_t>(pos.fullmove() * 2 - (pos.stm() == kWhite ? 1 : 0) - 1);
 }
 inline i32 normalizeScore(i32 score, int material) {
     if (score == 0 || isDecisive(score)) return score;
@@ -332,7 +335,7 @@ private:
                 ++m_winPlies, m_lossPlies = 0, m_drawPlies = 0;
             } else if (norm < -kWinAdjMinScore) {
                 m_winPlies = 0, ++m_lossPlies, m_drawPlies = 0;
-            } else if (static_cast<uint32_t>(m_pos.fullmove() * 2) >= kDrawAdjMinPlies && std::abs(norm) < kDrawAdjMaxScore) {
+            } else if (plyFromStartpos(m_pos) >= kDrawAdjMinPlies && std::abs(norm) < kDrawAdjMaxScore) {
                 m_winPlies = 0, m_lossPlies = 0, ++m_drawPlies;
             } else {
                 m_winPlies = m_lossPlies = m_drawPlies = 0;

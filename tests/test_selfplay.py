@@ -101,7 +101,7 @@ def _research(oracle, board, depth, nodes_per_move):
         state["best"] = 0
         score = search(board, d, -MATE, MATE, 0)
         state["prev"] = state["best"]
-        if not (d < depth and state["nodes"] < nodes_per_move and abs(score) <= 30000):
+        if not (d < depth and state["nodes"] < nodes_per_move and abs(score) <= 25000):
             break
         d += 1
     return score, state["prev"]
@@ -157,3 +157,39 @@ def test_selfplay_is_deterministic_and_thread_count_only_reorders(net):
     a, sa = api.selfplay(net.image, 0, concurrency=64, total_games=64, threads=1, depth=2, nodes_per_move=100, max_plies=40, seed=3)
     b, sb = api.selfplay(net.image, 0, concurrency=64, total_games=64, threads=1, depth=2, nodes_per_move=100, max_plies=40, seed=3)
     assert np.array_equal(a, b) and sa == sb
+
+
+def _golden_datagen():
+    path = os.path.join(ROOT, "tests", "golden", "datagen_seed42.npz")
+    if not os.path.exists(path):
+        pytest.skip("run tests/golden/make_datagen_golden.py where /root/reference exists")
+    return np.load(path), np.load(os.path.join(ROOT, "tests", "golden", "playouts_seed42.npz"))
+
+
+def test_viriformat_records_match_reference_golden():
+    """Byte-for-byte against records written by the reference's own Viriformat class (standard + DFRC games)."""
+    d, g = _golden_datagen()
+    k = 0
+    for prefix in ("", "dfrc_"):
+        boards, moves, starts, evals = g[prefix + "boards"], g[prefix + "moves"], g[prefix + "starts"], g[prefix + "evals"]
+        for i in range(len(starts) - 1):
+            lo, hi = int(starts[i]), int(starts[i + 1])
+            scores = np.clip(evals[lo : hi - 1], -32768, 32767).astype(np.int16)
+            got = api.viriformat(boards[lo], moves[lo : hi - 1], scores, int(d["viri_outcome"][k]))
+            want = d["viri"][d["viri_off"][k] : d["viri_off"][k + 1]]
+            assert np.array_equal(got, want), f"{prefix}game {i}"
+            # and the parser / move decoder round-trips what was written
+            (start, vm, sc), = api.parse_viriformat(got)
+            assert np.array_equal(sc, scores) and int(start["wdl"]) == int(d["viri_outcome"][k])
+            b = boards[lo]
+            for j, v in enumerate(vm[:12]):
+                assert api.viri_to_move(b, int(v)) == int(moves[lo + j])
+                b = api.apply_move(b, int(moves[lo + j]))[0]
+            k += 1
+    assert k == len(d["viri_outcome"])
+
+
+def test_normalize_score_matches_reference_golden():
+    d, _ = _golden_datagen()
+    for b, s, m, n in zip(d["norm_boards"], d["norm_scores"], d["norm_material"], d["norm_out"]):
+        assert api.normalize_score(b, int(s)) == (int(m), int(n))
