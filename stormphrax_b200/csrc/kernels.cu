@@ -1419,7 +1419,7 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
  *     cp.async.bulk global -> shared, 1 KB = one activation row) into a ring of tiles, completion counted
  *     in bytes on the stage's `full` mbarrier; rows are padded to 1088 B so that the A-fragment reads
  *     (LDS.128, 8 rows x 4 k-chunks per quarter warp) touch every bank group once;
- *   - eight consumer warps take tiles round-robin.  A warp owns its tile's 32 rows (two m16 tiles), so
+ *   - eleven consumer warps take tiles round-robin.  A warp owns its tile's 32 rows (two m16 tiles), so
  *     every weight fragment it fetches from shared memory feeds two IMMAs, and releases the stage
  *     (`empty` mbarrier) as soon as L1 is done -- the epilogue, L2 and L3 run from registers while the
  *     TMA engine refills the stage;
@@ -1451,6 +1451,7 @@ struct HeadStreamShared {
     __align__(16) uint2 w2[kW2Words / 2];  /* l2_fragment_index */
     __align__(8) uint64_t full[kHeadStages];
     uint64_t empty[kHeadStages];
+    uint32_t gen[kHeadStages]; /* tiles consumed so far on each stage */
     uint32_t rows[kHeadStages][kTileRows];
 };
 static_assert(sizeof(HeadStreamShared) <= 227 * 1024, "one CTA per SM");
@@ -1477,7 +1478,7 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
     if (t0 >= t1) return;
 
     if (tid == 0) {
-        for (int i = 0; i < kHeadStages; ++i) mbar_init(&sh.full[i], 1), mbar_init(&sh.empty[i], 1);
+        for (int i = 0; i < kHeadStages; ++i) mbar_init(&sh.full[i], 1), mbar_init(&sh.empty[i], 1), sh.gen[i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1524,6 +1525,10 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
         for (uint32_t tile = cur + warp; tile < seg_end; tile += kHeadConsumers) {
             const uint32_t n = tile - t0;
             const int stage = n % kHeadStages;
+            /* A phase parity tells two consecutive uses of a stage apart, no more, and there are more
+             * consumer warps than stages: before waiting for ITS fill a warp makes sure every earlier tile
+             * of this stage has been consumed (then the barrier can only be in this tile's phase). */
+            while (*reinterpret_cast<volatile uint32_t*>(&sh.gen[stage]) != n / kHeadStages) __nanosleep(64);
             mbar_wait(&sh.full[stage], (n / kHeadStages) & 1);
 
             /* ---- L1: 32 rows x 32 outputs, k = 1024 */
@@ -1563,7 +1568,10 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) row_id[mt][0] = sh.rows[stage][16 * mt + g], row_id[mt][1] = sh.rows[stage][16 * mt + g + 8];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.empty[stage]); /* the TMA engine may refill the stage */
+            if (lane == 0) {
+                *reinterpret_cast<volatile uint32_t*>(&sh.gen[stage]) = n / kHeadStages + 1;
+                mbar_arrive(&sh.empty[stage]); /* the TMA engine may refill the stage */
+            }
 
             /* ---- L1 epilogue (multilayer.h:219-256), skip term of L3, L2 inputs as byte limbs in A-fragment order:
              * register index hrow + 2 cc = a0..a3 of an IMMA (row g | g+8, k-slots 4t.. | 16+4t..) */
