@@ -94,6 +94,14 @@ int sp_nnue_refresh(SpNnue* ctx, const uint32_t* slots, const SpPackedBoard* boa
 int sp_nnue_update(
     SpNnue* ctx, const uint32_t* src_slots, const uint32_t* dst_slots, const SpPackedBoard* after, size_t n);
 int sp_nnue_eval_slots(SpNnue* ctx, const uint32_t* slots, const uint8_t* stm, size_t n, int32_t* out);
+/* One round of a batched driver (many NnueStates, one evaluation each) in ONE submission and one wait:
+ * a refresh group, an update group -- each also evaluated, with the side to move of its boards, when its
+ * output array is given -- and an evaluate-only group (stm as in sp_nnue_eval_slots).  The groups must not
+ * depend on each other (different states).  Any group may be empty. */
+int sp_nnue_batch(
+    SpNnue* ctx, const uint32_t* refresh_slots, const SpPackedBoard* refresh_boards, size_t n_refresh, int32_t* refresh_out,
+    const uint32_t* src_slots, const uint32_t* dst_slots, const SpPackedBoard* after, size_t n_update, int32_t* update_out,
+    const uint32_t* eval_slots, const uint8_t* stm, size_t n_eval, int32_t* eval_out);
 int sp_nnue_update_eval(
     SpNnue* ctx,
     const uint32_t* src_slots,

@@ -55,6 +55,7 @@ SIGNATURES = {
     "sp_nnue_update": (C.c_int, [_vp, _vp, _vp, _vp, _sz]),
     "sp_nnue_eval_slots": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
     "sp_nnue_update_eval": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "sp_nnue_batch": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     "sp_nnue_refresh_device": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
     "sp_nnue_update_eval_device": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "sp_nnue_eval_playouts": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _vp]),

@@ -354,7 +354,7 @@ int eval_full_device(
             SP_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h, ctx->ev_head[buf], 0));
             SP_CUDA(ctx, cudaMemcpyAsync(io->out + off, d_out + off, m * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->d2h));
         }
-        ctx->counters[SP_CTR_LAUNCHES] += 2;
+        ctx->counters[SP_CTR_LAUNCHES] += 1;
     }
     if (overlap) { /* join: later work on `stream` sees every result */
         SP_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux));
@@ -602,7 +602,7 @@ int sp_nnue_forward_device(SpNnue* ctx, const uint8_t* d_act, const uint8_t* d_b
     DeviceGuard guard{ctx->device};
     if (const int rc = ensure_head_sort(ctx, n)) return rc;
     launch_head(ctx->net, d_act, d_bucket, n, d_out, nullptr, ctx->head_sort, ctx->sm_count, pick(ctx, stream));
-    ctx->counters[SP_CTR_LAUNCHES] += 4;
+    ctx->counters[SP_CTR_LAUNCHES] += 3;
     ctx->counters[SP_CTR_EVALS] += n;
     SP_CUDA(ctx, cudaGetLastError());
     return SP_OK;

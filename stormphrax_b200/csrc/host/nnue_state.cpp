@@ -51,13 +51,14 @@ const char* lastError() { return g_error.c_str(); }
 
 void EvalBatch::enqueue(uint32_t srcSlot, uint32_t dstSlot, bool rebuild, const SpPackedBoard& board, Color stm, i32* out) {
     std::lock_guard<std::mutex> lock{m_mutex};
-    if (rebuild) {
-        m_refreshSlots.push_back(dstSlot);
-        m_refreshBoards.push_back(board);
-    } else if (srcSlot != kNoUpdate) {
-        m_src.push_back(srcSlot);
-        m_dst.push_back(dstSlot);
-        m_boards.push_back(board);
+    const bool boardStm = stm == ((board.stm_ep & 0x80) ? kBlack : kWhite);
+    if (rebuild || srcSlot != kNoUpdate) {
+        Group& g = rebuild ? m_refresh : m_update;
+        g.src.push_back(srcSlot);
+        g.dst.push_back(dstSlot);
+        g.boards.push_back(board);
+        g.out.push_back(boardStm ? out : nullptr);
+        if (boardStm || !out) return;
     }
     if (!out) return;
     m_evalSlots.push_back(dstSlot);
@@ -67,16 +68,20 @@ void EvalBatch::enqueue(uint32_t srcSlot, uint32_t dstSlot, bool rebuild, const 
 
 int EvalBatch::flush() {
     std::lock_guard<std::mutex> lock{m_mutex};
-    int rc = SP_OK;
-    if (!m_refreshSlots.empty()) rc = sp_nnue_refresh(m_network, m_refreshSlots.data(), m_refreshBoards.data(), m_refreshSlots.size());
-    if (rc == SP_OK && !m_src.empty()) rc = sp_nnue_update(m_network, m_src.data(), m_dst.data(), m_boards.data(), m_src.size());
-    if (rc == SP_OK && !m_evalSlots.empty()) {
-        m_results.resize(m_evalSlots.size());
-        rc = sp_nnue_eval_slots(m_network, m_evalSlots.data(), m_stm.data(), m_evalSlots.size(), m_results.data());
-        if (rc == SP_OK)
-            for (size_t i = 0; i < m_out.size(); ++i) *m_out[i] = m_results[i];
+    m_refresh.results.resize(m_refresh.dst.size());
+    m_update.results.resize(m_update.dst.size());
+    m_results.resize(m_evalSlots.size());
+    const int rc = sp_nnue_batch(
+        m_network, m_refresh.dst.data(), m_refresh.boards.data(), m_refresh.dst.size(), m_refresh.results.data(), m_update.src.data(),
+        m_update.dst.data(), m_update.boards.data(), m_update.dst.size(), m_update.results.data(), m_evalSlots.data(), m_stm.data(),
+        m_evalSlots.size(), m_results.data());
+    if (rc == SP_OK) {
+        for (Group* g : {&m_refresh, &m_update})
+            for (size_t i = 0; i < g->out.size(); ++i)
+                if (g->out[i]) *g->out[i] = g->results[i];
+        for (size_t i = 0; i < m_out.size(); ++i) *m_out[i] = m_results[i];
     }
-    m_src.clear(), m_dst.clear(), m_boards.clear(), m_refreshSlots.clear(), m_refreshBoards.clear();
+    m_refresh.clear(), m_update.clear();
     m_evalSlots.clear(), m_stm.clear(), m_out.clear();
     if (rc != SP_OK) report("EvalBatch::flush", m_network, rc);
     return rc;

@@ -73,18 +73,27 @@ public:
     /* result is written to *out by flush().  A state may have ONE evaluation pending per flush.
      * out == nullptr: bring dstSlot up to date without evaluating it. */
     void enqueue(uint32_t srcSlot, uint32_t dstSlot, bool rebuild, const SpPackedBoard& board, Color stm, i32* out);
-    [[nodiscard]] size_t pending() const { return m_out.size(); }
+    [[nodiscard]] size_t pending() const { return m_out.size() + m_refresh.out.size() + m_update.out.size(); }
     /* Runs everything queued; returns an SpStatus. */
     int flush();
 
 private:
+    /* an item is refreshed or updated and evaluated in the same launch when the wanted side equals its board's
+     * side to move (the normal case); otherwise (null-move style evaluation, or no update needed) it joins the
+     * evaluate-only group, which runs last */
+    struct Group {
+        std::vector<uint32_t> src, dst;
+        std::vector<SpPackedBoard> boards;
+        std::vector<i32*> out; /* nullptr: result not wanted */
+        std::vector<i32> results;
+        void clear() { src.clear(), dst.clear(), boards.clear(), out.clear(); }
+    };
     SpNnue* m_network;
     std::mutex m_mutex;
-    std::vector<uint32_t> m_src, m_dst, m_refreshSlots;
-    std::vector<SpPackedBoard> m_boards, m_refreshBoards;
+    Group m_refresh, m_update;
+    std::vector<uint32_t> m_evalSlots;
     std::vector<uint8_t> m_stm;
     std::vector<i32*> m_out;
-    std::vector<uint32_t> m_evalSlots;
     std::vector<i32> m_results;
 };
 

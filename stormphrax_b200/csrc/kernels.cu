@@ -1433,14 +1433,18 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
  *     the CReLU half of the inputs is < 2^13, so its limbs 2 and 3 are skipped: 17 instead of 20
  *     contractions of length 32.
  */
+#ifndef SP_HEAD_PRODUCER
+#define SP_HEAD_PRODUCER 1 /* 1: a dedicated producer warp issues the bulk copies; 0: the warp that releases a stage refills it */
+#endif
 #ifndef SP_HEAD_CONSUMERS
-#define SP_HEAD_CONSUMERS 11 /* + the producer = 12 warps, three per scheduler: 168 registers each */
+#define SP_HEAD_CONSUMERS (SP_HEAD_PRODUCER ? 11 : 12) /* 12 warps in all, three per scheduler: 168 registers each */
 #endif
 #ifndef SP_HEAD_STAGES
 #define SP_HEAD_STAGES 5
 #endif
 constexpr int kHeadConsumers = SP_HEAD_CONSUMERS;
-constexpr int kStreamThreads = (kHeadConsumers + 1) * 32;
+constexpr bool kProducerWarp = SP_HEAD_PRODUCER != 0;
+constexpr int kStreamThreads = (kHeadConsumers + (kProducerWarp ? 1 : 0)) * 32;
 constexpr int kTileRows = 32;
 constexpr int kTileRowStride = SP_L1_SIZE + 64;
 constexpr int kHeadStages = SP_HEAD_STAGES;
@@ -1483,20 +1487,29 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
     }
     __syncthreads();
 
-    if (warp == kHeadConsumers) {
-        /* ---- producer: one bulk copy per lane and tile */
-        for (uint32_t n = 0; n < t1 - t0; ++n) {
-            const int stage = n % kHeadStages;
-            mbar_wait(&sh.empty[stage], ((n / kHeadStages) & 1) ^ 1);
-            const uint32_t row = sort.order[static_cast<size_t>(t0 + n) * kTileRows + lane];
-            sh.rows[stage][lane] = row;
-            const bool valid = row != kHeadNoRow;
-            const uint32_t bytes = __popc(__ballot_sync(kFull, valid)) * SP_L1_SIZE;
-            __syncwarp();
-            if (lane == 0) mbar_expect_tx(&sh.full[stage], bytes);
-            if (valid) bulk_copy_g2s(&sh.a[stage][lane * kTileRowStride], act + static_cast<size_t>(row) * SP_L1_SIZE, SP_L1_SIZE, &sh.full[stage]);
+    /* one bulk copy per lane: tile n of this CTA (its rows: `row` per lane) into stage n % kHeadStages */
+    auto issue_fill = [&](uint32_t n, uint32_t row) {
+        const int stage = n % kHeadStages;
+        sh.rows[stage][lane] = row;
+        const bool valid = row != kHeadNoRow;
+        const uint32_t bytes = __popc(__ballot_sync(kFull, valid)) * SP_L1_SIZE;
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(&sh.full[stage], bytes);
+        if (valid) bulk_copy_g2s(&sh.a[stage][lane * kTileRowStride], act + static_cast<size_t>(row) * SP_L1_SIZE, SP_L1_SIZE, &sh.full[stage]);
+    };
+    const uint32_t my_tiles = t1 - t0;
+    if (kProducerWarp) {
+        if (warp == kHeadConsumers) {
+            for (uint32_t n = 0; n < my_tiles; ++n) {
+                mbar_wait(&sh.empty[n % kHeadStages], ((n / kHeadStages) & 1) ^ 1);
+                issue_fill(n, sort.order[static_cast<size_t>(t0 + n) * kTileRows + lane]);
+            }
+            return;
         }
-        return;
+    } else if (warp < kHeadStages && static_cast<uint32_t>(warp) < my_tiles) {
+        /* no producer warp: the first kHeadStages tiles are requested here, every later tile by the warp that
+         * releases its stage (one issuing warp was the bottleneck: ~64 clk per copy, 32 copies per tile) */
+        issue_fill(warp, sort.order[static_cast<size_t>(t0 + warp) * kTileRows + lane]);
     }
 
     /* ---- consumers */
@@ -1529,6 +1542,10 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
              * consumer warps than stages: before waiting for ITS fill a warp makes sure every earlier tile
              * of this stage has been consumed (then the barrier can only be in this tile's phase). */
             while (*reinterpret_cast<volatile uint32_t*>(&sh.gen[stage]) != n / kHeadStages) __nanosleep(64);
+            /* rows of the tile that will follow this one on the stage (requested once L1 is done) */
+            const uint32_t refill = n + kHeadStages;
+            uint32_t refill_row = kHeadNoRow;
+            if (!kProducerWarp && refill < my_tiles) refill_row = sort.order[static_cast<size_t>(t0 + refill) * kTileRows + lane];
             mbar_wait(&sh.full[stage], (n / kHeadStages) & 1);
 
             /* ---- L1: 32 rows x 32 outputs, k = 1024 */
@@ -1568,9 +1585,16 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) row_id[mt][0] = sh.rows[stage][16 * mt + g], row_id[mt][1] = sh.rows[stage][16 * mt + g + 8];
             __syncwarp();
-            if (lane == 0) {
-                *reinterpret_cast<volatile uint32_t*>(&sh.gen[stage]) = n / kHeadStages + 1;
-                mbar_arrive(&sh.empty[stage]); /* the TMA engine may refill the stage */
+            if (kProducerWarp) {
+                if (lane == 0) {
+                    *reinterpret_cast<volatile uint32_t*>(&sh.gen[stage]) = n / kHeadStages + 1;
+                    mbar_arrive(&sh.empty[stage]); /* the TMA engine may refill the stage */
+                }
+            } else {
+                /* order this warp's generic-proxy reads of the stage before the async-proxy writes that refill it */
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh.gen[stage]) = n / kHeadStages + 1;
+                if (refill < my_tiles) issue_fill(refill, refill_row);
             }
 
             /* ---- L1 epilogue (multilayer.h:219-256), skip term of L3, L2 inputs as byte limbs in A-fragment order:

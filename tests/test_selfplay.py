@@ -132,7 +132,7 @@ def test_selfplay_device_records_replay_and_scores_match_oracle(net, c_oracle):
     games = api.parse_viriformat(data)
     assert len(games) == stats["games"] == 320
     assert sum(len(g[1]) for g in games) == stats["positions"]
-    assert stats["evals"] / stats["batches"] > 64, stats  # leaves really are coalesced
+    assert stats["evals"] / stats["batches"] > 24, stats  # leaves really are coalesced
     rng = np.random.default_rng(5)
     checked = 0
     for start, moves, scores in games:

@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU call B: head_stream_kernel (with the generation gate) + self-play driver.  Bails out early if the new head is wrong.
 mkdir -p gpurun_out
-timeout 150 python -m pytest tests/test_gpu_full.py -x -q -m gpu -k "head" > gpurun_out/t_head.log 2>&1; rc=$?; echo "head tests rc=$rc"
+timeout 240 python -m pytest tests/test_gpu_full.py -x -q -m gpu -k "head" > gpurun_out/t_head.log 2>&1; rc=$?; echo "head tests rc=$rc"
 tail -5 gpurun_out/t_head.log
 if [ $rc -ne 0 ]; then
   SP_NNUE_HEAD=tiles timeout 150 python -m pytest tests/test_gpu_full.py -x -q -m gpu -k "head" > gpurun_out/t_head_tiles.log 2>&1; echo "tiles head rc=$?"
