@@ -1196,6 +1196,52 @@ __global__ void head_scatter_kernel(const uint8_t* __restrict__ bucket, size_t n
         }
     }
 }
+/* The same sort for small launches (latency matters there: search-style batches of a few thousand
+ * positions): one block does histogram, group starts, padding and scatter, and needs no zeroed counters. */
+constexpr size_t kHeadSortSmall = 8192;
+__global__ void __launch_bounds__(1024)
+head_sort_small_kernel(const uint8_t* __restrict__ bucket, size_t n, const uint32_t* __restrict__ range, uint32_t range_len, HeadSort sort,
+                       int32_t* __restrict__ out) {
+    __shared__ uint32_t hist[SP_OUTPUT_BUCKETS], cursor[SP_OUTPUT_BUCKETS], start[SP_OUTPUT_BUCKETS + 1];
+    size_t first;
+    head_span(range, range_len, first, n);
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < SP_OUTPUT_BUCKETS) hist[threadIdx.x] = cursor[threadIdx.x] = 0;
+    __syncthreads();
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const int b = bucket[first + i];
+        if (b < SP_OUTPUT_BUCKETS) atomicAdd(&hist[b], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t at = 0;
+        for (int b = 0; b < SP_OUTPUT_BUCKETS; ++b) {
+            start[b] = at;
+            at += (hist[b] + kHeadGroupPad - 1) & ~(kHeadGroupPad - 1);
+        }
+        start[SP_OUTPUT_BUCKETS] = at;
+    }
+    __syncthreads();
+    if (threadIdx.x <= SP_OUTPUT_BUCKETS) sort.counters[16 + threadIdx.x] = start[threadIdx.x];
+    for (uint32_t i = threadIdx.x; i < SP_OUTPUT_BUCKETS * kHeadGroupPad; i += blockDim.x) {
+        const uint32_t b = i / kHeadGroupPad, at = start[b] + hist[b] + i % kHeadGroupPad;
+        if (at < start[b + 1]) sort.order[at] = kHeadNoRow;
+    }
+    const size_t n_round = (n + 31) & ~size_t{31};
+    for (size_t i = threadIdx.x; i < n_round; i += blockDim.x) {
+        const int b = i < n ? bucket[first + i] : 0xFE;
+        const unsigned peers = __match_any_sync(kFull, b);
+        if (b < SP_OUTPUT_BUCKETS) {
+            const int leader = __ffs(peers) - 1;
+            uint32_t slot = 0;
+            if (lane == leader) slot = atomicAdd(&cursor[b], static_cast<uint32_t>(__popc(peers)));
+            slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1));
+            sort.order[start[b] + slot] = static_cast<uint32_t>(first + i);
+        } else if (i < n) {
+            out[first + i] = INT32_MIN; /* rejected board */
+        }
+    }
+}
 constexpr uint32_t kNoRow = kHeadNoRow;
 
 /*
@@ -1434,10 +1480,10 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
  *     contractions of length 32.
  */
 #ifndef SP_HEAD_PRODUCER
-#define SP_HEAD_PRODUCER 1 /* 1: a dedicated producer warp issues the bulk copies; 0: the warp that releases a stage refills it */
+#define SP_HEAD_PRODUCER 0 /* 1: a dedicated producer warp issues the bulk copies; 0: the warp that releases a stage refills it */
 #endif
 #ifndef SP_HEAD_CONSUMERS
-#define SP_HEAD_CONSUMERS (SP_HEAD_PRODUCER ? 11 : 12) /* 12 warps in all, three per scheduler: 168 registers each */
+#define SP_HEAD_CONSUMERS (SP_HEAD_PRODUCER ? 11 : 8) /* 8 warps = two per scheduler at 255 registers (measured best); 12 = three at 168 */
 #endif
 #ifndef SP_HEAD_STAGES
 #define SP_HEAD_STAGES 5
@@ -1468,6 +1514,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kHeadConsumers * 32) : "memory"); }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+/* Requests tile n of the CTA (lane l holds the position index of its row l, or kHeadNoRow) into stage
+ * n % kHeadStages: one 1 KB bulk copy per row.  UBLKCP takes its operands from uniform registers; issued
+ * per lane the compiler serialises the warp in a loop of ~64 clk per copy (measured: the issuing warp
+ * was the kernel's bottleneck).  Broadcasting each row index with a shuffle and letting one elected lane
+ * issue all the copies gives straight-line code whose R2UR latencies overlap. */
+__device__ __noinline__ void head_issue_fill(HeadStreamShared& sh, const uint8_t* __restrict__ act, uint32_t n, uint32_t row, int lane) {
+    const int stage = n % kHeadStages;
+    sh.rows[stage][lane] = row;
+    const uint32_t bytes = __popc(__ballot_sync(kFull, row != kHeadNoRow)) * SP_L1_SIZE;
+    __syncwarp();
+    const bool leader = elect_one();
+    if (leader) mbar_expect_tx(&sh.full[stage], bytes);
+    uint8_t* dst = &sh.a[stage][0];
+#pragma unroll
+    for (int i = 0; i < kTileRows; ++i) {
+        const uint32_t r = __shfl_sync(kFull, row, i);
+        if (r != kHeadNoRow && leader) bulk_copy_g2s(dst + i * kTileRowStride, act + static_cast<size_t>(r) * SP_L1_SIZE, SP_L1_SIZE, &sh.full[stage]);
+    }
+}
+
 __global__ void __launch_bounds__(kStreamThreads, 1)
 head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __restrict__ out, HeadSort sort) {
     extern __shared__ __align__(16) unsigned char head_smem[];
@@ -1487,16 +1559,7 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
     }
     __syncthreads();
 
-    /* one bulk copy per lane: tile n of this CTA (its rows: `row` per lane) into stage n % kHeadStages */
-    auto issue_fill = [&](uint32_t n, uint32_t row) {
-        const int stage = n % kHeadStages;
-        sh.rows[stage][lane] = row;
-        const bool valid = row != kHeadNoRow;
-        const uint32_t bytes = __popc(__ballot_sync(kFull, valid)) * SP_L1_SIZE;
-        __syncwarp();
-        if (lane == 0) mbar_expect_tx(&sh.full[stage], bytes);
-        if (valid) bulk_copy_g2s(&sh.a[stage][lane * kTileRowStride], act + static_cast<size_t>(row) * SP_L1_SIZE, SP_L1_SIZE, &sh.full[stage]);
-    };
+    auto issue_fill = [&](uint32_t n, uint32_t row) { head_issue_fill(sh, act, n, row, lane); };
     const uint32_t my_tiles = t1 - t0;
     if (kProducerWarp) {
         if (warp == kHeadConsumers) {
@@ -1836,10 +1899,14 @@ void launch_head(
     int sm_count, cudaStream_t stream, uint32_t range_len) {
     if (!n) return;
     const size_t slots = std::min(sort.capacity, n + kHeadGroupPad * SP_OUTPUT_BUCKETS); /* n bounds the rows of this launch */
-    cudaMemsetAsync(sort.counters, 0, kHeadSortCounters * sizeof(uint32_t), stream);
-    const unsigned sort_grid = static_cast<unsigned>(std::min<size_t>((n + 1023) / 1024, static_cast<size_t>(sm_count) * 4));
-    head_hist_kernel<<<sort_grid, 256, 0, stream>>>(bucket, n, range, range_len, sort);
-    head_scatter_kernel<<<sort_grid, 256, 0, stream>>>(bucket, n, range, range_len, sort, out);
+    if (n <= kHeadSortSmall) {
+        head_sort_small_kernel<<<1, 1024, 0, stream>>>(bucket, n, range, range_len, sort, out);
+    } else {
+        cudaMemsetAsync(sort.counters, 0, kHeadSortCounters * sizeof(uint32_t), stream);
+        const unsigned sort_grid = static_cast<unsigned>(std::min<size_t>((n + 1023) / 1024, static_cast<size_t>(sm_count) * 4));
+        head_hist_kernel<<<sort_grid, 256, 0, stream>>>(bucket, n, range, range_len, sort);
+        head_scatter_kernel<<<sort_grid, 256, 0, stream>>>(bucket, n, range, range_len, sort, out);
+    }
     /* opt in to > 48 KB of dynamic shared memory (a per-device attribute: set it on every launch) */
     if (head_uses_tiles()) {
         cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadShared)));
