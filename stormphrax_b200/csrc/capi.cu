@@ -409,6 +409,18 @@ static int create_impl(const void* net_image, size_t len, int device, SpNnue** o
     const NetLayout L;
     std::vector<uint8_t> img(L.total);
     build_device_image(bytes + SP_NET_HEADER_BYTES, L, img.data());
+    /* buckets whose L2 weights all fit int16: the streaming head then contracts two weight limbs instead of four */
+    uint32_t l2_narrow_mask = 0;
+    {
+        const int32_t* w2 = reinterpret_cast<const int32_t*>(img.data() + L.l2_w);
+        for (int b = 0; b < SP_OUTPUT_BUCKETS; ++b) {
+            bool narrow = true;
+            for (int i = 0; i < 2 * SP_L2_SIZE * SP_L3_SIZE; ++i) narrow = narrow && w2[b * 2 * SP_L2_SIZE * SP_L3_SIZE + i] >= -32768 && w2[b * 2 * SP_L2_SIZE * SP_L3_SIZE + i] <= 32767;
+            if (narrow) l2_narrow_mask |= 1u << b;
+        }
+        if (const char* env = std::getenv("SP_NNUE_L2_NARROW")) /* 0: always take the general path (tests, A/B) */
+            if (std::atoi(env) == 0) l2_narrow_mask = 0;
+    }
     SP_CUDA(nullptr, cudaMalloc(&ctx->d_net_blob, L.total));
     SP_CUDA(nullptr, cudaMemcpy(ctx->d_net_blob, img.data(), L.total, cudaMemcpyHostToDevice));
     FeatureTables tables;
@@ -448,6 +460,7 @@ static int create_impl(const void* net_image, size_t len, int device, SpNnue** o
     ctx->net.l2_w = reinterpret_cast<const int32_t*>(b + L.l2_w);
     ctx->net.l2_limbs = reinterpret_cast<const uint32_t*>(b + L.l2_limbs);
     ctx->net.l2_frags = reinterpret_cast<const uint32_t*>(b + L.l2_frags);
+    ctx->net.l2_narrow = l2_narrow_mask;
     ctx->net.l2_b = reinterpret_cast<const int32_t*>(b + L.l2_b);
     ctx->net.l3_w = reinterpret_cast<const int32_t*>(b + L.l3_w);
     ctx->net.l3_b = reinterpret_cast<const int32_t*>(b + L.l3_b);

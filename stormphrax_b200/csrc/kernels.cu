@@ -20,6 +20,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -1584,6 +1585,7 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
         for (int i = 1; i < SP_OUTPUT_BUCKETS; ++i)
             if (sort.counters[16 + i] <= cur * kTileRows) b = i;
         const uint32_t seg_end = min(t1, sort.counters[16 + b + 1] / kTileRows);
+        const bool narrow_w2 = (net.l2_narrow >> b) & 1;
 
         consumers_sync(); /* nobody still reads the previous bucket's weights */
         {
@@ -1714,31 +1716,69 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
 #pragma unroll
                     for (int k = 0; k < 4; ++k) acc[mt][nt][k] = 0;
             const uint2* w2 = sh.w2 + lane;
+            auto shl8 = [&]() {
 #pragma unroll
-            for (int shift = 3; shift >= 0; --shift) {
-                if (shift < 3) {
+                for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt)
+                    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[mt][nt][k] = static_cast<int>(static_cast<uint32_t>(acc[mt][nt][k]) << 8);
+            };
+            /* The squared half of the inputs is negative only after a wrapped square (|x| > 46340): without
+             * one in this tile its limbs 2 and 3 are zero like those of the CReLU half. */
+            uint32_t high = 0;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) high |= sq_l[mt][2][r] | sq_l[mt][3][r];
+            const bool wide_inputs = __any_sync(kFull, high != 0);
+            if (narrow_w2 && !wide_inputs) {
+                /* Weights that fit int16 (true of the whole bucket, found at upload) are lo + 256 hi with lo = byte 0
+                 * unsigned and hi = byte 1 SIGNED -- the same stored bytes, read by a u8 x s8 IMMA -- and inputs below
+                 * 2^16 are a0 + 256 a1: in * w = a0 lo + 2^8 (a0 hi + a1 lo) + 2^16 a1 hi, four contractions per
+                 * k-half instead of ten / seven. */
+#pragma unroll
+                for (int level = 2; level >= 0; --level) {
+                    if (level < 2) shl8();
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int j = level - i; /* input limb i with weight limb j */
+                        if (j < 0 || j > 1) continue;
 #pragma unroll
                         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) acc[mt][nt][k] = static_cast<int>(static_cast<uint32_t>(acc[mt][nt][k]) << 8);
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const uint2 wf = w2[((j * 8 + nt) * 2 + ks) * 32];
+#pragma unroll
+                                for (int mt = 0; mt < 2; ++mt) {
+                                    const uint32_t* a = ks == 0 ? cr_l[mt][i] : sq_l[mt][i];
+                                    if (j == 1) mma_u8s8(acc[mt][nt], a[0], a[1], a[2], a[3], wf.x, wf.y);
+                                    else mma_u8u8(acc[mt][nt], a[0], a[1], a[2], a[3], wf.x, wf.y);
+                                }
+                            }
+                    }
                 }
+            } else {
 #pragma unroll
-                for (int i = 0; i <= shift; ++i) { /* input limb i with weight limb shift - i */
-                    const int j = shift - i;
+                for (int shift = 3; shift >= 0; --shift) {
+                    if (shift < 3) shl8();
 #pragma unroll
-                    for (int nt = 0; nt < 8; ++nt) {
-                        if (i < 2) {
-                            const uint2 wf = w2[((j * 8 + nt) * 2 + 0) * 32];
+                    for (int i = 0; i <= shift; ++i) { /* input limb i with weight limb shift - i */
+                        const int j = shift - i;
+                        if (i >= 2 && !wide_inputs) continue; /* warp-uniform */
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) {
+                            if (i < 2) {
+                                const uint2 wf = w2[((j * 8 + nt) * 2 + 0) * 32];
+#pragma unroll
+                                for (int mt = 0; mt < 2; ++mt)
+                                    mma_u8u8(acc[mt][nt], cr_l[mt][i][0], cr_l[mt][i][1], cr_l[mt][i][2], cr_l[mt][i][3], wf.x, wf.y);
+                            }
+                            const uint2 wf = w2[((j * 8 + nt) * 2 + 1) * 32];
 #pragma unroll
                             for (int mt = 0; mt < 2; ++mt)
-                                mma_u8u8(acc[mt][nt], cr_l[mt][i][0], cr_l[mt][i][1], cr_l[mt][i][2], cr_l[mt][i][3], wf.x, wf.y);
+                                mma_u8u8(acc[mt][nt], sq_l[mt][i][0], sq_l[mt][i][1], sq_l[mt][i][2], sq_l[mt][i][3], wf.x, wf.y);
                         }
-                        const uint2 wf = w2[((j * 8 + nt) * 2 + 1) * 32];
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt)
-                            mma_u8u8(acc[mt][nt], sq_l[mt][i][0], sq_l[mt][i][1], sq_l[mt][i][2], sq_l[mt][i][3], wf.x, wf.y);
                     }
                 }
             }
@@ -1907,13 +1947,19 @@ void launch_head(
         head_hist_kernel<<<sort_grid, 256, 0, stream>>>(bucket, n, range, range_len, sort);
         head_scatter_kernel<<<sort_grid, 256, 0, stream>>>(bucket, n, range, range_len, sort, out);
     }
-    /* opt in to > 48 KB of dynamic shared memory (a per-device attribute: set it on every launch) */
-    if (head_uses_tiles()) {
+    /* opt in to > 48 KB of dynamic shared memory: a per-device attribute, set once per device */
+    static std::atomic<uint64_t> configured{0};
+    int device = 0;
+    cudaGetDevice(&device);
+    if (!((configured.load(std::memory_order_relaxed) >> (device & 63)) & 1)) {
         cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadShared)));
+        cudaFuncSetAttribute(head_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadStreamShared)));
+        configured.fetch_or(uint64_t{1} << (device & 63), std::memory_order_relaxed);
+    }
+    if (head_uses_tiles()) {
         const unsigned grid = static_cast<unsigned>((slots + kHeadRows - 1) / kHeadRows);
         head_kernel<<<grid, kHeadWarps * 32, sizeof(HeadShared), stream>>>(net, act, bucket, out, sort);
     } else {
-        cudaFuncSetAttribute(head_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadStreamShared)));
         const unsigned grid = static_cast<unsigned>(std::min<size_t>((slots + kTileRows - 1) / kTileRows, static_cast<size_t>(sm_count)));
         head_stream_kernel<<<grid, kStreamThreads, sizeof(HeadStreamShared), stream>>>(net, act, out, sort);
     }

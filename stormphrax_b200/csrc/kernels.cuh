@@ -35,6 +35,7 @@ struct DeviceNet {
     const int32_t* l3_w; /* [8][64] */
     const int32_t* l3_b;
     const FeatureTables* tables;
+    uint32_t l2_narrow; /* bit b: every L2 weight of bucket b fits int16 (head_stream_kernel then needs 2 weight limbs, not 4) */
 };
 
 struct SlotStore {

@@ -230,3 +230,35 @@ def test_dense_head_large_mixed_buckets(gpu_ctx, c_oracle):
     gpu_ctx.forward_device(_dev(act[perm]), _dev(bucket[perm]), n, d_out, s)
     gpu_ctx.sync(s)
     assert (d_out.cpu().numpy() == got[perm]).all()
+
+
+def test_dense_head_l2_paths(net, stress_net, monkeypatch):
+    """The streaming head picks its L2 form per tile: int16-range weights + inputs below 2^16 (two limbs each),
+    the general four-limb form without the zero input limbs, and the full form after a wrapped square.
+    All three must agree with the oracle: normal net (narrow weights) with FT-range and full-range activations,
+    the same net with the narrow form switched off, and the stress net (full-range weights, wrapping squares)."""
+    import torch
+
+    from oracle.bind import COracle
+
+    rng = np.random.default_rng(17)
+    n = 2500
+    acts = {"ft_range": rng.integers(0, 128, (n, 1024), dtype=np.uint8), "full_range": rng.integers(0, 256, (n, 1024), dtype=np.uint8)}
+    bucket = rng.integers(0, 8, n, dtype=np.uint8)
+    s = _stream()
+    oracle = COracle()
+    try:
+        for network, narrow in ((net, "1"), (net, "0"), (stress_net, "1")):
+            monkeypatch.setenv("SP_NNUE_L2_NARROW", narrow)
+            oracle.load_net(network.image)
+            with api.Nnue(network.image, 0) as ctx:
+                for name, act in acts.items():
+                    d_out = torch.empty(n, dtype=torch.int32, device="cuda")
+                    ctx.forward_device(_dev(act), _dev(bucket), n, d_out, s)
+                    ctx.sync(s)
+                    got = d_out.cpu().numpy()
+                    pick = rng.choice(n, 400, replace=False)
+                    want = np.array([oracle.forward(act[i], int(bucket[i])) for i in pick], dtype=np.int32)
+                    assert (got[pick] == want).all(), (narrow, name)
+    finally:
+        oracle.load_net(net.image)  # the C oracle keeps one global network
