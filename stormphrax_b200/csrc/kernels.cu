@@ -448,6 +448,22 @@ __device__ __forceinline__ uint4 ldg_no_allocate(const uint4* p) {
     return r;
 }
 
+/* The lane's view of a weight table (table + lane).  The compiler re-associates the uniform table pointer out
+ * of it and forms every row address with four instructions (IADD3 + IMAD.X + LEA + LEA.HI.X on lane +
+ * offset).  SP_ROW_ADDR=1 hides the pointer behind an empty asm so that a row address is ONE IMAD.WIDE.U32:
+ * 7 % fewer instructions in the full refresh -- and 6 % SLOWER on the GPU (84.9 vs 90.7 Mpos/s; the wide
+ * multiply sits on the half-rate FMA pipe in front of every load).  Kept as an experiment knob, off. */
+#ifndef SP_ROW_ADDR
+#define SP_ROW_ADDR 0
+#endif
+__device__ __forceinline__ const uint4* lane_view(const uint4* table, int lane) {
+    const uint4* p = table + lane;
+#if SP_ROW_ADDR
+    asm volatile("" : "+l"(p));
+#endif
+    return p;
+}
+
 /* `base` = table + lane; `off` = uint4 offset of the row (a list entry) */
 __device__ __forceinline__ void load_psq_row(const uint4* base, uint32_t off, uint4 (&c)[4]) {
     const uint4* r = base + off;
@@ -491,8 +507,8 @@ __device__ __forceinline__ void add_thr_wide(uint32_t (&s)[8], uint32_t (&o)[8],
 __device__ __forceinline__ void rebuild_perspective(
     const DeviceNet& net, const uint32_t* psq_list, int n_psq, const uint32_t* thr_list, int n_thr, int lane, uint32_t (&v)[16]) {
     static_assert(kPsqGroup == 4 && kThrGroupFull % 4 == 0, "list entries are fetched four at a time");
-    const uint4* psq_base = net.psq + lane;
-    const uint4* thr_base = net.thr + lane;
+    const uint4* psq_base = lane_view(net.psq, lane);
+    const uint4* thr_base = lane_view(net.thr, lane);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = 0;
 #pragma unroll 1
@@ -558,8 +574,8 @@ __device__ __noinline__ void rebuild_perspective_cold(
  * complements are repaid by one constant at the end. */
 __device__ __forceinline__ void update_perspective(const DeviceNet& net, const WarpScratch& ws, int c, int lane, uint32_t (&v)[16]) {
     static_assert(kPsqGroupDelta == 2 && kThrGroupDelta == 2, "list entries are fetched two at a time");
-    const uint4* psq_base = net.psq + lane;
-    const uint4* thr_base = net.thr + lane;
+    const uint4* psq_base = lane_view(net.psq, lane);
+    const uint4* thr_base = lane_view(net.thr, lane);
     const int n_psq = ws.n_psq_delta[c]; /* padded */
     int psq_subs = 0;
 #pragma unroll 1
