@@ -197,6 +197,14 @@ int sp_nnue_profile_read(SpNnue* ctx, double ms[SP_NUM_KERNEL_CLASSES], uint64_t
 /* Debug/test access: accumulators of a slot in LOGICAL order, int16[2][1024] (black, white). */
 int sp_nnue_read_slot(SpNnue* ctx, uint32_t slot, int16_t* out_acc, SpPackedBoard* out_board);
 
+/* sp_nnue_batch with every array on the device (results too), enqueued on `stream` without waiting: the form a
+ * GPU-resident driver uses (sp_selfplay_run_gpu).  Errors found on the device are reported by the next
+ * sp_nnue_sync. */
+int sp_nnue_batch_device(
+    SpNnue* ctx, const uint32_t* d_refresh_slots, const SpPackedBoard* d_refresh_boards, size_t n_refresh, int32_t* d_refresh_out,
+    const uint32_t* d_src_slots, const uint32_t* d_dst_slots, const SpPackedBoard* d_after, size_t n_update, int32_t* d_update_out,
+    const uint32_t* d_eval_slots, const uint8_t* d_stm, size_t n_eval, int32_t* d_eval_out, void* stream);
+
 /* ---------------------------------------------------------------- batched self-play (datagen)
  * Replaces the per-thread game loop of src/datagen/datagen.cpp:96-321 (`datagen::run`, :323-400): random
  * opening plies, search -> applyMove -> NnueState::applyImmediately -> (move, score) until the game is
@@ -220,6 +228,14 @@ typedef struct SpSelfplayStats {
     uint64_t games, positions, nodes, evals, batches, searches;
 } SpSelfplayStats;
 int sp_selfplay_run(
+    const void* net_image, size_t len, int device, const SpSelfplayParams* params, SpSelfplayStats* stats, uint8_t* out,
+    size_t out_capacity, size_t* out_len);
+/* The same games played by a GPU-resident driver: one device thread per game slot runs the search state
+ * machine, the host only submits one sp_nnue_batch_device per round (`threads` is ignored).  Game slot g plays
+ * total_games / concurrency games (+ 1 for the first total_games % concurrency slots) whichever entry point is
+ * used, every (slot, game) has its own random stream, and records come out slot-major: both entry points
+ * produce the same bytes. */
+int sp_selfplay_run_gpu(
     const void* net_image, size_t len, int device, const SpSelfplayParams* params, SpSelfplayStats* stats, uint8_t* out,
     size_t out_capacity, size_t* out_len);
 

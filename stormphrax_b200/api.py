@@ -76,6 +76,8 @@ SIGNATURES = {
     "sp_host_features": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "sp_host_feature_delta": (C.c_int, [_vp, _vp, C.c_int] + [_vp] * 8),
     "sp_selfplay_run": (C.c_int, [_vp, _sz, C.c_int, _vp, _vp, _vp, _sz, _vp]),
+    "sp_selfplay_run_gpu": (C.c_int, [_vp, _sz, C.c_int, _vp, _vp, _vp, _sz, _vp]),
+    "sp_nnue_batch_device": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp]),
     "sp_host_viriformat": (C.c_long, [_vp, _vp, _vp, C.c_uint32, C.c_int, _vp, _sz]),
     "sp_host_normalize_score": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
 }
@@ -413,15 +415,17 @@ class SelfplayStats(C.Structure):
 
 
 def selfplay(net_image, device: int = 0, *, concurrency: int = 1024, total_games: int = 1024, threads: int = 1, depth: int = 3,
-             nodes_per_move: int = 5000, max_plies: int = 300, seed: int = 42, capacity: int | None = None):
-    """Batched self-play on the device (sp_selfplay_run).  Returns (viriformat bytes as uint8 array, stats dict)."""
+             nodes_per_move: int = 5000, max_plies: int = 300, seed: int = 42, capacity: int | None = None, resident: bool = False):
+    """Batched self-play (sp_selfplay_run; resident=True: sp_selfplay_run_gpu, the games' searches run on the device too).
+    Returns (viriformat bytes as uint8 array, stats dict)."""
     img = np.ascontiguousarray(net_image, dtype=np.uint8)
     p = SelfplayParams(concurrency, total_games, threads, depth, nodes_per_move, max_plies, seed)
     st = SelfplayStats()
     cap = capacity if capacity is not None else total_games * (32 + 4 * (max_plies + 2))
     out = np.empty(cap, dtype=np.uint8)
     out_len = C.c_size_t(0)
-    rc = lib().sp_selfplay_run(img.ctypes.data, img.size, device, C.byref(p), C.byref(st), out.ctypes.data, cap, C.byref(out_len))
+    run = lib().sp_selfplay_run_gpu if resident else lib().sp_selfplay_run
+    rc = run(img.ctypes.data, img.size, device, C.byref(p), C.byref(st), out.ctypes.data, cap, C.byref(out_len))
     if rc != SP_OK:
         raise NnueError(rc, (lib().sp_nnue_last_error(None) or b"").decode())
     return out[: out_len.value].copy(), {k: int(getattr(st, k)) for k, _ in SelfplayStats._fields_}

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsp_nnue.so")
 
-CUDA_SOURCES = ["kernels.cu", "capi.cu"]
+CUDA_SOURCES = ["kernels.cu", "capi.cu", "selfplay_gpu.cu"]
 HOST_SOURCES = ["host/position.cpp", "host/host_capi.cpp", "host/nnue_state.cpp", "host/selfplay.cpp"]
 HEADERS = ["kernels.cuh", "sp_features.h", "sp_delta.h", "host/position.h", "host/nnue_state.h", "host/selfplay.h", "host/rng.h",
            "../../include/sp_nnue.h", "../../include/sp_types.h"]

@@ -51,13 +51,13 @@ struct UpdateContext {};
 /* Same callback surface as eval::BoardObserver (nnue_state.h:33-45); every callback is a no-op. */
 struct BoardObserver {
     UpdateContext& ctx;
-    void prepareKingMove(Color, Square, Square) {}
-    template <typename P> void pieceAdded(const P&, Piece, Square) {}
-    template <typename P> void pieceRemoved(const P&, Piece, Square) {}
-    template <typename P> void pieceMutated(const P&, Piece, Piece, Square) {}
-    template <typename P> void pieceMoved(const P&, Piece, Square, Square) {}
-    template <typename P> void piecePromoted(const P&, Piece, Square, Piece, Square) {}
-    template <typename P> void finalize(const P&, const P&) {}
+    SP_POS_HD void prepareKingMove(Color, Square, Square) {}
+    template <typename P> SP_POS_HD void pieceAdded(const P&, Piece, Square) {}
+    template <typename P> SP_POS_HD void pieceRemoved(const P&, Piece, Square) {}
+    template <typename P> SP_POS_HD void pieceMutated(const P&, Piece, Piece, Square) {}
+    template <typename P> SP_POS_HD void pieceMoved(const P&, Piece, Square, Square) {}
+    template <typename P> SP_POS_HD void piecePromoted(const P&, Piece, Square, Piece, Square) {}
+    template <typename P> SP_POS_HD void finalize(const P&, const P&) {}
 };
 
 class NnueState;
@@ -166,10 +166,10 @@ private:
 /* ---- eval.h wrappers (src/eval/eval.cpp:25-28, 74-77, 109-112) */
 struct Contempt {
     i32 value[2]{0, 0};
-    i32 operator[](Color c) const { return value[c]; }
+    SP_POS_HD i32 operator[](Color c) const { return value[c]; }
 };
 
-inline i32 adjustStatic(i32 eval, Color stm, const Contempt& contempt) {
+SP_POS_HD inline i32 adjustStatic(i32 eval, Color stm, const Contempt& contempt) {
     eval += contempt[stm];
     return eval < -kScoreWin + 1 ? -kScoreWin + 1 : (eval > kScoreWin - 1 ? kScoreWin - 1 : eval);
 }

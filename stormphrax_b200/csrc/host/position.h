@@ -12,11 +12,18 @@
 #ifndef SP_HOST_POSITION_H
 #define SP_HOST_POSITION_H
 
-#include <array>
 #include <cstdint>
 #include <string>
 
 #include "../sp_features.h"
+
+/* The board core (put / remove / attacks / applyMove / generateLegal / pack) is header-inline and compiles for
+ * the device as well: the GPU-resident self-play driver (selfplay_gpu.cu) runs the same code per game. */
+#if defined(__CUDACC__)
+    #define SP_POS_HD __host__ __device__
+#else
+    #define SP_POS_HD
+#endif
 
 namespace sp::host {
 
@@ -30,75 +37,93 @@ enum class MoveType : uint16_t { kStandard = 0, kPromotion, kCastling, kEnPassan
 struct Move {
     uint16_t raw{0};
 
-    Square from() const { return raw >> 10; }
-    Square to() const { return (raw >> 4) & 0x3F; }
-    int promo() const { return ((raw >> 2) & 3) + 1; } /* piece type */
-    MoveType type() const { return static_cast<MoveType>(raw & 3); }
-    explicit operator bool() const { return raw != 0; }
-    bool operator==(const Move& o) const { return raw == o.raw; }
+    SP_POS_HD Square from() const { return raw >> 10; }
+    SP_POS_HD Square to() const { return (raw >> 4) & 0x3F; }
+    SP_POS_HD int promo() const { return ((raw >> 2) & 3) + 1; } /* piece type */
+    SP_POS_HD MoveType type() const { return static_cast<MoveType>(raw & 3); }
+    SP_POS_HD explicit operator bool() const { return raw != 0; }
+    SP_POS_HD bool operator==(const Move& o) const { return raw == o.raw; }
 
-    static Move standard(Square s, Square d) { return {static_cast<uint16_t>(s << 10 | d << 4)}; }
-    static Move promotion(Square s, Square d, int pt) {
+    SP_POS_HD static Move standard(Square s, Square d) { return {static_cast<uint16_t>(s << 10 | d << 4)}; }
+    SP_POS_HD static Move promotion(Square s, Square d, int pt) {
         return {static_cast<uint16_t>(s << 10 | d << 4 | (pt - 1) << 2 | 1)};
     }
-    static Move castling(Square king, Square rook) { return {static_cast<uint16_t>(king << 10 | rook << 4 | 2)}; }
-    static Move enPassant(Square s, Square d) { return {static_cast<uint16_t>(s << 10 | d << 4 | 3)}; }
+    SP_POS_HD static Move castling(Square king, Square rook) { return {static_cast<uint16_t>(king << 10 | rook << 4 | 2)}; }
+    SP_POS_HD static Move enPassant(Square s, Square d) { return {static_cast<uint16_t>(s << 10 | d << 4 | 3)}; }
 };
 
 struct NullObserver {
-    void prepareKingMove(Color, Square, Square) {}
-    template <typename P> void pieceAdded(const P&, Piece, Square) {}
-    template <typename P> void pieceRemoved(const P&, Piece, Square) {}
-    template <typename P> void pieceMutated(const P&, Piece, Piece, Square) {}
-    template <typename P> void pieceMoved(const P&, Piece, Square, Square) {}
-    template <typename P> void piecePromoted(const P&, Piece, Square, Piece, Square) {}
-    template <typename P> void finalize(const P&, const P&) {}
+    SP_POS_HD void prepareKingMove(Color, Square, Square) {}
+    template <typename P> SP_POS_HD void pieceAdded(const P&, Piece, Square) {}
+    template <typename P> SP_POS_HD void pieceRemoved(const P&, Piece, Square) {}
+    template <typename P> SP_POS_HD void pieceMutated(const P&, Piece, Piece, Square) {}
+    template <typename P> SP_POS_HD void pieceMoved(const P&, Piece, Square, Square) {}
+    template <typename P> SP_POS_HD void piecePromoted(const P&, Piece, Square, Piece, Square) {}
+    template <typename P> SP_POS_HD void finalize(const P&, const P&) {}
 };
 
 class Position {
 public:
-    Position();
+    SP_POS_HD Position() {
+        for (int i = 0; i < 64; ++i) m_mailbox[i] = kNoPiece;
+    }
 
     static Position startpos();
     static bool fromFen(const std::string& fen, Position& out);
     static bool fromPacked(const SpPackedBoard& packed, Position& out);
-    [[nodiscard]] SpPackedBoard pack() const;
+    [[nodiscard]] SP_POS_HD SpPackedBoard pack() const;
     [[nodiscard]] std::string toFen() const;
 
     /* Moves are assumed to be legal (same contract as the reference). */
     template <typename Observer>
-    [[nodiscard]] Position applyMove(Move move, Observer&& observer) const;
-    [[nodiscard]] Position applyMove(Move move) const { return applyMove(move, NullObserver{}); }
+    [[nodiscard]] SP_POS_HD Position applyMove(Move move, Observer&& observer) const;
+    [[nodiscard]] SP_POS_HD Position applyMove(Move move) const { return applyMove(move, NullObserver{}); }
 
     /* All legal moves; returns the count (<= 256). Castling is encoded king-takes-rook. */
-    int generateLegal(Move* out) const;
+    SP_POS_HD int generateLegal(Move* out) const;
 
-    [[nodiscard]] Piece pieceOn(Square sq) const { return m_mailbox[sq]; }
-    [[nodiscard]] const std::array<uint8_t, 64>& mailbox() const { return m_mailbox; }
-    [[nodiscard]] uint64_t occ() const { return m_color[0] | m_color[1]; }
-    [[nodiscard]] uint64_t bb(Color c) const { return m_color[c]; }
-    [[nodiscard]] uint64_t bbType(int type) const { return m_type[type]; }
-    [[nodiscard]] uint64_t bb(int type, Color c) const { return m_type[type] & m_color[c]; }
-    [[nodiscard]] Square king(Color c) const { return m_king[c]; }
-    [[nodiscard]] Color stm() const { return m_stm; }
-    [[nodiscard]] Square enPassant() const { return m_ep; }
-    [[nodiscard]] int halfmove() const { return m_halfmove; }
-    [[nodiscard]] int fullmove() const { return m_fullmove; }
+    [[nodiscard]] SP_POS_HD Piece pieceOn(Square sq) const { return m_mailbox[sq]; }
+    [[nodiscard]] SP_POS_HD const uint8_t* mailbox() const { return m_mailbox; }
+    [[nodiscard]] SP_POS_HD uint64_t occ() const { return m_color[0] | m_color[1]; }
+    [[nodiscard]] SP_POS_HD uint64_t bb(Color c) const { return m_color[c]; }
+    [[nodiscard]] SP_POS_HD uint64_t bbType(int type) const { return m_type[type]; }
+    [[nodiscard]] SP_POS_HD uint64_t bb(int type, Color c) const { return m_type[type] & m_color[c]; }
+    [[nodiscard]] SP_POS_HD Square king(Color c) const { return m_king[c]; }
+    [[nodiscard]] SP_POS_HD Color stm() const { return m_stm; }
+    [[nodiscard]] SP_POS_HD Square enPassant() const { return m_ep; }
+    [[nodiscard]] SP_POS_HD int halfmove() const { return m_halfmove; }
+    [[nodiscard]] SP_POS_HD int fullmove() const { return m_fullmove; }
     /* [color][0 = kingside, 1 = queenside] rook squares that may still castle */
-    [[nodiscard]] Square castlingRook(Color c, int side) const { return m_rooks[c][side]; }
+    [[nodiscard]] SP_POS_HD Square castlingRook(Color c, int side) const { return m_rooks[c][side]; }
 
-    [[nodiscard]] bool isAttacked(Square sq, Color by, uint64_t occupancy) const;
-    [[nodiscard]] bool isCheck() const { return isAttacked(m_king[m_stm], m_stm ^ 1, occ()); }
+    [[nodiscard]] SP_POS_HD bool isAttacked(Square sq, Color by, uint64_t occupancy) const {
+        const uint64_t them = m_color[by];
+        if (pawn_attacks(sq, by ^ 1) & them & m_type[kPawn]) return true;
+        if (knight_attacks(sq) & them & m_type[kKnight]) return true;
+        if (king_attacks(sq) & them & m_type[kKing]) return true;
+        if (bishop_attacks(sq, occupancy) & them & (m_type[kBishop] | m_type[kQueen])) return true;
+        if (rook_attacks(sq, occupancy) & them & (m_type[kRook] | m_type[kQueen])) return true;
+        return false;
+    }
+    [[nodiscard]] SP_POS_HD bool isCheck() const { return isAttacked(m_king[m_stm], m_stm ^ 1, occ()); }
 
     /* View for the shared feature code (sp_features.h) */
     void toBoard(Board& b) const;
 
 private:
-    void put(Piece p, Square sq);
-    void remove(Piece p, Square sq);
-    void filterEp();
+    SP_POS_HD void put(Piece p, Square sq) {
+        m_mailbox[sq] = static_cast<uint8_t>(p);
+        m_color[p & 1] |= bit(sq);
+        m_type[p >> 1] |= bit(sq);
+    }
+    SP_POS_HD void remove(Piece p, Square sq) {
+        m_mailbox[sq] = kNoPiece;
+        m_color[p & 1] &= ~bit(sq);
+        m_type[p >> 1] &= ~bit(sq);
+    }
+    SP_POS_HD void filterEp();
 
-    std::array<uint8_t, 64> m_mailbox{};
+    uint8_t m_mailbox[64];
     uint64_t m_color[2]{};
     uint64_t m_type[6]{};
     Square m_king[2]{kNoSquare, kNoSquare};
@@ -113,7 +138,7 @@ private:
  * Observer protocol, callback for callback as in src/position.cpp:1306-1466.
  */
 template <typename Observer>
-Position Position::applyMove(Move move, Observer&& observer) const {
+SP_POS_HD Position Position::applyMove(Move move, Observer&& observer) const {
     Position np = *this;
     np.m_stm = m_stm ^ 1;
     np.m_ep = kNoSquare;
@@ -211,6 +236,120 @@ Position Position::applyMove(Move move, Observer&& observer) const {
     }
     np.filterEp();
     return np;
+}
+
+/* marlinformat record, src/datagen/marlinformat.h:43-84 */
+SP_POS_HD inline SpPackedBoard Position::pack() const {
+    SpPackedBoard out{};
+    out.occupancy = occ();
+    int i = 0;
+    for (uint64_t bbs = occ(); bbs; bbs &= bbs - 1, ++i) {
+        const Square sq = lsb64(bbs);
+        const Piece p = pieceOn(sq);
+        unsigned pt = static_cast<unsigned>(p >> 1);
+        if (pt == kRook) {
+            const Color c = p & 1;
+            if (m_rooks[c][0] == sq || m_rooks[c][1] == sq) pt = 6;
+        }
+        const unsigned nib = pt | ((p & 1) == kBlack ? 8u : 0u);
+        out.pieces[i / 2] |= static_cast<uint8_t>(nib << ((i % 2) * 4));
+    }
+    const Square ep = m_ep == kNoSquare ? kNoSquare : ((m_ep & 7) | (m_stm == kBlack ? 2 * 8 : 5 * 8));
+    out.stm_ep = static_cast<uint8_t>((m_stm == kBlack ? 0x80 : 0) | ep);
+    out.halfmove = static_cast<uint8_t>(m_halfmove > 255 ? 255 : m_halfmove);
+    out.fullmove = static_cast<uint16_t>(m_fullmove);
+    return out;
+}
+
+/* Keep the en-passant square only if some en-passant capture is legal
+ * (intent of Position::filterEp, src/position.cpp:1608-1700). */
+SP_POS_HD inline void Position::filterEp() {
+    if (m_ep == kNoSquare) return;
+    const Color us = m_stm;
+    const Piece pawn = kPawn << 1 | us;
+    uint64_t candidates = pawn_attacks(m_ep, us ^ 1) & bb(kPawn, us);
+    const Square capSq = m_ep ^ 8;
+    if (pieceOn(capSq) != (kPawn << 1 | (us ^ 1))) candidates = 0;
+    bool ok = false;
+    for (; candidates && !ok; candidates &= candidates - 1) {
+        const Square src = lsb64(candidates);
+        Position np = *this;
+        np.remove(pawn ^ 1, capSq);
+        np.remove(pawn, src);
+        np.put(pawn, m_ep);
+        ok = !np.isAttacked(np.m_king[us], us ^ 1, np.occ());
+    }
+    if (!ok) m_ep = kNoSquare;
+}
+
+SP_POS_HD inline int Position::generateLegal(Move* out) const {
+    Move pseudo[256];
+    int n = 0;
+    const Color us = m_stm, them = us ^ 1;
+    const uint64_t own = m_color[us], enemy = m_color[them], all = own | enemy;
+    const int up = us == kWhite ? 8 : -8;
+    const int promoRank = us == kWhite ? 7 : 0, startRank = us == kWhite ? 1 : 6;
+
+    for (uint64_t bbs = own; bbs; bbs &= bbs - 1) {
+        const Square src = lsb64(bbs);
+        const Piece p = pieceOn(src);
+        const int type = p >> 1;
+        if (type == kPawn) {
+            auto push = [&](Square dst) {
+                if ((dst >> 3) == promoRank) {
+                    for (int pt = kQueen; pt >= kKnight; --pt) pseudo[n++] = Move::promotion(src, dst, pt);
+                } else {
+                    pseudo[n++] = Move::standard(src, dst);
+                }
+            };
+            const Square one = src + up;
+            if (!(all & bit(one))) {
+                push(one);
+                if ((src >> 3) == startRank && !(all & bit(one + up))) pseudo[n++] = Move::standard(src, one + up);
+            }
+            for (uint64_t caps = pawn_attacks(src, us) & enemy; caps; caps &= caps - 1) push(lsb64(caps));
+            if (m_ep != kNoSquare && (pawn_attacks(src, us) & bit(m_ep))) pseudo[n++] = Move::enPassant(src, m_ep);
+        } else {
+            for (uint64_t dsts = piece_attacks(p, src, all) & ~own; dsts; dsts &= dsts - 1)
+                pseudo[n++] = Move::standard(src, lsb64(dsts));
+        }
+    }
+
+    /* castling (Chess960 rules, src/movegen.cpp:172-196): squares the king and rook cross or land
+     * on must be empty apart from the two of them; the king may not start on, cross or land on an
+     * attacked square. Rook-shielded attacks on the landing square are caught by the make-and-test. */
+    const Square ksq = m_king[us];
+    if (!isAttacked(ksq, them, all)) {
+        for (int side = 0; side < 2; ++side) {
+            const Square rsq = m_rooks[us][side];
+            if (rsq == kNoSquare) continue;
+            const Square kingDst = (ksq & 56) | (side == 0 ? 6 : 2);
+            const Square rookDst = (ksq & 56) | (side == 0 ? 5 : 3);
+            auto between = [](Square a, Square b) { /* exclusive of a, inclusive of b */
+                uint64_t m = 0;
+                const int step = b > a ? 1 : -1;
+                for (Square s = a; s != b;) {
+                    s += step;
+                    m |= bit(s);
+                }
+                return m;
+            };
+            const uint64_t clear = (between(ksq, kingDst) | between(ksq, rsq) | bit(kingDst) | bit(rookDst))
+                                 & ~(bit(ksq) | bit(rsq));
+            if (clear & all) continue;
+            bool safe = true;
+            for (uint64_t path = between(ksq, kingDst); path && safe; path &= path - 1)
+                safe = !isAttacked(lsb64(path), them, all);
+            if (safe) pseudo[n++] = Move::castling(ksq, rsq);
+        }
+    }
+
+    int legal = 0;
+    for (int i = 0; i < n; ++i) {
+        const Position np = applyMove(pseudo[i]);
+        if (!np.isAttacked(np.m_king[us], them, np.occ())) out[legal++] = pseudo[i];
+    }
+    return legal;
 }
 
 } // namespace sp::host

@@ -4,6 +4,12 @@
 
 #include <cstdint>
 
+#if defined(__CUDACC__)
+    #define SP_RNG_HD __host__ __device__
+#else
+    #define SP_RNG_HD
+#endif
+
 namespace sp::host {
 
 /* splitmix64 seeding + JSF64 stream + Lemire's bounded draw: public-domain generators, the same
@@ -11,7 +17,7 @@ namespace sp::host {
  * from a (seed, game index) pair on any machine. */
 struct SplitMix64 {
     uint64_t s;
-    uint64_t next() {
+    SP_RNG_HD uint64_t next() {
         s += 0x9E3779B97F4A7C15ULL;
         uint64_t z = s;
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
@@ -22,11 +28,11 @@ struct SplitMix64 {
 
 struct Jsf64 {
     uint64_t a{0xF1EA5EED}, b, c, d;
-    explicit Jsf64(uint64_t seed) : b{seed}, c{seed}, d{seed} {
+    SP_RNG_HD explicit Jsf64(uint64_t seed) : b{seed}, c{seed}, d{seed} {
         for (int i = 0; i < 20; ++i) next();
     }
-    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
-    uint64_t next() {
+    SP_RNG_HD static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    SP_RNG_HD uint64_t next() {
         const uint64_t e = a - rotl(b, 7);
         a = b ^ rotl(c, 13);
         b = c + rotl(d, 37);
@@ -34,7 +40,7 @@ struct Jsf64 {
         d = e + a;
         return d;
     }
-    uint32_t below(uint32_t bound) {
+    SP_RNG_HD uint32_t below(uint32_t bound) {
         if (!bound) return 0;
         uint32_t x = static_cast<uint32_t>(next() >> 32);
         uint64_t m = static_cast<uint64_t>(x) * bound;

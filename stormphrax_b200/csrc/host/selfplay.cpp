@@ -24,15 +24,12 @@ extern "C" int sp_selfplay_run(
         std::vector<std::thread> pool;
         for (uint32_t t = 0; t < threads; ++t)
             pool.emplace_back([&, t] {
-                selfplay::Params p;
-                p.concurrency = std::max<uint32_t>(1, params->concurrency / threads);
-                p.totalGames = params->total_games / threads + (t < params->total_games % threads ? 1 : 0);
-                p.depth = std::min<uint32_t>(std::max<uint32_t>(1, params->depth), selfplay::kMaxPly - 8);
-                p.nodesPerMove = params->nodes_per_move;
-                p.maxPlies = params->max_plies ? params->max_plies : 300;
-                p.seed = params->seed + 0x9E3779B97F4A7C15ULL * (t + 1);
-                if (!p.totalGames) return;
-                selfplay::DeviceEvaluator evaluator{contexts[t], p.concurrency};
+                selfplay::Params p = selfplay::makeParams(*params);
+                /* thread t plays a contiguous range of the game slots */
+                p.slotBegin = static_cast<uint32_t>(uint64_t{p.concurrency} * t / threads);
+                p.slotEnd = static_cast<uint32_t>(uint64_t{p.concurrency} * (t + 1) / threads);
+                if (p.slotEnd == p.slotBegin) return;
+                selfplay::DeviceEvaluator evaluator{contexts[t], p.localSlots()};
                 selfplay::Driver<selfplay::DeviceEvaluator> driver{p, evaluator};
                 if (!driver.run(records[t], per_thread[t])) failed.store(1);
             });

@@ -43,11 +43,14 @@ namespace sp::host::selfplay {
 
 using eval::i32;
 
+template <typename T> SP_POS_HD constexpr T hdMax(T a, T b) { return a > b ? a : b; }
+template <typename T> SP_POS_HD constexpr T hdAbs(T a) { return a < 0 ? -a : a; }
+
 constexpr i32 kScoreMate = 32766;  /* src/core.h:706 */
 constexpr i32 kScoreTbWin = 30000; /* src/core.h:707 */
 constexpr int kMaxPly = 24;        /* search stack depth of the stand-in search (depth + extensions) */
 
-inline bool isDecisive(i32 score) { return std::abs(score) > eval::kScoreWin; } /* core.h:722-724 */
+SP_POS_HD inline bool isDecisive(i32 score) { return hdAbs(score) > eval::kScoreWin; } /* core.h:722-724 */
 
 /* datagen.cpp:72-90 */
 constexpr i32 kWinAdjMinScore = 1250;
@@ -60,66 +63,119 @@ enum class Outcome : uint8_t { kWhiteLoss = 0, kDraw, kWhiteWin }; /* datagen/co
 
 /* wdl::wdlParams / normalizeScore<false>, src/wdl.cpp:28-80: a cubic in material / 58 (material clamped to
  * [17, 78]) gives the score that means "50 % win"; the normalised score is 100 * score / that. */
-inline int classicalMaterial(const Position& pos) {
-    return __builtin_popcountll(pos.bbType(kPawn)) + 3 * __builtin_popcountll(pos.bbType(kKnight))
-         + 3 * __builtin_popcountll(pos.bbType(kBishop)) + 5 * __builtin_popcountll(pos.bbType(kRook))
-         + 9 * __builtin_popcountll(pos.bbType(kQueen));
+SP_POS_HD inline int classicalMaterial(const Position& pos) {
+    return popcount64(pos.bbType(kPawn)) + 3 * popcount64(pos.bbType(kKnight)) + 3 * popcount64(pos.bbType(kBishop))
+         + 5 * popcount64(pos.bbType(kRook)) + 9 * popcount64(pos.bbType(kQueen));
 }
-inline uint32_t plyFromStartpos(const Position& pos) { /* src/position.h:511-513 */
+SP_POS_HD inline uint32_t plyFromStartpos(const Position& pos) { /* src/position.h:511-513 */
     return static_cast<uint32_t>(pos.fullmove() * 2 - (pos.stm() == kWhite ? 1 : 0) - 1);
 }
-inline i32 normalizeScore(i32 score, int material) {
+/* No fused multiply-add anywhere in it: the device must round exactly like the host (and the reference). */
+SP_POS_HD inline i32 normalizeScore(i32 score, int material) {
     if (score == 0 || isDecisive(score)) return score;
-    static constexpr double kA[4] = {-244.97139595, 687.39969858, -654.38002091, 608.47087786};
-    const double m = static_cast<double>(std::clamp(material, 17, 78)) / 58.0;
-    const double a = ((kA[0] * m + kA[1]) * m + kA[2]) * m + kA[3];
-    return static_cast<i32>(std::round(100.0 * (static_cast<double>(score) / a)));
+    const double m = static_cast<double>(material < 17 ? 17 : (material > 78 ? 78 : material)) / 58.0;
+#if defined(__CUDA_ARCH__)
+    double a = __dadd_rn(__dmul_rn(-244.97139595, m), 687.39969858);
+    a = __dadd_rn(__dmul_rn(a, m), -654.38002091);
+    a = __dadd_rn(__dmul_rn(a, m), 608.47087786);
+    return static_cast<i32>(round(__dmul_rn(100.0, __ddiv_rn(static_cast<double>(score), a))));
+#else
+    volatile double a = -244.97139595 * m; /* volatile: keeps the host compiler from contracting into FMAs too */
+    a = a + 687.39969858;
+    a = a * m;
+    a = a + -654.38002091;
+    a = a * m;
+    a = a + 608.47087786;
+    volatile double q = static_cast<double>(score) / a;
+    q = 100.0 * q;
+    return static_cast<i32>(std::round(q));
+#endif
 }
 
 /* One game in viriformat (src/datagen/viriformat.cpp:33-63): the 32-byte start record with the outcome in
  * `wdl`, then (move, score) pairs of 4 bytes, then 4 zero bytes. */
-inline uint16_t viriMove(Move m) {
-    static constexpr uint16_t kTypes[4] = {0x0000, 0xC000, 0x8000, 0x4000}; /* standard, promotion, castling, en passant */
+SP_POS_HD inline uint16_t viriMove(Move m) {
+    const int type = static_cast<int>(m.type()); /* standard, promotion, castling, en passant -> 0x0000, 0xC000, 0x8000, 0x4000 */
+    const uint16_t flags = static_cast<uint16_t>(type == 0 ? 0x0000 : (type == 1 ? 0xC000 : (type == 2 ? 0x8000 : 0x4000)));
     const uint16_t promoIdx = m.type() == MoveType::kPromotion ? static_cast<uint16_t>(m.promo() - 1) : 0;
-    return static_cast<uint16_t>(m.from() | m.to() << 6 | promoIdx << 12 | kTypes[static_cast<int>(m.type())]);
+    return static_cast<uint16_t>(m.from() | m.to() << 6 | promoIdx << 12 | flags);
 }
+constexpr uint32_t kMaxRecordMoves = 512; /* a record holds at most this many (move, score) pairs: Params::maxPlies <= 510 */
 struct ViriGame {
     SpPackedBoard initial{};
-    std::vector<std::pair<uint16_t, int16_t>> moves;
+    uint32_t n{0};
+    uint32_t moves[kMaxRecordMoves]; /* move | score << 16, i.e. the record's bytes */
 
-    void start(const Position& pos) {
+    SP_POS_HD void start(const Position& pos) {
         initial = pos.pack();
         initial.eval = 0, initial.wdl = 0, initial.extra = 0;
-        moves.clear();
+        n = 0;
     }
-    void push(Move move, i32 score) { moves.emplace_back(viriMove(move), static_cast<int16_t>(score)); }
+    SP_POS_HD void push(Move move, i32 score) {
+        if (n < kMaxRecordMoves) moves[n++] = viriMove(move) | static_cast<uint32_t>(static_cast<uint16_t>(static_cast<int16_t>(score))) << 16;
+    }
+    [[nodiscard]] SP_POS_HD static constexpr size_t maxBytes(uint32_t maxPlies) { return sizeof(SpPackedBoard) + 4 * (size_t{maxPlies} + 2); }
+    [[nodiscard]] SP_POS_HD size_t bytes() const { return sizeof(SpPackedBoard) + 4 * (size_t{n} + 1); }
+    /* writes bytes() bytes: start record with the outcome, the pairs, the 4-byte terminator */
+    SP_POS_HD void serialize(uint8_t* out, Outcome outcome) {
+        initial.wdl = static_cast<uint8_t>(outcome);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(&initial);
+        for (size_t i = 0; i < sizeof(SpPackedBoard); ++i) out[i] = src[i];
+        uint8_t* q = out + sizeof(SpPackedBoard);
+        for (uint32_t i = 0; i <= n; ++i) {
+            const uint32_t w = i < n ? moves[i] : 0u;
+            q[4 * i] = static_cast<uint8_t>(w), q[4 * i + 1] = static_cast<uint8_t>(w >> 8);
+            q[4 * i + 2] = static_cast<uint8_t>(w >> 16), q[4 * i + 3] = static_cast<uint8_t>(w >> 24);
+        }
+    }
     /* returns the number of positions written (moves + 1, like the reference) */
     size_t writeAllWithOutcome(std::vector<uint8_t>& out, Outcome outcome) {
-        initial.wdl = static_cast<uint8_t>(outcome);
         const size_t at = out.size();
-        out.resize(at + sizeof(SpPackedBoard) + 4 * moves.size() + 4, 0);
-        std::memcpy(out.data() + at, &initial, sizeof(SpPackedBoard));
-        uint8_t* p = out.data() + at + sizeof(SpPackedBoard);
-        for (const auto& [mv, sc] : moves) {
-            std::memcpy(p, &mv, 2), std::memcpy(p + 2, &sc, 2);
-            p += 4;
-        }
-        return moves.size() + 1;
+        out.resize(at + bytes());
+        serialize(out.data() + at, outcome);
+        return size_t{n} + 1;
     }
 };
 
 struct Params {
-    uint32_t concurrency = 1024;  /* games in flight per host thread */
-    uint32_t totalGames = 1024;   /* games to finish per host thread */
+    uint32_t concurrency = 1024;  /* game slots of this driver instance: games in flight */
+    uint32_t totalGames = 1024;   /* games to play: slot g plays totalGames / concurrency of them (+ 1 for the first totalGames % concurrency slots) */
     uint32_t depth = 3;           /* iterative deepening stops after this depth ... */
     uint32_t nodesPerMove = 5000; /* ... or once a finished iteration has used this many nodes (soft limit, datagen.cpp:76) */
-    uint32_t maxPlies = 300;      /* games still undecided are drawn here (stands in for repetition detection) */
+    uint32_t maxPlies = 300;      /* games still undecided are drawn here (stands in for repetition detection); at most 510 */
     uint64_t seed = 42;
+    uint32_t slotBegin = 0, slotEnd = 0; /* the slots THIS driver instance plays (a host thread's share); 0, 0 = all */
+    Position start;               /* the start position (Position::startpos(), built on the host) */
+
+    [[nodiscard]] SP_POS_HD uint32_t localSlots() const { return slotEnd > slotBegin ? slotEnd - slotBegin : concurrency; }
+    [[nodiscard]] SP_POS_HD uint32_t firstSlot() const { return slotEnd > slotBegin ? slotBegin : 0; }
+
+    [[nodiscard]] SP_POS_HD uint32_t gamesOfSlot(uint32_t slot) const { return totalGames / concurrency + (slot < totalGames % concurrency ? 1 : 0); }
+    /* every (slot, game number) has its own random stream, whichever driver or thread plays it */
+    [[nodiscard]] SP_POS_HD uint64_t gameSeed(uint32_t slot, uint32_t k) const {
+        SplitMix64 mix{seed + 0x9E3779B97F4A7C15ULL * (uint64_t{slot} + 1)};
+        uint64_t v = mix.next();
+        for (uint32_t i = 0; i < k; ++i) v = mix.next();
+        return v;
+    }
 };
 
 struct Stats {
     uint64_t games{0}, positions{0}, nodes{0}, evals{0}, batches{0}, searches{0};
 };
+
+/* C-ABI parameters -> Params (host only: builds the start position) */
+inline Params makeParams(const SpSelfplayParams& in) {
+    Params p;
+    p.concurrency = in.concurrency ? in.concurrency : 1;
+    p.totalGames = in.total_games;
+    p.depth = in.depth < 1 ? 1 : (in.depth > static_cast<uint32_t>(kMaxPly - 8) ? static_cast<uint32_t>(kMaxPly - 8) : in.depth);
+    p.nodesPerMove = in.nodes_per_move;
+    p.maxPlies = in.max_plies ? (in.max_plies > kMaxRecordMoves - 2 ? kMaxRecordMoves - 2 : in.max_plies) : 300;
+    p.seed = in.seed;
+    p.start = Position::startpos();
+    return p;
+}
 
 /* ------------------------------------------------------------------ evaluator over the device */
 class DeviceEvaluator {
@@ -143,43 +199,43 @@ private:
     std::vector<eval::NnueState> m_states;
 };
 
-/* ------------------------------------------------------------------ one game: search + game loop as a state machine */
+/* ------------------------------------------------------------------ one game: search + game loop as a state machine
+ * Host and device code: the same class runs per host-driver slot and per GPU thread (selfplay_gpu.cu). */
 template <typename Evaluator>
 class Game {
 public:
     enum class Status { kNeedEval, kGameOver };
 
-    void start(uint32_t id, uint64_t seed, const Params& params, Evaluator* evaluator, Stats* stats) {
-        m_id = id, m_params = &params, m_eval = evaluator, m_stats = stats;
+    SP_POS_HD void start(uint32_t id, uint64_t seed, const Params& params, Evaluator* evaluator, Stats* stats) {
+        m_id = id, m_params = params, m_eval = evaluator, m_stats = stats;
         m_rng = Jsf64{seed};
         newGame();
     }
+    /* after the object was moved to another address space: rebind what it points to */
+    SP_POS_HD void bind(Evaluator* evaluator, Stats* stats) { m_eval = evaluator, m_stats = stats; }
 
     /* Runs until a static evaluation is needed (queued with the evaluator; call again after its flush)
      * or the game is over (its record is then in `record()` / `outcome()`). */
-    Status step() {
+    SP_POS_HD Status step() {
         for (;;) {
-            if (m_phase == Phase::kSearch) {
-                if (!runSearch()) return Status::kNeedEval;
-                /* one iteration finished */
-                m_score = m_rootScore, m_best = m_rootBest;
-                if (m_iterDepth < m_params->depth && m_searchNodes < m_params->nodesPerMove && !isDecisive(m_score)) {
-                    beginIteration(m_iterDepth + 1);
-                    continue;
-                }
-                ++m_stats->searches;
-                if (playMove()) return Status::kGameOver;
-                beginSearch();
+            if (!runSearch()) return Status::kNeedEval;
+            /* one iteration finished */
+            m_score = m_rootScore, m_best = m_rootBest;
+            if (m_iterDepth < m_params.depth && m_searchNodes < m_params.nodesPerMove && !isDecisive(m_score)) {
+                beginIteration(m_iterDepth + 1);
+                continue;
             }
+            ++m_stats->searches;
+            if (playMove()) return Status::kGameOver;
+            beginSearch();
         }
     }
 
-    [[nodiscard]] const ViriGame& record() const { return m_record; }
-    [[nodiscard]] ViriGame& record() { return m_record; }
-    [[nodiscard]] Outcome outcome() const { return m_outcome; }
+    [[nodiscard]] SP_POS_HD ViriGame& record() { return m_record; }
+    [[nodiscard]] SP_POS_HD Outcome outcome() const { return m_outcome; }
+    [[nodiscard]] SP_POS_HD i32* leaf() { return &m_leaf; }
 
 private:
-    enum class Phase { kSearch };
     enum class NodePhase : uint8_t { kEnter, kWaitEval, kLoop };
 
     struct Node {
@@ -192,14 +248,14 @@ private:
         NodePhase phase;
     };
 
-    void newGame() {
+    SP_POS_HD void newGame() {
         /* datagen.cpp:146-178: 8 or 9 random plies from the start position; start over on a dead end */
         for (;;) {
-            m_pos = Position::startpos();
+            m_pos = m_params.start;
             const uint32_t plies = 8 + static_cast<uint32_t>(m_rng.next() >> 63);
             bool dead = false;
+            Move moves[256];
             for (uint32_t i = 0; i < plies; ++i) {
-                Move moves[256];
                 const int n = m_pos.generateLegal(moves);
                 if (!n) {
                     dead = true;
@@ -207,23 +263,21 @@ private:
                 }
                 m_pos = m_pos.applyMove(moves[m_rng.below(static_cast<uint32_t>(n))]);
             }
-            Move moves[256];
             if (!dead && m_pos.generateLegal(moves)) break;
         }
         m_eval->reset(m_id, m_pos);
         m_record.start(m_pos);
         m_winPlies = m_lossPlies = m_drawPlies = 0;
         m_plies = 0;
-        m_phase = Phase::kSearch;
         beginSearch();
     }
 
-    void beginSearch() {
+    SP_POS_HD void beginSearch() {
         m_searchNodes = 0;
         beginIteration(1);
     }
 
-    void beginIteration(uint32_t depth) {
+    SP_POS_HD void beginIteration(uint32_t depth) {
         m_iterDepth = depth;
         m_sp = 0;
         Node& root = m_stack[0];
@@ -234,21 +288,25 @@ private:
         m_rootBest = Move{};
     }
 
-    /* order: captures by victim value first, the previous iteration's best root move before everything */
-    void orderMoves(Node& nd, bool root) const {
-        auto key = [&](Move m) {
+    /* order: captures by victim value first, the previous iteration's best root move before everything.
+     * Stable insertion sort by descending key (the same order std::stable_sort gives). */
+    SP_POS_HD void orderMoves(Node& nd, bool root) const {
+        int keys[256];
+        for (int i = 0; i < nd.n; ++i) {
+            const Move m = nd.moves[i];
             int k = 0;
             const Piece victim = m.type() == MoveType::kEnPassant ? kPawn << 1 : (m.type() == MoveType::kCastling ? kNoPiece : nd.pos.pieceOn(m.to()));
             if (victim != kNoPiece) k = 16 + 2 * (victim >> 1) - ((nd.pos.pieceOn(m.from()) >> 1) > (victim >> 1) ? 1 : 0);
             if (m.type() == MoveType::kPromotion) k += 8;
             if (root && m == m_best) k = 1000;
-            return k;
-        };
-        std::stable_sort(nd.moves, nd.moves + nd.n, [&](Move a, Move b) { return key(a) > key(b); });
+            int j = i;
+            for (; j > 0 && keys[j - 1] < k; --j) keys[j] = keys[j - 1], nd.moves[j] = nd.moves[j - 1];
+            keys[j] = k, nd.moves[j] = m;
+        }
     }
 
     /* Negamax alpha-beta on an explicit stack.  Returns false when it had to queue an evaluation. */
-    bool runSearch() {
+    SP_POS_HD bool runSearch() {
         i32 ret = 0;
         for (;;) {
             Node& nd = m_stack[m_sp];
@@ -313,12 +371,12 @@ private:
                 parent.best = v;
                 if (m_sp == 0) m_rootBest = parent.moves[parent.next - 1];
             }
-            parent.alpha = std::max(parent.alpha, v);
+            parent.alpha = hdMax(parent.alpha, v);
         }
     }
 
     /* datagen.cpp:206-300.  Returns true when the game is over. */
-    bool playMove() {
+    SP_POS_HD bool playMove() {
         const i32 score = m_score; /* side-to-move relative; the reference's datagen search reports white-relative */
         const i32 whiteScore = m_pos.stm() == kWhite ? score : -score;
         const Move move = m_best;
@@ -335,7 +393,7 @@ private:
                 ++m_winPlies, m_lossPlies = 0, m_drawPlies = 0;
             } else if (norm < -kWinAdjMinScore) {
                 m_winPlies = 0, ++m_lossPlies, m_drawPlies = 0;
-            } else if (plyFromStartpos(m_pos) >= kDrawAdjMinPlies && std::abs(norm) < kDrawAdjMaxScore) {
+            } else if (plyFromStartpos(m_pos) >= kDrawAdjMinPlies && hdAbs(norm) < kDrawAdjMaxScore) {
                 m_winPlies = 0, m_lossPlies = 0, ++m_drawPlies;
             } else {
                 m_winPlies = m_lossPlies = m_drawPlies = 0;
@@ -352,13 +410,13 @@ private:
 
         Move replies[256];
         const int nReplies = m_pos.generateLegal(replies);
-        const bool bareKings = __builtin_popcountll(m_pos.occ()) <= 2;
-        if (m_pos.halfmove() >= 100 || bareKings || m_plies >= m_params->maxPlies) { /* isDrawn stand-in, datagen.cpp:264-268 */
+        const bool bareKings = popcount64(m_pos.occ()) <= 2;
+        if (m_pos.halfmove() >= 100 || bareKings || m_plies >= m_params.maxPlies) { /* isDrawn stand-in, datagen.cpp:264-268 */
             m_outcome = Outcome::kDraw;
             m_record.push(move, 0);
             return true;
         }
-        m_record.push(move, std::abs(whiteScore) <= 2 ? 0 : whiteScore);
+        m_record.push(move, hdAbs(whiteScore) <= 2 ? 0 : whiteScore);
         if (over) return true;
         if (!nReplies) { /* the reference finds this at its next search (datagen.cpp:213-222) */
             m_outcome = m_pos.isCheck() ? (m_pos.stm() == kBlack ? Outcome::kWhiteWin : Outcome::kWhiteLoss) : Outcome::kDraw;
@@ -368,14 +426,13 @@ private:
     }
 
     uint32_t m_id{0};
-    const Params* m_params{nullptr};
+    Params m_params;
     Evaluator* m_eval{nullptr};
     Stats* m_stats{nullptr};
     Jsf64 m_rng{0};
     Position m_pos;
     ViriGame m_record;
     Outcome m_outcome{Outcome::kDraw};
-    Phase m_phase{Phase::kSearch};
     uint32_t m_winPlies{0}, m_lossPlies{0}, m_drawPlies{0}, m_plies{0};
     /* search */
     Node m_stack[kMaxPly + 1];
@@ -389,16 +446,19 @@ private:
 template <typename Evaluator>
 class Driver {
 public:
-    Driver(const Params& params, Evaluator& evaluator) : m_params{params}, m_eval{evaluator}, m_games(params.concurrency) {}
+    Driver(const Params& params, Evaluator& evaluator) : m_params{params}, m_eval{evaluator}, m_games(params.localSlots()) {}
 
-    /* Plays params.totalGames games, at most params.concurrency at a time; appends their viriformat records
-     * to `out` in completion order.  Returns false if a device batch failed. */
+    /* Slot g plays params.gamesOfSlot(g) games one after the other, all slots concurrently.  The viriformat
+     * records are appended to `out` slot by slot (slot-major, game order within a slot): the same bytes
+     * whichever driver -- this one or the GPU-resident one -- played them.  Returns false if a device
+     * batch failed. */
     bool run(std::vector<uint8_t>& out, Stats& stats) {
-        SplitMix64 seeds{m_params.seed};
-        uint32_t started = 0;
-        std::vector<uint32_t> active;
-        for (uint32_t g = 0; g < m_params.concurrency && started < m_params.totalGames; ++g, ++started) {
-            m_games[g].start(g, seeds.next(), m_params, &m_eval, &stats);
+        const uint32_t slots = m_params.localSlots(), first = m_params.firstSlot(); /* local index l = global slot first + l */
+        std::vector<std::vector<uint8_t>> records(slots);
+        std::vector<uint32_t> played(slots, 0), active;
+        for (uint32_t g = 0; g < slots; ++g) {
+            if (!m_params.gamesOfSlot(first + g)) continue;
+            m_games[g].start(g, m_params.gameSeed(first + g, 0), m_params, &m_eval, &stats);
             active.push_back(g);
         }
         while (!active.empty()) {
@@ -408,13 +468,12 @@ public:
                 bool alive = true;
                 while (m_games[g].step() == Game<Evaluator>::Status::kGameOver) {
                     stats.games += 1;
-                    m_games[g].record().writeAllWithOutcome(out, m_games[g].outcome());
-                    if (started >= m_params.totalGames) {
+                    m_games[g].record().writeAllWithOutcome(records[g], m_games[g].outcome());
+                    if (++played[g] >= m_params.gamesOfSlot(first + g)) {
                         alive = false;
                         break;
                     }
-                    ++started;
-                    m_games[g].start(g, seeds.next(), m_params, &m_eval, &stats); /* the slot starts its next game */
+                    m_games[g].start(g, m_params.gameSeed(first + g, played[g]), m_params, &m_eval, &stats); /* the slot's next game */
                 }
                 if (alive) active[keep++] = g;
             }
@@ -423,6 +482,7 @@ public:
             ++stats.batches;
             if (!m_eval.flush()) return false;
         }
+        for (const auto& r : records) out.insert(out.end(), r.begin(), r.end());
         return true;
     }
 

@@ -131,6 +131,7 @@ struct Recursive {
 
 int main() {
     selfplay::Params params;
+    params.start = Position::startpos();
     params.concurrency = 24, params.totalGames = 60, params.depth = 3, params.nodesPerMove = 400, params.maxPlies = 120, params.seed = 7;
     StandInEvaluator evaluator;
     selfplay::Driver<StandInEvaluator> driver{params, evaluator};

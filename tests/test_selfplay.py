@@ -153,10 +153,27 @@ def test_selfplay_device_records_replay_and_scores_match_oracle(net, c_oracle):
 
 
 @pytest.mark.gpu
-def test_selfplay_is_deterministic_and_thread_count_only_reorders(net):
-    a, sa = api.selfplay(net.image, 0, concurrency=64, total_games=64, threads=1, depth=2, nodes_per_move=100, max_plies=40, seed=3)
-    b, sb = api.selfplay(net.image, 0, concurrency=64, total_games=64, threads=1, depth=2, nodes_per_move=100, max_plies=40, seed=3)
-    assert np.array_equal(a, b) and sa == sb
+def test_selfplay_is_deterministic_whatever_the_thread_count(net):
+    """Every (slot, game) has its own random stream and records are emitted slot-major."""
+    kw = dict(concurrency=64, total_games=100, depth=2, nodes_per_move=100, max_plies=40, seed=3)
+    a, sa = api.selfplay(net.image, 0, threads=1, **kw)
+    b, sb = api.selfplay(net.image, 0, threads=3, **kw)
+    assert np.array_equal(a, b)
+    assert {k: v for k, v in sa.items() if k != "batches"} == {k: v for k, v in sb.items() if k != "batches"}
+
+
+@pytest.mark.gpu
+def test_gpu_resident_selfplay_plays_the_same_games_as_the_host_driver(net):
+    """sp_selfplay_run_gpu: the search state machine runs per device thread; records must be byte-identical to the
+    host driver's (same board code, same search, exact integer evaluations), and so must the node / eval counts."""
+    kw = dict(concurrency=96, total_games=150, depth=3, nodes_per_move=400, max_plies=50, seed=21)
+    host, sh = api.selfplay(net.image, 0, threads=2, **kw)
+    dev, sd = api.selfplay(net.image, 0, resident=True, **kw)
+    assert len(api.parse_viriformat(dev)) == 150
+    assert np.array_equal(host, dev)
+    for k in ("games", "positions", "nodes", "evals", "searches"):
+        assert sh[k] == sd[k], (k, sh[k], sd[k])
+    assert sd["evals"] / sd["batches"] > 40  # one device batch per round of all running games
 
 
 def _golden_datagen():
