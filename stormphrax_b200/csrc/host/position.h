@@ -81,6 +81,9 @@ public:
 
     /* All legal moves; returns the count (<= 256). Castling is encoded king-takes-rook. */
     SP_POS_HD int generateLegal(Move* out) const;
+    /* The same list in the same order with every pseudo-legal move made and tested (the obviously correct
+     * form; tests/cpp/test_movegen.cpp holds generateLegal against it). */
+    SP_POS_HD int generateLegalSlow(Move* out) const;
 
     [[nodiscard]] SP_POS_HD Piece pieceOn(Square sq) const { return m_mailbox[sq]; }
     [[nodiscard]] SP_POS_HD const uint8_t* mailbox() const { return m_mailbox; }
@@ -111,6 +114,7 @@ public:
     void toBoard(Board& b) const;
 
 private:
+    SP_POS_HD int generatePseudo(Move* pseudo) const;
     SP_POS_HD void put(Piece p, Square sq) {
         m_mailbox[sq] = static_cast<uint8_t>(p);
         m_color[p & 1] |= bit(sq);
@@ -282,8 +286,7 @@ SP_POS_HD inline void Position::filterEp() {
     if (!ok) m_ep = kNoSquare;
 }
 
-SP_POS_HD inline int Position::generateLegal(Move* out) const {
-    Move pseudo[256];
+SP_POS_HD inline int Position::generatePseudo(Move* pseudo) const {
     int n = 0;
     const Color us = m_stm, them = us ^ 1;
     const uint64_t own = m_color[us], enemy = m_color[them], all = own | enemy;
@@ -343,11 +346,69 @@ SP_POS_HD inline int Position::generateLegal(Move* out) const {
             if (safe) pseudo[n++] = Move::castling(ksq, rsq);
         }
     }
+    return n;
+}
 
+/* squares strictly between two aligned squares (0 if they share no rank, file or diagonal) */
+SP_POS_HD inline uint64_t between_mask(Square a, Square b) {
+    const uint64_t ra = rook_attacks(a, bit(b));
+    if (ra & bit(b)) return ra & rook_attacks(b, bit(a));
+    const uint64_t ba = bishop_attacks(a, bit(b));
+    if (ba & bit(b)) return ba & bishop_attacks(b, bit(a));
+    return 0;
+}
+/* the whole line through two aligned squares */
+SP_POS_HD inline uint64_t line_mask(Square a, Square b) {
+    const uint64_t ra = rook_attacks(a, 0);
+    if (ra & bit(b)) return (ra & rook_attacks(b, 0)) | bit(a) | bit(b);
+    const uint64_t ba = bishop_attacks(a, 0);
+    if (ba & bit(b)) return (ba & bishop_attacks(b, 0)) | bit(a) | bit(b);
+    return 0;
+}
+
+SP_POS_HD inline int Position::generateLegalSlow(Move* out) const {
+    Move pseudo[256];
+    const int n = generatePseudo(pseudo);
+    const Color us = m_stm, them = us ^ 1;
     int legal = 0;
     for (int i = 0; i < n; ++i) {
         const Position np = applyMove(pseudo[i]);
         if (!np.isAttacked(np.m_king[us], them, np.occ())) out[legal++] = pseudo[i];
+    }
+    return legal;
+}
+
+/* Pseudo-legal generation, then: in check, make and test every move; otherwise only king moves, castling
+ * and en passant need the test -- any other move is legal unless its piece is pinned and leaves the line
+ * through the king and the pinner. */
+SP_POS_HD inline int Position::generateLegal(Move* out) const {
+    Move pseudo[256];
+    const int n = generatePseudo(pseudo);
+    const Color us = m_stm, them = us ^ 1;
+    const Square ksq = m_king[us];
+    const uint64_t own = m_color[us], enemy = m_color[them], all = own | enemy;
+    const bool inCheck = isAttacked(ksq, them, all);
+    uint64_t pinned = 0;
+    if (!inCheck) {
+        uint64_t snipers = (rook_attacks(ksq, 0) & enemy & (m_type[kRook] | m_type[kQueen]))
+                         | (bishop_attacks(ksq, 0) & enemy & (m_type[kBishop] | m_type[kQueen]));
+        for (; snipers; snipers &= snipers - 1) {
+            const uint64_t blockers = between_mask(ksq, lsb64(snipers)) & all;
+            if (blockers && !(blockers & (blockers - 1))) pinned |= blockers & own;
+        }
+    }
+    int legal = 0;
+    for (int i = 0; i < n; ++i) {
+        const Move m = pseudo[i];
+        const Square src = m.from();
+        bool ok;
+        if (inCheck || src == ksq || m.type() == MoveType::kEnPassant || m.type() == MoveType::kCastling) {
+            const Position np = applyMove(m);
+            ok = !np.isAttacked(np.m_king[us], them, np.occ());
+        } else {
+            ok = !(pinned & bit(src)) || (line_mask(ksq, src) & bit(m.to()));
+        }
+        if (ok) out[legal++] = m;
     }
     return legal;
 }

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/sp_nnue.h"
@@ -102,10 +103,11 @@ __global__ void __launch_bounds__(128) selfplay_init_kernel(Slots sl, GpuEvaluat
     if (g >= sl.n) return;
     sl.stats[g] = Stats{};
     sl.played[g] = 0, sl.record_len[g] = 0;
-    sl.alive[g] = params.gamesOfSlot(g) ? 1 : 0;
+    const uint32_t slot = params.firstSlot() + g; /* g is local to this driver instance */
+    sl.alive[g] = params.gamesOfSlot(slot) ? 1 : 0;
     if (!sl.alive[g]) return;
     DeviceGame* game = new (&sl.games[g]) DeviceGame();
-    game->start(g, params.gameSeed(g, 0), params, ev, &sl.stats[g]);
+    game->start(g, params.gameSeed(slot, 0), params, ev, &sl.stats[g]);
 }
 
 /* every running game advances until it needs a static evaluation (or its slot has played all its games) */
@@ -118,11 +120,12 @@ __global__ void __launch_bounds__(128) selfplay_step_kernel(Slots sl, GpuEvaluat
         ViriGame& rec = game.record();
         rec.serialize(sl.records + g * sl.record_stride + sl.record_len[g], game.outcome());
         sl.record_len[g] += static_cast<uint32_t>(rec.bytes());
-        if (++sl.played[g] >= params.gamesOfSlot(g)) {
+        const uint32_t slot = params.firstSlot() + g;
+        if (++sl.played[g] >= params.gamesOfSlot(slot)) {
             sl.alive[g] = 0;
             return;
         }
-        game.start(g, params.gameSeed(g, sl.played[g]), params, ev, &sl.stats[g]);
+        game.start(g, params.gameSeed(slot, sl.played[g]), params, ev, &sl.stats[g]);
     }
     atomicAdd(&ev->rq.counters[3], 1u);
 }
@@ -149,23 +152,15 @@ struct DeviceBuffers {
     }
 };
 
-} // namespace
-
-extern "C" int sp_selfplay_run_gpu(
-    const void* net_image, size_t len, int device, const SpSelfplayParams* in, SpSelfplayStats* stats, uint8_t* out, size_t out_capacity,
-    size_t* out_len) {
-    if (!net_image || !in || !stats || !out_len || (!out && out_capacity)) return SP_ERR_INVALID;
+/* One driver instance: the game slots [params.slotBegin, params.slotEnd) with their own evaluator context,
+ * stream and buffers.  Several instances (host threads) overlap one instance's search step with another's
+ * evaluation batch on the device. */
+int run_instance(const void* net_image, size_t len, int device, const Params& params, Stats& total, uint64_t& batches, std::vector<uint8_t>& records) {
     SpNnue* ctx = nullptr;
     int rc = sp_nnue_create(net_image, len, device, &ctx);
     if (rc != SP_OK) return rc;
-    const Params params = makeParams(*in);
-    const uint32_t n = params.concurrency;
-    *stats = SpSelfplayStats{};
-    *out_len = 0;
-
-    int prev_device = 0;
-    cudaGetDevice(&prev_device);
     cudaSetDevice(device);
+    const uint32_t n = params.localSlots();
     {
         DeviceBuffers mem;
         Slots sl{};
@@ -173,9 +168,8 @@ extern "C" int sp_selfplay_run_gpu(
         GpuEvaluator ev{};
         GpuEvaluator* d_ev = nullptr;
         i32 *d_out_refresh = nullptr, *d_out_update = nullptr, *d_out_eval = nullptr;
-        uint32_t games_per_slot = params.gamesOfSlot(0);
         sl.n = n;
-        sl.record_stride = static_cast<size_t>(games_per_slot) * ViriGame::maxBytes(params.maxPlies);
+        sl.record_stride = static_cast<size_t>(params.gamesOfSlot(0)) * ViriGame::maxBytes(params.maxPlies); /* slot 0 plays the most games */
         bool ok = mem.alloc(sl.games, n) && mem.alloc(sl.stats, n) && mem.alloc(sl.played, n) && mem.alloc(sl.alive, n)
                && mem.alloc(sl.records, static_cast<size_t>(n) * sl.record_stride) && mem.alloc(sl.record_len, n)
                && mem.alloc(rq.refresh_slot, n) && mem.alloc(rq.refresh_board, n) && mem.alloc(rq.refresh_out, n) && mem.alloc(rq.update_src, n)
@@ -188,12 +182,9 @@ extern "C" int sp_selfplay_run_gpu(
         if (rc == SP_OK && cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) rc = SP_ERR_CUDA;
         uint32_t* h_counters = nullptr;
         if (rc == SP_OK && cudaMallocHost(&h_counters, 4 * sizeof(uint32_t)) != cudaSuccess) rc = SP_ERR_CUDA;
-        uint64_t batches = 0;
         if (rc == SP_OK) {
             ev.rq = rq;
             cudaMemcpyAsync(d_ev, &ev, sizeof(ev), cudaMemcpyHostToDevice, stream);
-            /* the games' search runs per thread on its own stack: move lists and board copies */
-            cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024);
             const unsigned grid = (n + 127) / 128;
             cudaMemsetAsync(rq.counters, 0, 4 * sizeof(uint32_t), stream);
             selfplay_init_kernel<<<grid, 128, 0, stream>>>(sl, d_ev, params);
@@ -223,30 +214,69 @@ extern "C" int sp_selfplay_run_gpu(
             std::vector<uint32_t> h_len(n);
             cudaMemcpy(h_stats.data(), sl.stats, n * sizeof(Stats), cudaMemcpyDeviceToHost);
             cudaMemcpy(h_len.data(), sl.record_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-            size_t total = 0;
-            for (uint32_t g = 0; g < n; ++g) {
-                stats->games += h_stats[g].games, stats->positions += h_stats[g].positions, stats->nodes += h_stats[g].nodes;
-                stats->evals += h_stats[g].evals, stats->searches += h_stats[g].searches;
-                total += h_len[g];
-            }
-            stats->batches = batches;
-            *out_len = total;
-            if (out && total > out_capacity) rc = SP_ERR_CAPACITY;
-            if (out && rc == SP_OK) {
-                std::vector<uint8_t> h_records(static_cast<size_t>(n) * sl.record_stride);
-                cudaMemcpy(h_records.data(), sl.records, h_records.size(), cudaMemcpyDeviceToHost);
-                size_t at = 0;
-                for (uint32_t g = 0; g < n; ++g) { /* slot-major, like the host driver */
-                    std::copy_n(h_records.data() + g * sl.record_stride, h_len[g], out + at);
-                    at += h_len[g];
-                }
+            std::vector<uint8_t> h_records(static_cast<size_t>(n) * sl.record_stride);
+            cudaMemcpy(h_records.data(), sl.records, h_records.size(), cudaMemcpyDeviceToHost);
+            for (uint32_t g = 0; g < n; ++g) { /* slot-major, like the host driver */
+                total.games += h_stats[g].games, total.positions += h_stats[g].positions, total.nodes += h_stats[g].nodes;
+                total.evals += h_stats[g].evals, total.searches += h_stats[g].searches;
+                records.insert(records.end(), h_records.begin() + static_cast<ptrdiff_t>(g * sl.record_stride),
+                               h_records.begin() + static_cast<ptrdiff_t>(g * sl.record_stride + h_len[g]));
             }
             if (cudaGetLastError() != cudaSuccess) rc = SP_ERR_CUDA;
         }
         if (h_counters) cudaFreeHost(h_counters);
         if (stream) cudaStreamDestroy(stream);
     }
-    cudaSetDevice(prev_device);
     sp_nnue_destroy(ctx);
     return rc;
+}
+
+} // namespace
+
+extern "C" int sp_selfplay_run_gpu(
+    const void* net_image, size_t len, int device, const SpSelfplayParams* in, SpSelfplayStats* stats, uint8_t* out, size_t out_capacity,
+    size_t* out_len) {
+    if (!net_image || !in || !stats || !out_len || (!out && out_capacity)) return SP_ERR_INVALID;
+    const Params params = makeParams(*in);
+    const uint32_t instances = std::min<uint32_t>(std::max<uint32_t>(1, in->threads), params.concurrency);
+    *stats = SpSelfplayStats{};
+    *out_len = 0;
+    int prev_device = 0;
+    cudaGetDevice(&prev_device);
+    cudaSetDevice(device);
+    /* the games' search runs per thread on its own stack: move lists and board copies */
+    cudaDeviceSetLimit(cudaLimitStackSize, 8 * 1024);
+    std::vector<Stats> totals(instances);
+    std::vector<uint64_t> batches(instances, 0);
+    std::vector<std::vector<uint8_t>> records(instances);
+    std::vector<int> rcs(instances, SP_OK);
+    std::vector<std::thread> pool;
+    for (uint32_t t = 0; t < instances; ++t)
+        pool.emplace_back([&, t] {
+            Params p = params;
+            p.slotBegin = static_cast<uint32_t>(uint64_t{p.concurrency} * t / instances);
+            p.slotEnd = static_cast<uint32_t>(uint64_t{p.concurrency} * (t + 1) / instances);
+            rcs[t] = run_instance(net_image, len, device, p, totals[t], batches[t], records[t]);
+        });
+    for (auto& th : pool) th.join();
+    cudaSetDevice(prev_device);
+    int rc = SP_OK;
+    size_t total = 0;
+    for (uint32_t t = 0; t < instances; ++t) {
+        if (rcs[t] != SP_OK) rc = rcs[t];
+        stats->games += totals[t].games, stats->positions += totals[t].positions, stats->nodes += totals[t].nodes;
+        stats->evals += totals[t].evals, stats->searches += totals[t].searches, stats->batches += batches[t];
+        total += records[t].size();
+    }
+    if (rc != SP_OK) return rc;
+    *out_len = total;
+    if (out && total > out_capacity) return SP_ERR_CAPACITY;
+    if (out) {
+        size_t at = 0;
+        for (const auto& r : records) {
+            std::copy(r.begin(), r.end(), out + at);
+            at += r.size();
+        }
+    }
+    return SP_OK;
 }

@@ -31,6 +31,16 @@ def test_selfplay_host_logic(tmp_path):
     assert "0 failures" in r.stdout
 
 
+def test_pin_aware_movegen_equals_make_and_test(tmp_path):
+    exe = str(tmp_path / "test_movegen")
+    subprocess.run(
+        ["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_movegen.cpp"), os.path.join(HOST, "position.cpp")],
+        check=True,
+    )
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and " 0 failures" in r.stdout, r.stdout + r.stderr[-2000:]
+
+
 def test_viriformat_move_encoding():
     """from | to << 6 | promo << 12 | type flags (viriformat.cpp:33-49) against hand-built moves."""
     b = api.board_from_fen("r3k2r/1P6/8/3pP3/8/8/8/R3K2R w KQkq d6 0 1")
@@ -174,6 +184,9 @@ def test_gpu_resident_selfplay_plays_the_same_games_as_the_host_driver(net):
     for k in ("games", "positions", "nodes", "evals", "searches"):
         assert sh[k] == sd[k], (k, sh[k], sd[k])
     assert sd["evals"] / sd["batches"] > 40  # one device batch per round of all running games
+    # three concurrent driver instances (slot ranges) on the same device: still the same bytes
+    dev3, sd3 = api.selfplay(net.image, 0, resident=True, threads=3, **kw)
+    assert np.array_equal(host, dev3) and sd3["evals"] == sh["evals"]
 
 
 def _golden_datagen():
