@@ -32,6 +32,9 @@ using namespace sp::host;
 using namespace sp::host::selfplay;
 
 constexpr uint32_t kSlotsPerGame = kMaxPly + 1;
+#ifndef SP_SELFPLAY_MIN_BLOCKS
+#define SP_SELFPLAY_MIN_BLOCKS 4 /* 128-thread blocks per SM the step kernel is compiled for (register budget) */
+#endif
 
 /* request lists of one round; capacity = number of game slots each (a game has one request per round) */
 struct Requests {
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(128) selfplay_init_kernel(Slots sl, GpuEvaluat
 }
 
 /* every running game advances until it needs a static evaluation (or its slot has played all its games) */
-__global__ void __launch_bounds__(128) selfplay_step_kernel(Slots sl, GpuEvaluator* ev, Params params) {
+__global__ void __launch_bounds__(128, SP_SELFPLAY_MIN_BLOCKS) selfplay_step_kernel(Slots sl, GpuEvaluator* ev, Params params) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= sl.n || !sl.alive[g]) return;
     DeviceGame& game = sl.games[g];
