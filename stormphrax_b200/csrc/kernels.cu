@@ -1478,14 +1478,16 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
  * this library that is bound by it: 1 KB of activations per position, read once).
  *
  *   - one persistent CTA per SM works on a contiguous run of 32-row tiles of the bucket-grouped order;
- *   - a producer warp keeps kHeadStages tiles in flight: every lane issues ONE bulk copy (TMA engine,
- *     cp.async.bulk global -> shared, 1 KB = one activation row) into a ring of tiles, completion counted
- *     in bytes on the stage's `full` mbarrier; rows are padded to 1088 B so that the A-fragment reads
- *     (LDS.128, 8 rows x 4 k-chunks per quarter warp) touch every bank group once;
- *   - eleven consumer warps take tiles round-robin.  A warp owns its tile's 32 rows (two m16 tiles), so
- *     every weight fragment it fetches from shared memory feeds two IMMAs, and releases the stage
- *     (`empty` mbarrier) as soon as L1 is done -- the epilogue, L2 and L3 run from registers while the
- *     TMA engine refills the stage;
+ *   - kHeadStages tiles are kept in flight in a ring of stages: one bulk copy per activation row (TMA
+ *     engine, cp.async.bulk global -> shared, 1 KB), completion counted in bytes on the stage's `full`
+ *     mbarrier; rows are padded to 1088 B so that the A-fragment reads (LDS.128, 8 rows x 4 k-chunks per
+ *     quarter warp) touch every bank group once;
+ *   - every warp is a consumer; warp w takes tiles w, w + kHeadWarpsStream, ...  A warp owns its tile's
+ *     32 rows (two m16 tiles), so every weight fragment it fetches from shared memory feeds two IMMAs.
+ *     As soon as L1 is done it releases the stage and itself requests the tile that follows on it -- the
+ *     epilogue, L2 and L3 then run from registers while the TMA engine refills the stage.  (A dedicated
+ *     producer warp was the first design: ncu showed that single issuing warp to be the bottleneck,
+ *     profiles/r1_head_stream_ncu_v7.md.)
  *   - L1 -> L2 without a shared-memory round trip: the contraction index of an IMMA may be visited in
  *     any order as long as A and B agree, so L2's k-slots are DEFINED as the order in which L1's C
  *     fragment leaves the outputs in a lane (lane (g, t) holds outputs 8t .. 8t+7 of rows g and g+8 =
@@ -1493,21 +1495,16 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
  *     (l2_fragment_index);
  *   - L2 by Horner's rule over the limb weight: acc = (acc << 8) + sum_{i+j = s} a_i w_j for s = 3..0,
  *     the IMMA accumulating straight into acc (s32 accumulation wraps, as everything here must);
- *     the CReLU half of the inputs is < 2^13, so its limbs 2 and 3 are skipped: 17 instead of 20
- *     contractions of length 32.
+ *     zero limbs are skipped (see the three forms at the L2 step below).
  */
-#ifndef SP_HEAD_PRODUCER
-#define SP_HEAD_PRODUCER 0 /* 1: a dedicated producer warp issues the bulk copies; 0: the warp that releases a stage refills it */
-#endif
 #ifndef SP_HEAD_CONSUMERS
-#define SP_HEAD_CONSUMERS (SP_HEAD_PRODUCER ? 11 : 8) /* 8 warps = two per scheduler at 255 registers (measured best); 12 = three at 168 */
+#define SP_HEAD_CONSUMERS 8 /* warps per CTA: two per scheduler at up to 255 registers (measured best; 12 = three at 168) */
 #endif
 #ifndef SP_HEAD_STAGES
 #define SP_HEAD_STAGES 5
 #endif
 constexpr int kHeadConsumers = SP_HEAD_CONSUMERS;
-constexpr bool kProducerWarp = SP_HEAD_PRODUCER != 0;
-constexpr int kStreamThreads = (kHeadConsumers + (kProducerWarp ? 1 : 0)) * 32;
+constexpr int kStreamThreads = kHeadConsumers * 32;
 constexpr int kTileRows = 32;
 constexpr int kTileRowStride = SP_L1_SIZE + 64;
 constexpr int kHeadStages = SP_HEAD_STAGES;
@@ -1517,15 +1514,12 @@ struct HeadStreamShared {
     __align__(16) uint4 w1[kW1Bytes / 16]; /* chunk (k-quad q, output quad g) at q * 8 + (g ^ ((q >> 2 & 3) << 1)) */
     __align__(16) uint2 w2[kW2Words / 2];  /* l2_fragment_index */
     __align__(8) uint64_t full[kHeadStages];
-    uint64_t empty[kHeadStages];
     uint32_t gen[kHeadStages]; /* tiles consumed so far on each stage */
     uint32_t rows[kHeadStages][kTileRows];
 };
 static_assert(sizeof(HeadStreamShared) <= 227 * 1024, "one CTA per SM");
+static_assert(kHeadConsumers >= kHeadStages, "the first kHeadStages warps request the first tiles");
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
@@ -1571,24 +1565,15 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
     if (t0 >= t1) return;
 
     if (tid == 0) {
-        for (int i = 0; i < kHeadStages; ++i) mbar_init(&sh.full[i], 1), mbar_init(&sh.empty[i], 1), sh.gen[i] = 0;
+        for (int i = 0; i < kHeadStages; ++i) mbar_init(&sh.full[i], 1), sh.gen[i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     auto issue_fill = [&](uint32_t n, uint32_t row) { head_issue_fill(sh, act, n, row, lane); };
     const uint32_t my_tiles = t1 - t0;
-    if (kProducerWarp) {
-        if (warp == kHeadConsumers) {
-            for (uint32_t n = 0; n < my_tiles; ++n) {
-                mbar_wait(&sh.empty[n % kHeadStages], ((n / kHeadStages) & 1) ^ 1);
-                issue_fill(n, sort.order[static_cast<size_t>(t0 + n) * kTileRows + lane]);
-            }
-            return;
-        }
-    } else if (warp < kHeadStages && static_cast<uint32_t>(warp) < my_tiles) {
-        /* no producer warp: the first kHeadStages tiles are requested here, every later tile by the warp that
-         * releases its stage (one issuing warp was the bottleneck: ~64 clk per copy, 32 copies per tile) */
+    if (warp < kHeadStages && static_cast<uint32_t>(warp) < my_tiles) {
+        /* the first kHeadStages tiles are requested here, every later tile by the warp that releases its stage */
         issue_fill(warp, sort.order[static_cast<size_t>(t0 + warp) * kTileRows + lane]);
     }
 
@@ -1626,7 +1611,7 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
             /* rows of the tile that will follow this one on the stage (requested once L1 is done) */
             const uint32_t refill = n + kHeadStages;
             uint32_t refill_row = kHeadNoRow;
-            if (!kProducerWarp && refill < my_tiles) refill_row = sort.order[static_cast<size_t>(t0 + refill) * kTileRows + lane];
+            if (refill < my_tiles) refill_row = sort.order[static_cast<size_t>(t0 + refill) * kTileRows + lane];
             mbar_wait(&sh.full[stage], (n / kHeadStages) & 1);
 
             /* ---- L1: 32 rows x 32 outputs, k = 1024 */
@@ -1666,17 +1651,10 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) row_id[mt][0] = sh.rows[stage][16 * mt + g], row_id[mt][1] = sh.rows[stage][16 * mt + g + 8];
             __syncwarp();
-            if (kProducerWarp) {
-                if (lane == 0) {
-                    *reinterpret_cast<volatile uint32_t*>(&sh.gen[stage]) = n / kHeadStages + 1;
-                    mbar_arrive(&sh.empty[stage]); /* the TMA engine may refill the stage */
-                }
-            } else {
-                /* order this warp's generic-proxy reads of the stage before the async-proxy writes that refill it */
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh.gen[stage]) = n / kHeadStages + 1;
-                if (refill < my_tiles) issue_fill(refill, refill_row);
-            }
+            /* order this warp's generic-proxy reads of the stage before the async-proxy writes that refill it */
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh.gen[stage]) = n / kHeadStages + 1;
+            if (refill < my_tiles) issue_fill(refill, refill_row);
 
             /* ---- L1 epilogue (multilayer.h:219-256), skip term of L3, L2 inputs as byte limbs in A-fragment order:
              * register index hrow + 2 cc = a0..a3 of an IMMA (row g | g+8, k-slots 4t.. | 16+4t..) */
