@@ -223,6 +223,8 @@ typedef struct SpSelfplayParams {
     uint32_t nodes_per_move; /* ... or once a finished iteration has used this many nodes (datagen.cpp:76 soft limit) */
     uint32_t max_plies;      /* undecided games are drawn here (0 = 300) */
     uint64_t seed;
+    uint32_t dfrc;           /* 1: `datagen <fmt> dfrc`: every game starts from a random double-Fischer-random position */
+    uint32_t reserved;       /* 0 */
 } SpSelfplayParams;
 typedef struct SpSelfplayStats {
     uint64_t games, positions, nodes, evals, batches, searches;
@@ -263,6 +265,8 @@ size_t sp_host_playouts(
     uint32_t* game_start);
 int sp_host_board_from_fen(const char* fen, SpPackedBoard* out);
 int sp_host_board_to_fen(const SpPackedBoard* board, char* out, size_t cap);
+/* Double Fischer random start position (Position::fromDfrcIndex, src/position.cpp:1215-1270): index = black * 960 + white */
+int sp_host_board_from_dfrc(uint32_t index, SpPackedBoard* out);
 int sp_host_legal_moves(const SpPackedBoard* board, SpMove* out /* [256] */);
 int sp_host_in_check(const SpPackedBoard* board); /* 1 / 0, -1 for a malformed record */
 int sp_host_apply_move(const SpPackedBoard* board, SpMove move, SpPackedBoard* out);

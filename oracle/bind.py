@@ -90,6 +90,7 @@ class Reference:
         L.spref_viriformat.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_int, _vp, C.c_size_t]
         L.spref_viriformat.restype = C.c_long
         L.spref_normalize_score.argtypes = [_vp, C.c_int32, _vp, _vp]
+        L.spref_board_from_dfrc.argtypes = [C.c_uint32, _vp]
         self._net = None
 
     @staticmethod
@@ -196,6 +197,12 @@ class Reference:
         rc = self.lib.spref_apply_move(_ptr(board), int(move), _ptr(out))
         if rc:
             raise RuntimeError("spref_apply_move failed")
+        return out
+
+    def board_from_dfrc(self, index: int) -> np.ndarray:
+        out = np.zeros(1, dtype=BOARD_DTYPE)
+        if self.lib.spref_board_from_dfrc(int(index), _ptr(out)):
+            raise RuntimeError("spref_board_from_dfrc failed")
         return out
 
     def viriformat(self, start: np.ndarray, moves, scores, outcome: int) -> np.ndarray:

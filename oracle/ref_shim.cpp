@@ -556,6 +556,17 @@ int spref_board_from_fen(const char* fen, SpPackedBoard* out) {
     return 0;
 }
 
+// Position::fromDfrcIndex (src/position.cpp:1215-1270)
+int spref_board_from_dfrc(uint32_t index, SpPackedBoard* out) {
+    opts::mutableOpts().chess960 = true;
+    const auto pos = Position::fromDfrcIndex(index);
+    if (!pos) {
+        return 1;
+    }
+    *out = pack(*pos);
+    return 0;
+}
+
 // One game through the reference's own Viriformat writer (src/datagen/viriformat.cpp:27-63): start(),
 // push() per (move, score), writeAllWithOutcome().  Returns the bytes written, or -1.
 long spref_viriformat(

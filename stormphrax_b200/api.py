@@ -70,6 +70,7 @@ SIGNATURES = {
     "sp_host_playouts": (_sz, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp]),
     "sp_host_board_from_fen": (C.c_int, [C.c_char_p, _vp]),
     "sp_host_board_to_fen": (C.c_int, [_vp, C.c_char_p, _sz]),
+    "sp_host_board_from_dfrc": (C.c_int, [C.c_uint32, _vp]),
     "sp_host_legal_moves": (C.c_int, [_vp, _vp]),
     "sp_host_in_check": (C.c_int, [_vp]),
     "sp_host_apply_move": (C.c_int, [_vp, C.c_uint16, _vp]),
@@ -314,6 +315,14 @@ def board_from_fen(fen: str) -> np.ndarray:
     return out
 
 
+def board_from_dfrc(index: int) -> np.ndarray:
+    out = np.zeros(1, dtype=BOARD_DTYPE)
+    rc = lib().sp_host_board_from_dfrc(int(index), out.ctypes.data)
+    if rc:
+        raise NnueError(rc, "bad DFRC index")
+    return out
+
+
 def board_to_fen(board) -> str:
     board = _boards(board).reshape(1)
     buf = C.create_string_buffer(128)
@@ -407,6 +416,8 @@ class SelfplayParams(C.Structure):
         ("nodes_per_move", C.c_uint32),
         ("max_plies", C.c_uint32),
         ("seed", C.c_uint64),
+        ("dfrc", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 
@@ -415,11 +426,11 @@ class SelfplayStats(C.Structure):
 
 
 def selfplay(net_image, device: int = 0, *, concurrency: int = 1024, total_games: int = 1024, threads: int = 1, depth: int = 3,
-             nodes_per_move: int = 5000, max_plies: int = 300, seed: int = 42, capacity: int | None = None, resident: bool = False):
+             nodes_per_move: int = 5000, max_plies: int = 300, seed: int = 42, capacity: int | None = None, resident: bool = False, dfrc: bool = False):
     """Batched self-play (sp_selfplay_run; resident=True: sp_selfplay_run_gpu, the games' searches run on the device too).
     Returns (viriformat bytes as uint8 array, stats dict)."""
     img = np.ascontiguousarray(net_image, dtype=np.uint8)
-    p = SelfplayParams(concurrency, total_games, threads, depth, nodes_per_move, max_plies, seed)
+    p = SelfplayParams(concurrency, total_games, threads, depth, nodes_per_move, max_plies, seed, int(dfrc), 0)
     st = SelfplayStats()
     cap = capacity if capacity is not None else total_games * (32 + 4 * (max_plies + 2))
     out = np.empty(cap, dtype=np.uint8)

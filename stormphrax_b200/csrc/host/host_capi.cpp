@@ -119,6 +119,12 @@ int sp_host_legal_moves(const SpPackedBoard* board, SpMove* out) {
     return n;
 }
 
+int sp_host_board_from_dfrc(uint32_t index, SpPackedBoard* out) {
+    if (!out || index >= 960u * 960u) return SP_ERR_INVALID;
+    *out = Position::fromDfrcIndex(index).pack();
+    return SP_OK;
+}
+
 int sp_host_in_check(const SpPackedBoard* board) {
     Position p;
     if (!Position::fromPacked(*board, p)) return -1;

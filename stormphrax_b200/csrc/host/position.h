@@ -69,6 +69,9 @@ public:
     }
 
     static Position startpos();
+    /* Double Fischer random start position n = black * 960 + white, both sides numbered by Scharnagl's
+     * scheme (src/position.cpp:38-100, 1215-1270); n < 960 * 960.  518 * 960 + 518 is the standard one. */
+    SP_POS_HD static Position fromDfrcIndex(uint32_t n);
     static bool fromFen(const std::string& fen, Position& out);
     static bool fromPacked(const SpPackedBoard& packed, Position& out);
     [[nodiscard]] SP_POS_HD SpPackedBoard pack() const;
@@ -347,6 +350,54 @@ SP_POS_HD inline int Position::generatePseudo(Move* pseudo) const {
         }
     }
     return n;
+}
+
+/* Scharnagl's direct derivation of back rank n (0..959), files a..h: bishops from n mod 4 and (n / 4) mod 4
+ * on their own square colours, the queen on the ((n / 16) mod 6)-th free file, the knights on the pair of
+ * free files numbered n / 96 (0..9: 01 02 03 04 12 13 14 23 24 34), rook, king, rook on what is left. */
+SP_POS_HD inline void scharnagl_backrank(uint32_t n, int (&rank)[8]) {
+    for (int& t : rank) t = -1;
+    auto nthFree = [&](int k) {
+        for (int f = 0; f < 8; ++f)
+            if (rank[f] < 0 && k-- == 0) return f;
+        return 7;
+    };
+    rank[2 * (n % 4) + 1] = kBishop;
+    n /= 4;
+    rank[2 * (n % 4)] = kBishop;
+    n /= 4;
+    rank[nthFree(static_cast<int>(n % 6))] = kQueen;
+    n /= 6;
+    /* the n-th pair (a, b), a < b, of the five free files in lexicographic order */
+    int a = 0, b = 1;
+    for (uint32_t k = 0; k < n; ++k)
+        if (++b == 5) ++a, b = a + 1;
+    const int fa = nthFree(a), fb = nthFree(b);
+    rank[fa] = kKnight, rank[fb] = kKnight;
+    rank[nthFree(0)] = kRook;
+    rank[nthFree(0)] = kKing;
+    rank[nthFree(0)] = kRook;
+}
+
+SP_POS_HD inline Position Position::fromDfrcIndex(uint32_t n) {
+    Position p;
+    int back[2][8]; /* [color] */
+    scharnagl_backrank(n % 960, back[kWhite]);
+    scharnagl_backrank((n / 960) % 960, back[kBlack]);
+    for (Color c = 0; c < 2; ++c) {
+        const int base = c == kWhite ? 0 : 56, pawns = c == kWhite ? 8 : 48;
+        bool firstRook = true;
+        for (int f = 0; f < 8; ++f) {
+            p.put(kPawn << 1 | c, pawns + f);
+            p.put(back[c][f] << 1 | c, base + f);
+            if (back[c][f] == kKing) p.m_king[c] = base + f;
+            if (back[c][f] == kRook) { /* the rook on the lower file castles queenside */
+                p.m_rooks[c][firstRook ? 1 : 0] = base + f;
+                firstRook = false;
+            }
+        }
+    }
+    return p;
 }
 
 /* squares strictly between two aligned squares (0 if they share no rank, file or diagonal) */

@@ -144,6 +144,7 @@ struct Params {
     uint32_t nodesPerMove = 5000; /* ... or once a finished iteration has used this many nodes (soft limit, datagen.cpp:76) */
     uint32_t maxPlies = 300;      /* games still undecided are drawn here (stands in for repetition detection); at most 510 */
     uint64_t seed = 42;
+    uint32_t dfrc = 0;            /* 1: every game starts from a random double-Fischer-random position (datagen.cpp:146-148) */
     uint32_t slotBegin = 0, slotEnd = 0; /* the slots THIS driver instance plays (a host thread's share); 0, 0 = all */
     Position start;               /* the start position (Position::startpos(), built on the host) */
 
@@ -173,6 +174,7 @@ inline Params makeParams(const SpSelfplayParams& in) {
     p.nodesPerMove = in.nodes_per_move;
     p.maxPlies = in.max_plies ? (in.max_plies > kMaxRecordMoves - 2 ? kMaxRecordMoves - 2 : in.max_plies) : 300;
     p.seed = in.seed;
+    p.dfrc = in.dfrc ? 1 : 0;
     p.start = Position::startpos();
     return p;
 }
@@ -249,9 +251,9 @@ private:
     };
 
     SP_POS_HD void newGame() {
-        /* datagen.cpp:146-178: 8 or 9 random plies from the start position; start over on a dead end */
+        /* datagen.cpp:146-178: 8 or 9 random plies from the (standard or random DFRC) start position; start over on a dead end */
         for (;;) {
-            m_pos = m_params.start;
+            m_pos = m_params.dfrc ? Position::fromDfrcIndex(m_rng.below(960u * 960u)) : m_params.start;
             const uint32_t plies = 8 + static_cast<uint32_t>(m_rng.next() >> 63);
             bool dead = false;
             Move moves[256];

@@ -129,10 +129,7 @@ struct Recursive {
     }
 };
 
-int main() {
-    selfplay::Params params;
-    params.start = Position::startpos();
-    params.concurrency = 24, params.totalGames = 60, params.depth = 3, params.nodesPerMove = 400, params.maxPlies = 120, params.seed = 7;
+static int run(const selfplay::Params& params) {
     StandInEvaluator evaluator;
     selfplay::Driver<StandInEvaluator> driver{params, evaluator};
     std::vector<uint8_t> out;
@@ -184,8 +181,19 @@ int main() {
     }
     EXPECT(games == params.totalGames, "parsed %zu records", games);
     EXPECT(positions == stats.positions, "parsed %zu positions, driver counted %llu", positions, static_cast<unsigned long long>(stats.positions));
-    std::printf("%zu games, %zu positions, %llu nodes, %llu evals in %llu batches (%.1f per batch), %zu searches re-checked, %d failures\n", games,
+    std::printf("%s: %zu games, %zu positions, %llu nodes, %llu evals in %llu batches (%.1f per batch), %zu searches re-checked, %d failures\n",
+                params.dfrc ? "dfrc" : "standard", games,
                 positions, static_cast<unsigned long long>(stats.nodes), static_cast<unsigned long long>(stats.evals),
                 static_cast<unsigned long long>(stats.batches), static_cast<double>(stats.evals) / static_cast<double>(stats.batches), compared, g_failures);
     return g_failures ? 1 : 0;
+}
+
+int main() {
+    selfplay::Params params;
+    params.start = Position::startpos();
+    params.concurrency = 24, params.totalGames = 40, params.depth = 3, params.nodesPerMove = 400, params.maxPlies = 120, params.seed = 7;
+    int rc = run(params);
+    params.dfrc = 1, params.totalGames = 30, params.seed = 8; /* `datagen dfrc`: Chess960 castling through search, records and replay */
+    rc |= run(params);
+    return rc;
 }

@@ -187,6 +187,13 @@ def test_gpu_resident_selfplay_plays_the_same_games_as_the_host_driver(net):
     # three concurrent driver instances (slot ranges) on the same device: still the same bytes
     dev3, sd3 = api.selfplay(net.image, 0, resident=True, threads=3, **kw)
     assert np.array_equal(host, dev3) and sd3["evals"] == sh["evals"]
+    # `datagen dfrc`: random double-Fischer-random starts (Chess960 castling through the whole stack)
+    kw = dict(concurrency=48, total_games=60, depth=2, nodes_per_move=200, max_plies=40, seed=5, dfrc=True)
+    host, sh = api.selfplay(net.image, 0, threads=2, **kw)
+    dev, sd = api.selfplay(net.image, 0, resident=True, **kw)
+    assert np.array_equal(host, dev) and sh["evals"] == sd["evals"]
+    starts = {api.board_to_fen(g[0]).split()[0] for g in api.parse_viriformat(dev)}
+    assert len(starts) > 50  # (almost) every game has its own start position
 
 
 def _golden_datagen():
@@ -217,6 +224,13 @@ def test_viriformat_records_match_reference_golden():
                 b = api.apply_move(b, int(moves[lo + j]))[0]
             k += 1
     assert k == len(d["viri_outcome"])
+
+
+def test_dfrc_start_positions_match_reference_golden():
+    d, _ = _golden_datagen()
+    for i, want in zip(d["dfrc_index"], d["dfrc_boards"]):
+        assert api.board_from_dfrc(int(i))[0].tobytes() == want.tobytes(), int(i)
+    assert api.board_to_fen(api.board_from_dfrc(518 * 960 + 518)).startswith("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w")
 
 
 def test_normalize_score_matches_reference_golden():
