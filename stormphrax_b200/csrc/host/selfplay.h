@@ -152,12 +152,12 @@ struct Params {
     [[nodiscard]] SP_POS_HD uint32_t firstSlot() const { return slotEnd > slotBegin ? slotBegin : 0; }
 
     [[nodiscard]] SP_POS_HD uint32_t gamesOfSlot(uint32_t slot) const { return totalGames / concurrency + (slot < totalGames % concurrency ? 1 : 0); }
-    /* every (slot, game number) has its own random stream, whichever driver or thread plays it */
+    /* Every (slot, game number) has its own random stream, whichever driver or thread plays it.  (slot and k
+     * enter through different odd multipliers, neither of them SplitMix64's own increment: stepping one
+     * generator per slot made game k of slot g the same game as game 0 of slot g + k.) */
     [[nodiscard]] SP_POS_HD uint64_t gameSeed(uint32_t slot, uint32_t k) const {
-        SplitMix64 mix{seed + 0x9E3779B97F4A7C15ULL * (uint64_t{slot} + 1)};
-        uint64_t v = mix.next();
-        for (uint32_t i = 0; i < k; ++i) v = mix.next();
-        return v;
+        SplitMix64 mix{seed ^ (0xD1B54A32D192ED03ULL * (uint64_t{slot} + 1)) ^ (0x8CB92BA72F3D8DD7ULL * (uint64_t{k} + 1))};
+        return mix.next();
     }
 };
 

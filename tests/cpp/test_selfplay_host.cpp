@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <string>
 
 #include "../../stormphrax_b200/csrc/host/selfplay.h"
 
@@ -143,7 +144,9 @@ static int run(const selfplay::Params& params) {
 
     /* ---- records: replay, and re-search every recorded position with the recursive search */
     size_t at = 0, games = 0, positions = 0, compared = 0;
+    std::map<std::string, int> seen; /* record bytes -> count: every game must have its own random stream */
     while (at < out.size()) {
+        const size_t record_begin = at;
         SpPackedBoard initial;
         std::memcpy(&initial, out.data() + at, sizeof(initial));
         at += sizeof(initial);
@@ -177,6 +180,7 @@ static int run(const selfplay::Params& params) {
             pos = pos.applyMove(played);
             ++positions;
         }
+        EXPECT(++seen[std::string(out.begin() + static_cast<long>(record_begin), out.begin() + static_cast<long>(at))] == 1, "record %zu: the same game was played twice", games);
         ++games;
     }
     EXPECT(games == params.totalGames, "parsed %zu records", games);
