@@ -185,7 +185,7 @@ def test_gpu_resident_selfplay_plays_the_same_games_as_the_host_driver(net):
     assert np.array_equal(host, dev)
     for k in ("games", "positions", "nodes", "evals", "searches"):
         assert sh[k] == sd[k], (k, sh[k], sd[k])
-    assert sd["evals"] / sd["batches"] > 40  # one device batch per round of all running games
+    assert sd["evals"] / sd["batches"] > 12  # one device batch per round of all running games (96 slots, long tail)
     # three concurrent driver instances (slot ranges) on the same device: still the same bytes
     dev3, sd3 = api.selfplay(net.image, 0, resident=True, threads=3, **kw)
     assert np.array_equal(host, dev3) and sd3["evals"] == sh["evals"]
