@@ -247,8 +247,11 @@ extern "C" int sp_selfplay_run_gpu(
     int prev_device = 0;
     cudaGetDevice(&prev_device);
     cudaSetDevice(device);
-    /* the games' search runs per thread on its own stack: move lists and board copies */
-    cudaDeviceSetLimit(cudaLimitStackSize, 8 * 1024);
+    /* the games' search runs per thread on its own stack (move lists, board copies: 2 KB measured); the
+     * caller's limit is put back afterwards */
+    size_t prev_stack = 0;
+    cudaDeviceGetLimit(&prev_stack, cudaLimitStackSize);
+    cudaDeviceSetLimit(cudaLimitStackSize, std::max<size_t>(prev_stack, 8 * 1024));
     std::vector<Stats> totals(instances);
     std::vector<uint64_t> batches(instances, 0);
     std::vector<std::vector<uint8_t>> records(instances);
@@ -262,6 +265,7 @@ extern "C" int sp_selfplay_run_gpu(
             rcs[t] = run_instance(net_image, len, device, p, totals[t], batches[t], records[t]);
         });
     for (auto& th : pool) th.join();
+    if (prev_stack) cudaDeviceSetLimit(cudaLimitStackSize, prev_stack);
     cudaSetDevice(prev_device);
     int rc = SP_OK;
     size_t total = 0;
