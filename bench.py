@@ -128,14 +128,14 @@ class ClockSampler:
 
 # ------------------------------------------------------------------ CPU side (reference arm / cpu_baseline)
 
-def cpu_arm(boards, moves, starts, workload: str, budget_s: float):
+def cpu_arm(boards, moves, starts, workload: str, budget_s: float, threads: int | None = None):
     """Time the reference's own CPU code (oracle/_ref) -- or the C port if it cannot run here --
-    on a bounded prefix of the workload using every host core.  Returns (pos_per_s, info)."""
+    on a bounded prefix of the workload using every host core (or `threads`).  Returns (pos_per_s, info)."""
     from oracle.bind import COracle, Reference
     from stormphrax_b200 import net as N
 
     image = N.synthetic(NET_SEED).image
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     if Reference.available():
         ref = Reference()
         ref.load_net(image)
@@ -174,12 +174,15 @@ def run_reference(args, rank: int, world: int):
             rates.append(rate)
     value = float(np.mean(rates)) / 1e6
     n_sample = info["positions"]
+    # BASELINE configs[0]'s analogue: the same reference code on ONE host thread
+    one_rate, one_info = cpu_arm(boards, moves, starts, args.workload, 3.0, threads=1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * info["seconds"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int16/int8/int32", "data": "synthetic",
         "config": workload_config(args.workload, sample_positions=n_sample),
-        "cpu_baseline": {"value": value, "unit": UNIT, **{k: info[k] for k in ("cores", "kind", "sample", "isa")}},
+        "cpu_baseline": {"value": value, "unit": UNIT, **{k: info[k] for k in ("cores", "kind", "sample", "isa")},
+                         "single_thread": {"value": one_rate / 1e6, "unit": UNIT, "sample": one_info["sample"]}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
