@@ -150,3 +150,15 @@ def test_delta_generator_equals_feature_set_difference(c_oracle, golden, key):
                         key, g, i, c, kind, api.board_to_fen(boards[i]), api.board_to_fen(boards[i + 1]))
                 checked += 1
     assert checked > 1000 and refreshes > 0
+
+
+def test_board_records_round_trip_through_the_board_model(golden):
+    """marlinformat record -> Position -> FEN -> Position -> record is the identity on every golden board (standard
+    and Chess960 castling rights, en passant squares, clocks); the eval / wdl / extra fields are not board state."""
+    for boards in (golden["boards"][::3], golden["dfrc_boards"][::3], golden["fen_boards"]):
+        for b in boards:
+            fen = api.board_to_fen(b)
+            again = api.board_from_fen(fen)[0]
+            for field in ("occupancy", "pieces", "stm_ep", "halfmove", "fullmove"):
+                assert np.array_equal(again[field], b[field]), (fen, field)
+            assert api.board_to_fen(again) == fen
