@@ -248,6 +248,8 @@ long sp_host_viriformat(
 /* wdl::normalizeScore<false>(score, pos.classicalMaterial()) as the driver's adjudication uses it
  * (src/wdl.cpp:28-80, src/position.h:515-523). */
 int sp_host_normalize_score(const SpPackedBoard* board, int32_t score, int32_t* material, int32_t* normalized);
+/* wdl::wdlModel(povScore, pos.classicalMaterial()): win and loss per mille (src/wdl.cpp:43-50; UCI output) */
+int sp_host_wdl_model(const SpPackedBoard* board, int32_t pov_score, int32_t* win, int32_t* loss);
 
 /* ---------------------------------------------------------------- host utilities (no GPU)
  * Workload generation and CPU execution of the shared feature code, for tests and benchmarks. */
@@ -269,6 +271,9 @@ int sp_host_board_to_fen(const SpPackedBoard* board, char* out, size_t cap);
 int sp_host_board_from_dfrc(uint32_t index, SpPackedBoard* out);
 int sp_host_legal_moves(const SpPackedBoard* board, SpMove* out /* [256] */);
 int sp_host_in_check(const SpPackedBoard* board); /* 1 / 0, -1 for a malformed record */
+/* adjustStatic + adjustEval through the C++ mirror's per-position form (csrc/host/nnue_state.h), on the host:
+ * same arguments and results as sp_nnue_adjust */
+int sp_host_adjust(const SpPackedBoard* boards, const int32_t* raw, const int32_t* correction, size_t n, const SpAdjustParams* params, int32_t* out);
 int sp_host_apply_move(const SpPackedBoard* board, SpMove move, SpPackedBoard* out);
 int sp_host_features(const SpPackedBoard* board, int perspective, int kind, uint32_t* out /* [512] */);
 /* Workload statistics for the roofline: out[0] = PSQ rows, out[1] = threat rows, out[2] = pawn-pair

@@ -91,6 +91,7 @@ class Reference:
         L.spref_viriformat.restype = C.c_long
         L.spref_normalize_score.argtypes = [_vp, C.c_int32, _vp, _vp]
         L.spref_board_from_dfrc.argtypes = [C.c_uint32, _vp]
+        L.spref_wdl_model.argtypes = [_vp, C.c_int32, _vp, _vp]
         self._net = None
 
     @staticmethod
@@ -198,6 +199,14 @@ class Reference:
         if rc:
             raise RuntimeError("spref_apply_move failed")
         return out
+
+    def wdl_model(self, board: np.ndarray, score: int):
+        """wdl::wdlModel(score, pos.classicalMaterial()) -> (win, loss) per mille"""
+        board = np.ascontiguousarray(board, dtype=BOARD_DTYPE).reshape(1)
+        win, loss = C.c_int32(), C.c_int32()
+        if self.lib.spref_wdl_model(_ptr(board), int(score), C.byref(win), C.byref(loss)):
+            raise RuntimeError("spref_wdl_model failed")
+        return win.value, loss.value
 
     def board_from_dfrc(self, index: int) -> np.ndarray:
         out = np.zeros(1, dtype=BOARD_DTYPE)

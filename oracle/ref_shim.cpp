@@ -556,6 +556,19 @@ int spref_board_from_fen(const char* fen, SpPackedBoard* out) {
     return 0;
 }
 
+// wdl::wdlModel(povScore, pos.classicalMaterial()) (src/wdl.cpp:43-50)
+int spref_wdl_model(const SpPackedBoard* board, int32_t score, int32_t* win, int32_t* loss) {
+    opts::mutableOpts().chess960 = true;
+    Position pos;
+    if (!toPosition(*board, pos)) {
+        return 1;
+    }
+    const auto [w, l] = wdl::wdlModel(score, pos.classicalMaterial());
+    *win = w;
+    *loss = l;
+    return 0;
+}
+
 // Position::fromDfrcIndex (src/position.cpp:1215-1270)
 int spref_board_from_dfrc(uint32_t index, SpPackedBoard* out) {
     opts::mutableOpts().chess960 = true;

@@ -73,6 +73,7 @@ SIGNATURES = {
     "sp_host_board_from_dfrc": (C.c_int, [C.c_uint32, _vp]),
     "sp_host_legal_moves": (C.c_int, [_vp, _vp]),
     "sp_host_in_check": (C.c_int, [_vp]),
+    "sp_host_adjust": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "sp_host_apply_move": (C.c_int, [_vp, C.c_uint16, _vp]),
     "sp_host_features": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "sp_host_feature_delta": (C.c_int, [_vp, _vp, C.c_int] + [_vp] * 8),
@@ -81,6 +82,7 @@ SIGNATURES = {
     "sp_nnue_batch_device": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp]),
     "sp_host_viriformat": (C.c_long, [_vp, _vp, _vp, C.c_uint32, C.c_int, _vp, _sz]),
     "sp_host_normalize_score": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
+    "sp_host_wdl_model": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
 }
 
 
@@ -341,6 +343,18 @@ def legal_moves(board) -> np.ndarray:
     return out[:n].copy()
 
 
+def host_adjust(boards, raw, params: "AdjustParams", correction=None) -> np.ndarray:
+    """adjustStatic + adjustEval through the C++ mirror's per-position form, on the host (sp_host_adjust)."""
+    boards = _boards(boards)
+    raw = np.ascontiguousarray(raw, dtype=np.int32)
+    corr = None if correction is None else np.ascontiguousarray(correction, dtype=np.int32)
+    out = np.empty(len(boards), dtype=np.int32)
+    rc = lib().sp_host_adjust(boards.ctypes.data, raw.ctypes.data, None if corr is None else corr.ctypes.data, len(boards), C.byref(params), out.ctypes.data)
+    if rc:
+        raise NnueError(rc, "sp_host_adjust failed")
+    return out
+
+
 def in_check(board) -> bool:
     rc = lib().sp_host_in_check(_boards(board).ctypes.data)
     if rc < 0:
@@ -486,3 +500,12 @@ def normalize_score(board, score: int):
     if rc:
         raise NnueError(rc, "bad board")
     return material.value, norm.value
+
+
+def wdl_model(board, pov_score: int):
+    """(win, loss) per mille of a side-to-move score (sp_host_wdl_model)."""
+    win, loss = C.c_int32(), C.c_int32()
+    rc = lib().sp_host_wdl_model(_boards(board).ctypes.data, int(pov_score), C.byref(win), C.byref(loss))
+    if rc:
+        raise NnueError(rc, "bad board")
+    return win.value, loss.value

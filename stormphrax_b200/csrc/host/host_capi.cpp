@@ -14,6 +14,7 @@
 #include "../../../include/sp_nnue.h"
 #include "../sp_delta.h"
 #include "../sp_features.h"
+#include "nnue_state.h"
 #include "position.h"
 #include "rng.h"
 
@@ -122,6 +123,22 @@ int sp_host_legal_moves(const SpPackedBoard* board, SpMove* out) {
 int sp_host_board_from_dfrc(uint32_t index, SpPackedBoard* out) {
     if (!out || index >= 960u * 960u) return SP_ERR_INVALID;
     *out = Position::fromDfrcIndex(index).pack();
+    return SP_OK;
+}
+
+/* adjustStatic + adjustEval of the C++ mirror (host/nnue_state.h) on an array: the host counterpart of
+ * sp_nnue_adjust, used by the tests */
+int sp_host_adjust(const SpPackedBoard* boards, const int32_t* raw, const int32_t* correction, size_t n, const SpAdjustParams* params, int32_t* out) {
+    if (!boards || !raw || !params || !out) return SP_ERR_INVALID;
+    for (size_t i = 0; i < n; ++i) {
+        const int stm = (boards[i].stm_ep & 0x80) ? kBlack : kWhite;
+        eval::Contempt contempt;
+        contempt.value[0] = params->contempt[0], contempt.value[1] = params->contempt[1];
+        eval::Optimism optimism;
+        optimism.value[0] = params->optimism[0], optimism.value[1] = params->optimism[1];
+        const int32_t adjusted = eval::adjustStatic(raw[i], stm, contempt);
+        out[i] = eval::adjustEvalPacked(boards[i], optimism, adjusted, correction ? correction[i] : 0, *params);
+    }
     return SP_OK;
 }
 

@@ -174,6 +174,39 @@ SP_POS_HD inline i32 adjustStatic(i32 eval, Color stm, const Contempt& contempt)
     return eval < -kScoreWin + 1 ? -kScoreWin + 1 : (eval > kScoreWin - 1 ? kScoreWin - 1 : eval);
 }
 
+/* eval::adjustEval (src/eval/eval.cpp:31-67) for ONE position, the form the search calls per node: material
+ * scaling, optimism, 50-move damping, correction, clamp.  `correction` is what the caller's
+ * CorrectionHistoryTable::correction(pos, keyHistory) returned (0 = adjustEval<false>).  Batches go through
+ * sp_nnue_adjust on the device; this is the same arithmetic on the host (checked against the same
+ * reference-generated vectors, tests/test_host.py). */
+struct Optimism {
+    i32 value[2]{0, 0};
+    i32 operator[](Color c) const { return value[c]; }
+};
+
+inline i32 adjustEvalPacked(const SpPackedBoard& board, const Optimism& optimism, i32 eval, i32 correction, const SpAdjustParams& tunables) {
+    int material = 0, k = 0;
+    for (uint64_t occ = board.occupancy; occ && k < 32; occ &= occ - 1, ++k) {
+        unsigned type = (board.pieces[k / 2] >> ((k % 2) * 4)) & 7;
+        if (type == 6) type = kRook; /* rook with castling rights */
+        if (type < static_cast<unsigned>(kKing)) material += tunables.scaling_value[type];
+    }
+    const Color stm = (board.stm_ep & 0x80) ? kBlack : kWhite;
+    eval = (eval * (tunables.material_scaling_base + material)
+            + optimism[stm] * (tunables.optimism_base + material * tunables.optimism_material_scale / 1024))
+         / 32768;
+    eval = eval * (200 - static_cast<i32>(board.halfmove)) / 200;
+    eval += correction / 2048;
+    return eval < -kScoreWin + 1 ? -kScoreWin + 1 : (eval > kScoreWin - 1 ? kScoreWin - 1 : eval);
+}
+
+template <typename Position>
+i32 adjustEval(const Position& pos, const Optimism& optimism, i32 eval, i32 correction = 0) {
+    SpAdjustParams tunables;
+    sp_nnue_adjust_defaults(&tunables);
+    return adjustEvalPacked(pos.pack(), optimism, eval, correction, tunables);
+}
+
 template <typename Position> i32 staticEval(const Position& pos, NnueState& state, const Contempt& contempt = {}) {
     return adjustStatic(state.evaluate(pos, pos.stm()), pos.stm(), contempt);
 }

@@ -78,3 +78,10 @@ extern "C" int sp_host_normalize_score(const SpPackedBoard* board, int32_t score
     *normalized = selfplay::normalizeScore(score, *material);
     return SP_OK;
 }
+
+extern "C" int sp_host_wdl_model(const SpPackedBoard* board, int32_t pov_score, int32_t* win, int32_t* loss) {
+    Position pos;
+    if (!board || !win || !loss || !Position::fromPacked(*board, pos)) return SP_ERR_BAD_BOARD;
+    selfplay::wdlModel(pov_score, selfplay::classicalMaterial(pos), *win, *loss);
+    return SP_OK;
+}

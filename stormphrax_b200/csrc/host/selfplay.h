@@ -92,6 +92,26 @@ SP_POS_HD inline i32 normalizeScore(i32 score, int material) {
 #endif
 }
 
+/* wdl::wdlModel (src/wdl.cpp:43-50): win / loss per mille of a side-to-move score, the logistic of
+ * (score -+ a) / b with a, b the two material cubics of wdl::wdlParams.  Host only (UCI / report output). */
+inline void wdlModel(i32 povScore, int material, i32& win, i32& loss) {
+    const double m = static_cast<double>(material < 17 ? 17 : (material > 78 ? 78 : material)) / 58.0;
+    auto cubic = [m](double c0, double c1, double c2, double c3) { /* Horner, one rounding per operation */
+        volatile double v = c0 * m;
+        v = v + c1;
+        v = v * m;
+        v = v + c2;
+        v = v * m;
+        v = v + c3;
+        return static_cast<double>(v);
+    };
+    const double a = cubic(-244.97139595, 687.39969858, -654.38002091, 608.47087786);
+    const double b = cubic(68.24072080, -111.17718819, 74.50316570, 71.16566713);
+    const double x = static_cast<double>(povScore);
+    win = static_cast<i32>(std::round(1000.0 / (1.0 + std::exp((a - x) / b))));
+    loss = static_cast<i32>(std::round(1000.0 / (1.0 + std::exp((a + x) / b))));
+}
+
 /* One game in viriformat (src/datagen/viriformat.cpp:33-63): the 32-byte start record with the outcome in
  * `wdl`, then (move, score) pairs of 4 bytes, then 4 zero bytes. */
 SP_POS_HD inline uint16_t viriMove(Move m) {

@@ -38,12 +38,14 @@ def main() -> None:
     rng = np.random.default_rng(42)
     scores = np.concatenate([rng.integers(-3000, 3001, len(nb) - 8), [0, 1, -1, 30000, 30001, -30001, 24999, -24999]]).astype(np.int32)
     mat, norm = zip(*(ref.normalize_score(b, int(s)) for b, s in zip(nb, scores)))
+    # win / loss per mille (wdl::wdlModel) on the same boards and scores
+    wdl = np.array([ref.wdl_model(b, int(s)) for b, s in zip(nb, scores)], dtype=np.int32)
     # double-Fischer-random start positions (Position::fromDfrcIndex)
     dfrc_index = np.unique(np.concatenate([np.arange(0, 960 * 960, 1543), [0, 518 * 960 + 518, 960 * 960 - 1, 959, 960, 518]])).astype(np.uint32)
     dfrc_boards = np.concatenate([ref.board_from_dfrc(int(i)) for i in dfrc_index])
     np.savez_compressed(
         os.path.join(HERE, "datagen_seed42.npz"),
-        dfrc_index=dfrc_index, dfrc_boards=dfrc_boards,
+        dfrc_index=dfrc_index, dfrc_boards=dfrc_boards, wdl_model=wdl,
         viri=np.concatenate(records), viri_off=np.array(offsets, dtype=np.uint32), viri_outcome=np.array(outcomes, dtype=np.uint8),
         norm_boards=nb, norm_scores=scores, norm_material=np.array(mat, dtype=np.int32), norm_out=np.array(norm, dtype=np.int32),
     )

@@ -162,3 +162,20 @@ def test_board_records_round_trip_through_the_board_model(golden):
             for field in ("occupancy", "pieces", "stm_ep", "halfmove", "fullmove"):
                 assert np.array_equal(again[field], b[field]), (fen, field)
             assert api.board_to_fen(again) == fen
+
+
+def test_host_adjust_eval_matches_reference_golden():
+    """The C++ mirror's per-position adjustStatic + adjustEval (host/nnue_state.h) on the vectors the reference's own
+    staticEvalOnce / adjustEval<false> produced, and with a correction term against the restated arithmetic."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "adjust_seed42.npz"))
+    boards, raw = g["adjust_boards"], g["adjust_raw"]
+    for k in range(3):
+        c0, c1, o0, o1 = (int(x) for x in g[f"adjust_params{k}"])
+        params = api.AdjustParams.defaults(contempt=(c0, c1), optimism=(o0, o1))
+        assert (api.host_adjust(boards, raw, params) == g[f"adjust_out{k}"]).all(), k
+    corr = np.random.default_rng(4).integers(-300000, 300000, len(boards)).astype(np.int32)
+    base = g["adjust_out0"].astype(np.int64)
+    want = np.clip(base + np.trunc(corr / 2048).astype(np.int64), -24999, 24999)
+    inside = np.abs(base) < 24999  # where the golden value was not clamped, the pre-clamp value is known
+    got = api.host_adjust(boards, raw, api.AdjustParams.defaults(), correction=corr)
+    assert (got[inside] == want[inside]).all()

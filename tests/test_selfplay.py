@@ -228,6 +228,12 @@ def test_viriformat_records_match_reference_golden():
     assert k == len(d["viri_outcome"])
 
 
+def test_wdl_model_matches_reference_golden():
+    d, _ = _golden_datagen()
+    for b, s, want in zip(d["norm_boards"], d["norm_scores"], d["wdl_model"]):
+        assert api.wdl_model(b, int(s)) == (int(want[0]), int(want[1])), (api.board_to_fen(b), int(s))
+
+
 def test_dfrc_start_positions_match_reference_golden():
     d, _ = _golden_datagen()
     for i, want in zip(d["dfrc_index"], d["dfrc_boards"]):
