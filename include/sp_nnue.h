@@ -209,19 +209,22 @@ int sp_nnue_batch_device(
  * Replaces the per-thread game loop of src/datagen/datagen.cpp:96-321 (`datagen::run`, :323-400): random
  * opening plies, search -> applyMove -> NnueState::applyImmediately -> (move, score) until the game is
  * decided or adjudicated, one viriformat record per game (src/datagen/viriformat.cpp:33-63).  Instead of
- * one game per thread, `concurrency` games run at once (split over `threads` host threads, each with its
- * own evaluator context on `device`); their searches are resumable and every static evaluation they ask
- * for is answered in device batches through the NnueState / EvalBatch mirror.  The search itself is a
- * stand-in (iterative-deepening alpha-beta, csrc/host/selfplay.h): the reference's search is out of scope.
- * `out` receives the concatenated records (thread by thread, completion order); *out_len is always set to
- * the bytes produced (SP_ERR_CAPACITY if they did not fit; out == NULL with out_capacity == 0 only counts). */
+ * one game per thread there are `concurrency` game slots playing at once (split into contiguous ranges over
+ * `threads` host threads, each with its own evaluator context on `device`); their searches are resumable
+ * and every static evaluation they ask for is answered in device batches through the NnueState / EvalBatch
+ * mirror.  The search itself is a stand-in (iterative-deepening alpha-beta, csrc/host/selfplay.h): the
+ * reference's search is out of scope.  Slot g plays total_games / concurrency games one after the other (+ 1
+ * for the first total_games % concurrency slots); every (slot, game number) has its own random stream.
+ * `out` receives the records slot by slot (slot-major, game order within a slot), so the bytes do not depend
+ * on `threads`; *out_len is always set to the bytes produced (SP_ERR_CAPACITY if they did not fit; out ==
+ * NULL with out_capacity == 0 only counts). */
 typedef struct SpSelfplayParams {
-    uint32_t concurrency;    /* games in flight, all threads together */
-    uint32_t total_games;    /* games to play, all threads together */
-    uint32_t threads;        /* host threads (0 = 1) */
+    uint32_t concurrency;    /* game slots = games in flight, all threads together */
+    uint32_t total_games;    /* games to play, all slots together */
+    uint32_t threads;        /* sp_selfplay_run: host threads; sp_selfplay_run_gpu: concurrent driver instances (0 = 1) */
     uint32_t depth;          /* iterative deepening stops after this depth ... */
     uint32_t nodes_per_move; /* ... or once a finished iteration has used this many nodes (datagen.cpp:76 soft limit) */
-    uint32_t max_plies;      /* undecided games are drawn here (0 = 300) */
+    uint32_t max_plies;      /* undecided games are drawn here (0 = 300; at most 510) */
     uint64_t seed;
     uint32_t dfrc;           /* 1: `datagen <fmt> dfrc`: every game starts from a random double-Fischer-random position */
     uint32_t reserved;       /* 0 */
@@ -233,10 +236,10 @@ int sp_selfplay_run(
     const void* net_image, size_t len, int device, const SpSelfplayParams* params, SpSelfplayStats* stats, uint8_t* out,
     size_t out_capacity, size_t* out_len);
 /* The same games played by a GPU-resident driver: one device thread per game slot runs the search state
- * machine, the host only submits one sp_nnue_batch_device per round (`threads` is ignored).  Game slot g plays
- * total_games / concurrency games (+ 1 for the first total_games % concurrency slots) whichever entry point is
- * used, every (slot, game) has its own random stream, and records come out slot-major: both entry points
- * produce the same bytes. */
+ * machine (the board model, move generator, search and record writer of csrc/host/selfplay.h compile for the
+ * device too); the host only reads four counters per round and submits one sp_nnue_batch_device.  `threads`
+ * driver instances (slot ranges, own context and stream each) run concurrently.  Same slots, same random
+ * streams, same record order: both entry points produce the same bytes. */
 int sp_selfplay_run_gpu(
     const void* net_image, size_t len, int device, const SpSelfplayParams* params, SpSelfplayStats* stats, uint8_t* out,
     size_t out_capacity, size_t* out_len);
