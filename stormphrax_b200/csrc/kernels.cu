@@ -1506,7 +1506,15 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
 constexpr int kHeadConsumers = SP_HEAD_CONSUMERS;
 constexpr int kStreamThreads = kHeadConsumers * 32;
 constexpr int kTileRows = 32;
-constexpr int kTileRowStride = SP_L1_SIZE + 64;
+/* SP_HEAD_LDMATRIX=1 (experiment prepared for the next round, NOT yet run on a GPU): the A fragments of L1 come
+ * from ldmatrix.x4, which delivers the four fragment registers of a lane directly.  Today they are packed
+ * out of two LDS.128 of different rows, and that packing is 30 % of the kernel's executed instructions
+ * (IMAD.MOV, profiles/r1_head_stream_ncu_v9.md).  ldmatrix reads 8 rows x 16 B per matrix, so the row padding
+ * becomes 16 B (8 consecutive rows on 8 bank groups) and the contraction index is visited in natural order. */
+#ifndef SP_HEAD_LDMATRIX
+#define SP_HEAD_LDMATRIX 0
+#endif
+constexpr int kTileRowStride = SP_L1_SIZE + (SP_HEAD_LDMATRIX ? 16 : 64);
 constexpr int kHeadStages = SP_HEAD_STAGES;
 
 struct HeadStreamShared {
@@ -1590,11 +1598,26 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
 
         consumers_sync(); /* nobody still reads the previous bucket's weights */
         {
+#if SP_HEAD_LDMATRIX
+            /* B fragments as the IMMAs want them: for k-step S (32 wide), lane (g, t) and n-tile nt the pair
+             * (b0, b1) = k-quads 8S + t and 8S + 4 + t of output 4g + nt sit in adjacent words, eight words per
+             * lane and k-step = two LDS.128; 16-byte chunks XOR-swizzled by t so that the eight lanes of a
+             * quarter warp (two g, four t) hit eight bank groups. */
+            const uint32_t* src1 = reinterpret_cast<const uint32_t*>(net.l1_w + static_cast<size_t>(b) * kW1Bytes);
+            uint32_t* dst1 = reinterpret_cast<uint32_t*>(sh.w1);
+            for (int i = tid; i < kW1Bytes / 4; i += kHeadConsumers * 32) {
+                const int q = i >> 5, o = i & 31; /* source word: k-quad q, output o */
+                const int S = q >> 3, half = (q >> 2) & 1, tt = q & 3, gg = o >> 2, nt = o & 3;
+                const int chunk = (((S * 4 + tt) * 8 + gg) * 2 + (nt >> 1)) ^ ((tt & 1) | ((tt >> 1) << 2));
+                dst1[chunk * 4 + (nt & 1) * 2 + half] = __ldg(src1 + i);
+            }
+#else
             const uint4* src1 = reinterpret_cast<const uint4*>(net.l1_w + static_cast<size_t>(b) * kW1Bytes);
             for (int i = tid; i < kW1Bytes / 16; i += kHeadConsumers * 32) {
                 const int q = i >> 3, og = i & 7;
                 sh.w1[q * 8 + (og ^ (((q >> 2) & 3) << 1))] = __ldg(src1 + i);
             }
+#endif
             const uint4* src2 = reinterpret_cast<const uint4*>(net.l2_frags + static_cast<size_t>(b) * kW2Words);
             uint4* dst2 = reinterpret_cast<uint4*>(sh.w2);
             for (int i = tid; i < kW2Words / 4; i += kHeadConsumers * 32) dst2[i] = __ldg(src2 + i);
@@ -1622,6 +1645,32 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) c[mt][i][j] = 0;
+#if SP_HEAD_LDMATRIX
+            /* lane l addresses row (l & 15) of an m-tile at byte 16 (l >> 4) of the 32-byte k-step: matrices 0..3 =
+             * (rows 0-7 | 8-15) x (bytes 0-15 | 16-31) = a0..a3 of mma.m16n8k32 */
+            const uint32_t a_lane = smem_addr(&sh.a[stage][(lane & 15) * kTileRowStride + 16 * (lane >> 4)]);
+            /* chunk of (k-step ks, lane) = ((ks * 4 + t) * 8 + g) * 2 + pair, swizzled in bits 0 and 2: 64 ks apart */
+            const int w_swz = (t & 1) | ((t >> 1) << 2);
+            const uint4* w01 = sh.w1 + (((t * 8 + g) * 2) ^ w_swz);
+            const uint4* w23 = sh.w1 + (((t * 8 + g) * 2 + 1) ^ w_swz);
+#pragma unroll 4
+            for (int ks = 0; ks < SP_L1_SIZE / 32; ++ks) {
+                uint32_t a[2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(a[mt][0]), "=r"(a[mt][1]), "=r"(a[mt][2]), "=r"(a[mt][3])
+                                 : "r"(a_lane + (16 * mt) * kTileRowStride + 32 * ks));
+                const uint4 b01 = w01[64 * ks], b23 = w23[64 * ks]; /* (b0, b1) of n-tiles 0, 1 | 2, 3 */
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    mma_u8s8(c[mt][0], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b01.x, b01.y);
+                    mma_u8s8(c[mt][1], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b01.z, b01.w);
+                    mma_u8s8(c[mt][2], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b23.x, b23.y);
+                    mma_u8s8(c[mt][3], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b23.z, b23.w);
+                }
+            }
+#else
             const uint8_t* a_base = &sh.a[stage][g * kTileRowStride + 16 * t];
             const uint4* w_base = sh.w1 + (g ^ (t << 1));
 #pragma unroll 4
@@ -1647,6 +1696,7 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
                     }
                 }
             }
+#endif
             uint32_t row_id[2][2];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) row_id[mt][0] = sh.rows[stage][16 * mt + g], row_id[mt][1] = sh.rows[stage][16 * mt + g + 8];
