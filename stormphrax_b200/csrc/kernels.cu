@@ -47,6 +47,10 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef SP_ENQ_UNROLL
 #define SP_ENQ_UNROLL 1 /* unroll of the 8-round board enumeration (more ILP, more code) */
 #endif
+#ifndef SP_ENQ_PREFETCH
+#define SP_ENQ_PREFETCH 0 /* 1 (prepared, NOT yet run on a GPU): the board enumeration fetches round k + 1's ray while round k works
+                             (today one dependent 64-bit table load per round: 2.7 % of ft_full's samples wait on it) */
+#endif
 #ifndef SP_FULL_MIN_BLOCKS
 #define SP_FULL_MIN_BLOCKS 4
 #endif
@@ -221,8 +225,16 @@ __device__ __forceinline__ int enqueue_board(
         if (rebuild & 2) ws.psq_add[kWhite][lane] = psq_index(t, kWhite, piece, sq, b.king[kWhite]) * kPsqVecs;
     }
     const bool attacker = has && type != kKing;
+#if SP_ENQ_PREFETCH
+    const bool slider_like = attacker && type != kKnight; /* pawns look along rays too */
+    uint64_t next_ray = slider_like ? t.rays[0][sq] : 0;
+#endif
 #pragma unroll kEnqUnroll
     for (int k = 0; k < 8; ++k) {
+#if SP_ENQ_PREFETCH
+        const uint64_t ray = next_ray;
+        if (slider_like && k < 7) next_ray = t.rays[k + 1][sq];
+#endif
         int target = kNoSquare;
         if (attacker) {
             if (type == kKnight) {
@@ -231,7 +243,11 @@ __device__ __forceinline__ int enqueue_board(
                 if (fx >= 0 && fx < 8 && ry >= 0 && ry < 8) target = ry * 8 + fx;
             } else {
                 uint64_t gap;
+#if SP_ENQ_PREFETCH
+                const int ahead = ray_first(ray, b.occ, k, gap);
+#else
                 const int ahead = ray_first(t, b.occ, sq, k, gap);
+#endif
                 if (ahead != kNoSquare && attacks_along(piece, k, gap == 0)) target = ahead;
             }
         }

@@ -80,6 +80,20 @@ SP_HD uint64_t squares_below(int s) { return bit(s) - 1; }
 
 /* First occupied square from s along k (exclusive of s), or kNoSquare; `between` receives the
  * empty squares passed over (the whole ray if it runs off the board). */
+SP_HD int ray_first(uint64_t ray, uint64_t occ, int k, uint64_t& between) { /* ray = t.rays[k][s], already fetched */
+    const uint64_t hits = ray & occ;
+    between = ray;
+    if (!hits) return kNoSquare;
+    int first;
+    if (dir_is_up(k)) {
+        first = lsb64(hits);
+        between = ray & squares_below(first);
+    } else {
+        first = msb64(hits);
+        between = ray & squares_above(first);
+    }
+    return first;
+}
 SP_HD int ray_first(const FeatureTables& t, uint64_t occ, int s, int k, uint64_t& between) {
     const uint64_t ray = t.rays[k][s];
     const uint64_t hits = ray & occ;
