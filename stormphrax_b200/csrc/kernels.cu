@@ -57,6 +57,9 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef SP_ACC_MIN_BLOCKS
 #define SP_ACC_MIN_BLOCKS 3
 #endif
+#ifndef SP_SLOTS_MIN_BLOCKS
+#define SP_SLOTS_MIN_BLOCKS 2 /* slot update kernel: CTAs per SM it is compiled for (38 % of a self-play round: to be swept) */
+#endif
 #ifndef SP_GAMES_MIN_BLOCKS
 #define SP_GAMES_MIN_BLOCKS 2
 #endif
@@ -840,7 +843,7 @@ __device__ __forceinline__ void store_slot_acc(const SlotStore& s, uint32_t slot
 /* dst[i] = (src ? src[i] advanced to boards[i] : rebuilt from boards[i]); optional activation output.
  * Replaces NnueState::reset / push + applyMove<BoardObserver> + ensureUpToDate
  * (nnue_state.cpp:539-570, 636-697). */
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, SP_SLOTS_MIN_BLOCKS)
 ft_slots_kernel(DeviceNet net, SlotStore slots, const uint32_t* __restrict__ src, const uint32_t* __restrict__ dst,
                 const SpPackedBoard* __restrict__ boards, size_t n, uint8_t* __restrict__ act, uint8_t* __restrict__ bucket,
                 DeviceStatus* status) {
@@ -1953,7 +1956,7 @@ void launch_ft_slots(
     const DeviceNet& net, SlotStore slots, const uint32_t* src, const uint32_t* dst, const SpPackedBoard* boards,
     size_t n, uint8_t* act, uint8_t* bucket, DeviceStatus* status, int sm_count, cudaStream_t stream) {
     if (!n) return;
-    ft_slots_kernel<<<grid_for(n, kWarpsPerCta, sm_count, 2), kThreads, 0, stream>>>(net, slots, src, dst, boards, n, act, bucket, status);
+    ft_slots_kernel<<<grid_for(n, kWarpsPerCta, sm_count, SP_SLOTS_MIN_BLOCKS), kThreads, 0, stream>>>(net, slots, src, dst, boards, n, act, bucket, status);
 }
 
 void launch_plan_rebuilds(
