@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Build the tuning variants of libsp_nnue.so (compile-time knobs at the top of kernels.cu / selfplay_gpu.cu) into
+stormphrax_b200/_lib/variants/<name>.so.  They travel to the GPU box with `gpurun` and are selected with
+SP_NNUE_LIB=<path> (tests, bench and tools all load the library through stormphrax_b200.api).
+usage: python tools/variants.py [name ...]        (no names: all)"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from stormphrax_b200 import build as B
+
+VARIANTS = {
+    # dense head: A fragments by ldmatrix (prepared in round 1, index algebra emulated on the CPU, never run on a GPU)
+    "head_ldmatrix": {"SP_HEAD_LDMATRIX": 1},
+    "head_ldmatrix_c12": {"SP_HEAD_LDMATRIX": 1, "SP_HEAD_CONSUMERS": 12},
+    # board enumeration: next round's ray fetched under the current round
+    "enq_prefetch": {"SP_ENQ_PREFETCH": 1},
+    "enq_unroll2": {"SP_ENQ_UNROLL": 2},
+    # slot update kernel (self-play path): CTAs per SM
+    "slots3": {"SP_SLOTS_MIN_BLOCKS": 3},
+    "slots4": {"SP_SLOTS_MIN_BLOCKS": 4},
+}
+
+
+def main():
+    names = sys.argv[1:] or list(VARIANTS)
+    out_dir = os.path.join(B.LIB_DIR, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    for name in names:
+        path = os.path.join(out_dir, name + ".so")
+        B.build(defines=VARIANTS[name], out=path)
+        print(path)
+
+
+main()
