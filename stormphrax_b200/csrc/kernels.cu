@@ -1499,8 +1499,8 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
  *   - one persistent CTA per SM works on a contiguous run of 32-row tiles of the bucket-grouped order;
  *   - kHeadStages tiles are kept in flight in a ring of stages: one bulk copy per activation row (TMA
  *     engine, cp.async.bulk global -> shared, 1 KB), completion counted in bytes on the stage's `full`
- *     mbarrier; rows are padded to 1088 B so that the A-fragment reads (LDS.128, 8 rows x 4 k-chunks per
- *     quarter warp) touch every bank group once;
+ *     mbarrier; rows are padded to 1040 B so that the A-fragment reads (ldmatrix: 8 rows x 16 B per matrix)
+ *     touch every bank group once;
  *   - every warp is a consumer; warp w takes tiles w, w + kHeadWarpsStream, ...  A warp owns its tile's
  *     32 rows (two m16 tiles), so every weight fragment it fetches from shared memory feeds two IMMAs.
  *     As soon as L1 is done it releases the stage and itself requests the tile that follows on it -- the
@@ -1525,13 +1525,15 @@ head_kernel(DeviceNet net, const uint8_t* __restrict__ act, const uint8_t* __res
 constexpr int kHeadConsumers = SP_HEAD_CONSUMERS;
 constexpr int kStreamThreads = kHeadConsumers * 32;
 constexpr int kTileRows = 32;
-/* SP_HEAD_LDMATRIX=1 (experiment prepared for the next round, NOT yet run on a GPU): the A fragments of L1 come
- * from ldmatrix.x4, which delivers the four fragment registers of a lane directly.  Today they are packed
- * out of two LDS.128 of different rows, and that packing is 30 % of the kernel's executed instructions
- * (IMAD.MOV, profiles/r1_head_stream_ncu_v9.md).  ldmatrix reads 8 rows x 16 B per matrix, so the row padding
- * becomes 16 B (8 consecutive rows on 8 bank groups) and the contraction index is visited in natural order. */
+/* SP_HEAD_LDMATRIX (default): the A fragments of L1 come from ldmatrix.x4, which delivers the four fragment
+ * registers of a lane directly, and the B fragment pairs are stored adjacent, so the L1 loop is 2 LDSM + 2
+ * LDS.128 + 8 IMMA per 32-wide k-step.  The first version (SP_HEAD_LDMATRIX=0) packed A quads out of two
+ * LDS.128 of different rows: that packing was 30 % of the kernel's executed instructions (IMAD.MOV,
+ * profiles/r1_head_stream_ncu_v9.md); 307 -> 272 us at M = 2^20.  ldmatrix reads 8 rows x 16 B per matrix, so
+ * the row padding is 16 B (8 consecutive rows on 8 bank groups) and the contraction index is visited in
+ * natural order. */
 #ifndef SP_HEAD_LDMATRIX
-#define SP_HEAD_LDMATRIX 0
+#define SP_HEAD_LDMATRIX 1
 #endif
 constexpr int kTileRowStride = SP_L1_SIZE + (SP_HEAD_LDMATRIX ? 16 : 64);
 constexpr int kHeadStages = SP_HEAD_STAGES;

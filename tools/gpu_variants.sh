@@ -5,7 +5,7 @@
 mkdir -p gpurun_out
 V=$PWD/stormphrax_b200/_lib/variants
 echo "== default"; SWEEP_LOGM=16,20 timeout 200 python tools/head_sweep.py 2>/dev/null | tail -4; timeout 200 python tools/kbench.py both 2>&1 | tail -2
-for v in head_ldmatrix head_ldmatrix_c12; do
+for v in head_lds head_c12; do
   [ -f $V/$v.so ] || continue
   echo "== $v"
   SP_NNUE_LIB=$V/$v.so timeout 200 python -m pytest tests/test_gpu_full.py -x -q -m gpu -k head > gpurun_out/t_$v.log 2>&1 || { echo "$v FAILED its tests"; tail -5 gpurun_out/t_$v.log; continue; }

@@ -9,9 +9,9 @@ sys.path.insert(0, ROOT)
 from stormphrax_b200 import build as B
 
 VARIANTS = {
-    # dense head: A fragments by ldmatrix (prepared in round 1, index algebra emulated on the CPU, never run on a GPU)
-    "head_ldmatrix": {"SP_HEAD_LDMATRIX": 1},
-    "head_ldmatrix_c12": {"SP_HEAD_LDMATRIX": 1, "SP_HEAD_CONSUMERS": 12},
+    # dense head: the pre-ldmatrix L1 loop (A quads packed from two LDS.128), and three warps per scheduler
+    "head_lds": {"SP_HEAD_LDMATRIX": 0},
+    "head_c12": {"SP_HEAD_CONSUMERS": 12},
     # board enumeration: next round's ray fetched under the current round
     "enq_prefetch": {"SP_ENQ_PREFETCH": 1},
     "enq_unroll2": {"SP_ENQ_UNROLL": 2},
