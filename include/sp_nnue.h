@@ -46,8 +46,10 @@ typedef enum SpStatus {
  * Replaces eval::init / eval::shutdown / eval::getNetwork / eval::isNetworkLoaded
  * (src/eval/nnue.h:38-45, src/eval/nnue.cpp:200-321).  `net_image` is a LOGICAL (un-permuted)
  * network file: 64-byte CBNF header (src/eval/header.h:38-52) + raw arrays
- * (src/eval/nnue/input.h:359-361, src/eval/nnue/arch/multilayer.h:492-496).  The reference
- * replicates the network per NUMA node (nnue.cpp:266-284); here it is one copy per GPU. */
+ * (src/eval/nnue/input.h:359-361, src/eval/nnue/arch/multilayer.h:492-496), or, when the header's
+ * kZstdCompressed flag is set, one zstd frame of those arrays (nnue.cpp:226-247; decoded with the system's
+ * libzstd.so.1).  The reference replicates the network per NUMA node (nnue.cpp:266-284); here it is one
+ * copy per GPU. */
 int sp_nnue_create(const void* net_image, size_t len, int device, SpNnue** out);
 void sp_nnue_destroy(SpNnue* ctx);
 const char* sp_nnue_last_error(const SpNnue* ctx); /* ctx may be NULL: error of the last failed create */
@@ -168,6 +170,19 @@ int sp_nnue_adjust_device(
     SpNnue* ctx, const SpPackedBoard* d_boards, const int32_t* d_raw, const int32_t* d_correction, size_t n,
     const SpAdjustParams* params, int32_t* d_out, void* stream);
 
+/* Score normalisation and the win / draw / loss model for a batch, on the device.
+ * Replaces wdl::normalizeScore<false>(score, pos.classicalMaterial()) and wdl::wdlModel(povScore, material)
+ * (src/wdl.cpp:28-80, src/position.h:515-523): what datagen's adjudication (src/datagen/datagen.cpp:224-253) and the
+ * UCI score output apply to a search score.  `scores` are white-relative or side-to-move-relative as the caller's
+ * use demands (the functions do not care).  normalized[i] is bit-exact with the reference; win[i] / loss[i] are per
+ * mille and pass through exp(): the last bit of a device exp may differ from libm's (at most one per mille).
+ * `normalized` may be NULL; `win` and `loss` are both given or both NULL. */
+int sp_nnue_wdl(
+    SpNnue* ctx, const SpPackedBoard* boards, const int32_t* scores, size_t n, int32_t* normalized, int32_t* win, int32_t* loss);
+int sp_nnue_wdl_device(
+    SpNnue* ctx, const SpPackedBoard* d_boards, const int32_t* d_scores, size_t n, int32_t* d_normalized, int32_t* d_win,
+    int32_t* d_loss, void* stream);
+
 /* ---------------------------------------------------------------- introspection
  * Counters since create (uint64 each): what the engine keeps per thread in SearchData
  * (src/thread.h:35-79) and sums at report time.  Multi-GPU runs all-reduce these over NCCL. */
@@ -268,6 +283,9 @@ size_t sp_host_playouts(
     SpPackedBoard* boards,
     SpMove* moves,
     uint32_t* game_start);
+/* The logical payload (SP_NET_PAYLOAD_BYTES of raw arrays) of a network image whose header may carry the
+ * kZstdCompressed flag: what sp_nnue_create uploads.  out may be NULL (size query).  Returns the payload size or -1. */
+long sp_host_net_payload(const void* net_image, size_t len, void* out, size_t cap);
 int sp_host_board_from_fen(const char* fen, SpPackedBoard* out);
 int sp_host_board_to_fen(const SpPackedBoard* board, char* out, size_t cap);
 /* Double Fischer random start position (Position::fromDfrcIndex, src/position.cpp:1215-1270): index = black * 960 + white */

@@ -83,6 +83,9 @@ SIGNATURES = {
     "sp_host_viriformat": (C.c_long, [_vp, _vp, _vp, C.c_uint32, C.c_int, _vp, _sz]),
     "sp_host_normalize_score": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
     "sp_host_wdl_model": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
+    "sp_host_net_payload": (C.c_long, [_vp, _sz, _vp, _sz]),
+    "sp_nnue_wdl": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "sp_nnue_wdl_device": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -237,6 +240,16 @@ class Nnue:
         self._check(self._lib.sp_nnue_adjust(self._h, boards.ctypes.data, raw.ctypes.data, _ptr(corr), boards.size, C.addressof(params), out.ctypes.data))
         return out
 
+    def wdl(self, boards, scores, model: bool = True):
+        """(normalizeScore<false>, win per mille, loss per mille) of `scores` on `boards`, computed on the device."""
+        boards = _boards(boards)
+        scores = np.ascontiguousarray(scores, dtype=np.int32)
+        norm = np.empty(boards.size, dtype=np.int32)
+        win = np.empty(boards.size, dtype=np.int32) if model else None
+        loss = np.empty(boards.size, dtype=np.int32) if model else None
+        self._check(self._lib.sp_nnue_wdl(self._h, boards.ctypes.data, scores.ctypes.data, boards.size, norm.ctypes.data, _ptr(win), _ptr(loss)))
+        return norm, win, loss
+
     # ---- accumulator slots (the NnueState stack, device resident)
     def slots_reserve(self, n_slots: int) -> None:
         self._check(self._lib.sp_nnue_slots_reserve(self._h, n_slots))
@@ -307,6 +320,16 @@ def playouts(seed: int, n_games: int, max_plies: int, threads: int = 0):
     starts = np.zeros(n_games + 1, dtype=np.uint32)
     n = L.sp_host_playouts(seed, n_games, max_plies, threads, boards.ctypes.data, moves.ctypes.data, starts.ctypes.data)
     return boards[:n].copy(), moves[:n].copy(), starts
+
+
+def net_payload(net_image) -> np.ndarray:
+    """Logical payload bytes of a network image, decompressing a zstd-flagged one (sp_host_net_payload)."""
+    image = np.ascontiguousarray(net_image, dtype=np.uint8)
+    out = np.empty(89_381_920, dtype=np.uint8)
+    n = lib().sp_host_net_payload(image.ctypes.data, image.size, out.ctypes.data, out.size)
+    if n < 0:
+        raise NnueError(SP_ERR_BAD_NETWORK, "not a loadable network image")
+    return out[:n]
 
 
 def board_from_fen(fen: str) -> np.ndarray:

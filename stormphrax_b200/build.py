@@ -17,8 +17,8 @@ LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsp_nnue.so")
 
 CUDA_SOURCES = ["kernels.cu", "capi.cu", "selfplay_gpu.cu"]
-HOST_SOURCES = ["host/position.cpp", "host/host_capi.cpp", "host/nnue_state.cpp", "host/selfplay.cpp"]
-HEADERS = ["kernels.cuh", "sp_features.h", "sp_delta.h", "host/position.h", "host/nnue_state.h", "host/selfplay.h", "host/rng.h",
+HOST_SOURCES = ["host/position.cpp", "host/host_capi.cpp", "host/nnue_state.cpp", "host/selfplay.cpp", "host/net_loader.cpp"]
+HEADERS = ["kernels.cuh", "sp_features.h", "sp_delta.h", "host/position.h", "host/nnue_state.h", "host/selfplay.h", "host/rng.h", "host/net_loader.h", "capi_slots.inc",
            "../../include/sp_nnue.h", "../../include/sp_types.h"]
 
 NVCC_FLAGS = [
@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False, defines: dict | None = Non
         return LIB_PATH
     os.makedirs(os.path.dirname(target), exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in CUDA_SOURCES + HOST_SOURCES if os.path.exists(os.path.join(CSRC, f))]
-    cmd = [nvcc(), *NVCC_FLAGS, *[f"-D{k}={v}" for k, v in (defines or {}).items()], "-shared", "-o", target, *srcs, "-lpthread"]
+    cmd = [nvcc(), *NVCC_FLAGS, *[f"-D{k}={v}" for k, v in (defines or {}).items()], "-shared", "-o", target, *srcs, "-lpthread", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

@@ -15,6 +15,7 @@
 
 #include "../../include/sp_nnue.h"
 #include "kernels.cuh"
+#include "host/net_loader.h"
 
 using namespace sp;
 using namespace sp::gpu;
@@ -75,7 +76,7 @@ struct SpNnue {
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error; /* create() may fail on several threads at once (sp_selfplay_run_gpu) */
 
 int fail(SpNnue* ctx, int code, const char* fmt, ...) {
     char buf[512];
@@ -110,7 +111,7 @@ const char* validate_header(const uint8_t* h) {
     if (!(in_b & 0x80)) return "network does not have the expected threat inputs";
     if ((in_b & 0x7F) != SP_INPUT_BUCKETS) return fmt("wrong number of input buckets %u (expected: %u)", in_b & 0x7F, SP_INPUT_BUCKETS);
     if (out_b != SP_OUTPUT_BUCKETS) return fmt("wrong number of output buckets %u (expected: %u)", out_b, SP_OUTPUT_BUCKETS);
-    if (flags & 0x0001) return "zstd-compressed network: decompress before upload";
+    (void)flags; /* kZstdCompressed (0x0001) is honoured by the loader: host/net_loader.cpp */
     return nullptr;
 }
 
@@ -345,7 +346,7 @@ int eval_full_device(
         }
         {
             Timed timed{ctx, hs, SP_KERNEL_HEAD};
-            launch_head(ctx->net, ctx->d_act2[buf], ctx->d_bucket2[buf], m, d_out + off, nullptr, ctx->head_sort, ctx->sm_count, hs);
+            SP_CUDA(ctx, launch_head(ctx->net, ctx->d_act2[buf], ctx->d_bucket2[buf], m, d_out + off, nullptr, ctx->head_sort, ctx->sm_count, hs));
             ctx->counters[SP_CTR_LAUNCHES] += 3;
         }
         if (overlap) SP_CUDA(ctx, cudaEventRecord(ctx->ev_head[buf], ctx->aux));
@@ -380,8 +381,11 @@ static int create_impl(const void* net_image, size_t len, int device, SpNnue** o
     if (!net_image || len < SP_NET_HEADER_BYTES) return fail(nullptr, SP_ERR_BAD_NETWORK, "missing network header");
     const uint8_t* bytes = static_cast<const uint8_t*>(net_image);
     if (const char* why = validate_header(bytes)) return fail(nullptr, SP_ERR_BAD_NETWORK, "%s", why);
-    if (len < size_t{SP_NET_HEADER_BYTES} + SP_NET_PAYLOAD_BYTES)
-        return fail(nullptr, SP_ERR_BAD_NETWORK, "network too small? %zu < %zu", len - SP_NET_HEADER_BYTES, size_t{SP_NET_PAYLOAD_BYTES});
+    /* raw arrays, or one zstd frame of them (eval::init, src/eval/nnue.cpp:215-263) */
+    std::vector<uint8_t> inflated;
+    std::string why_not;
+    const uint8_t* payload = sp::host::network_payload(bytes, len, SP_NET_PAYLOAD_BYTES, inflated, why_not);
+    if (!payload) return fail(nullptr, SP_ERR_BAD_NETWORK, "%s", why_not.c_str());
 
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
@@ -398,7 +402,9 @@ static int create_impl(const void* net_image, size_t len, int device, SpNnue** o
     DeviceGuard guard{device};
     cudaDeviceProp prop{};
     SP_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) return fail(nullptr, SP_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    /* arch-specific ("a") targets have no forward compatibility: only compute capability 10.0 can run this image */
+    if (prop.major != 10 || prop.minor != 0)
+        return fail(nullptr, SP_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* env = std::getenv("SP_NNUE_CHUNK")) {
         const long v = std::atol(env);
@@ -408,7 +414,7 @@ static int create_impl(const void* net_image, size_t len, int device, SpNnue** o
 
     const NetLayout L;
     std::vector<uint8_t> img(L.total);
-    build_device_image(bytes + SP_NET_HEADER_BYTES, L, img.data());
+    build_device_image(payload, L, img.data());
     /* buckets whose L2 weights all fit int16: the streaming head then contracts two weight limbs instead of four */
     uint32_t l2_narrow_mask = 0;
     {
@@ -614,7 +620,7 @@ int sp_nnue_forward_device(SpNnue* ctx, const uint8_t* d_act, const uint8_t* d_b
     if (reinterpret_cast<uintptr_t>(d_act) & 15) return fail(ctx, SP_ERR_INVALID, "d_act must be 16-byte aligned");
     DeviceGuard guard{ctx->device};
     if (const int rc = ensure_head_sort(ctx, n)) return rc;
-    launch_head(ctx->net, d_act, d_bucket, n, d_out, nullptr, ctx->head_sort, ctx->sm_count, pick(ctx, stream));
+    SP_CUDA(ctx, launch_head(ctx->net, d_act, d_bucket, n, d_out, nullptr, ctx->head_sort, ctx->sm_count, pick(ctx, stream)));
     ctx->counters[SP_CTR_LAUNCHES] += 3;
     ctx->counters[SP_CTR_EVALS] += n;
     SP_CUDA(ctx, cudaGetLastError());
@@ -633,7 +639,7 @@ int sp_nnue_adjust_device(
     if (!n) return SP_OK;
     if (!d_boards || !d_raw || !d_out || !params) return fail(ctx, SP_ERR_INVALID, "null argument");
     DeviceGuard guard{ctx->device};
-    launch_adjust(d_boards, d_raw, d_correction, n, *params, d_out, pick(ctx, stream));
+    launch_adjust(d_boards, d_raw, d_correction, n, *params, d_out, ctx->sm_count, pick(ctx, stream));
     ctx->counters[SP_CTR_LAUNCHES] += 1;
     SP_CUDA(ctx, cudaGetLastError());
     return SP_OK;
@@ -652,10 +658,46 @@ int sp_nnue_adjust(
     SP_CUDA(ctx, cudaMemcpyAsync(ctx->d_boards, boards, n * sizeof(SpPackedBoard), cudaMemcpyHostToDevice, ctx->stream));
     SP_CUDA(ctx, cudaMemcpyAsync(d_raw, raw, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     if (correction) SP_CUDA(ctx, cudaMemcpyAsync(d_corr, correction, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    launch_adjust(ctx->d_boards, d_raw, correction ? d_corr : nullptr, n, *params, ctx->d_out, ctx->stream);
+    launch_adjust(ctx->d_boards, d_raw, correction ? d_corr : nullptr, n, *params, ctx->d_out, ctx->sm_count, ctx->stream);
     ctx->counters[SP_CTR_LAUNCHES] += 1;
     SP_CUDA(ctx, cudaGetLastError());
     SP_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx, ctx->stream);
+}
+
+int sp_nnue_wdl_device(
+    SpNnue* ctx, const SpPackedBoard* d_boards, const int32_t* d_scores, size_t n, int32_t* d_normalized, int32_t* d_win,
+    int32_t* d_loss, void* stream) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!n) return SP_OK;
+    if (!d_boards || !d_scores || (!d_normalized && !d_win) || (!d_win != !d_loss)) return fail(ctx, SP_ERR_INVALID, "null argument");
+    DeviceGuard guard{ctx->device};
+    launch_wdl(d_boards, d_scores, n, d_normalized, d_win, d_loss, ctx->sm_count, pick(ctx, stream));
+    ctx->counters[SP_CTR_LAUNCHES] += 1;
+    SP_CUDA(ctx, cudaGetLastError());
+    return SP_OK;
+}
+
+int sp_nnue_wdl(
+    SpNnue* ctx, const SpPackedBoard* boards, const int32_t* scores, size_t n, int32_t* normalized, int32_t* win, int32_t* loss) {
+    if (!ctx) return SP_ERR_INVALID;
+    if (!n) return SP_OK;
+    if (!boards || !scores || (!normalized && !win) || (!win != !loss)) return fail(ctx, SP_ERR_INVALID, "null argument");
+    DeviceGuard guard{ctx->device};
+    if (const int rc = ensure_staging(ctx, n)) return rc;
+    int32_t* d_scores = reinterpret_cast<int32_t*>(ctx->d_ids); /* 3 * (cap + 1) words of scratch: scores, win, loss */
+    int32_t* d_win = d_scores + ctx->cap + 1;
+    int32_t* d_loss = d_win + ctx->cap + 1;
+    SP_CUDA(ctx, cudaMemcpyAsync(ctx->d_boards, boards, n * sizeof(SpPackedBoard), cudaMemcpyHostToDevice, ctx->stream));
+    SP_CUDA(ctx, cudaMemcpyAsync(d_scores, scores, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    launch_wdl(ctx->d_boards, d_scores, n, normalized ? ctx->d_out : nullptr, win ? d_win : nullptr, win ? d_loss : nullptr, ctx->sm_count, ctx->stream);
+    ctx->counters[SP_CTR_LAUNCHES] += 1;
+    SP_CUDA(ctx, cudaGetLastError());
+    if (normalized) SP_CUDA(ctx, cudaMemcpyAsync(normalized, ctx->d_out, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (win) {
+        SP_CUDA(ctx, cudaMemcpyAsync(win, d_win, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        SP_CUDA(ctx, cudaMemcpyAsync(loss, d_loss, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     return finish(ctx, ctx->stream);
 }
 

@@ -433,7 +433,10 @@ private:
         Move replies[256];
         const int nReplies = m_pos.generateLegal(replies);
         const bool bareKings = popcount64(m_pos.occ()) <= 2;
-        if (m_pos.halfmove() >= 100 || bareKings || m_plies >= m_params.maxPlies) { /* isDrawn stand-in, datagen.cpp:264-268 */
+        /* isDrawn stand-in, datagen.cpp:264-268.  Fifty-move rule as Position::isDrawn has it (position.cpp:621-633):
+         * a side that is in check with no legal reply has been mated, not drawn. */
+        const bool fiftyMoves = m_pos.halfmove() >= 100 && (nReplies || !m_pos.isCheck());
+        if (fiftyMoves || bareKings || m_plies >= m_params.maxPlies) {
             m_outcome = Outcome::kDraw;
             m_record.push(move, 0);
             return true;

@@ -977,12 +977,12 @@ struct KingPair {
 /* One warp per game, one lane per ply: which (board, perspective) pairs need a fresh accumulator. */
 __global__ void __launch_bounds__(256)
 plan_rebuilds_kernel(DeviceNet net, RebuildPlan plan, const SpPackedBoard* __restrict__ boards,
-                     const uint32_t* __restrict__ game_start, uint32_t n_games) {
+                     const uint32_t* __restrict__ game_start, uint32_t n_games, size_t n_boards) {
     const FeatureTables& t = *net.tables;
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t g = warp; g < n_games; g += n_warps) {
-        const size_t first = game_start[g], last = game_start[g + 1];
+        const size_t first = min(static_cast<size_t>(game_start[g]), n_boards), last = min(static_cast<size_t>(game_start[g + 1]), n_boards);
         KingPair carry{};      /* kings of the board before this round of 32 plies */
         bool carry_ok = false; /* false at the start of the game: the first board is always rebuilt */
         for (size_t base = first; base < last; base += 32) {
@@ -1051,7 +1051,7 @@ __global__ void rebuilds_done_kernel(RebuildPlan plan) { plan.counters[1] = min(
  * ply (datagen form, src/datagen/datagen.cpp:257-262: applyMove + applyImmediately + evaluate). */
 __global__ void __launch_bounds__(kThreads, SP_GAMES_MIN_BLOCKS)
 ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const uint32_t* __restrict__ game_start,
-                uint32_t n_games, uint8_t* __restrict__ act, uint8_t* __restrict__ bucket, RebuildPlan plan, DeviceStatus* status) {
+                uint32_t n_games, size_t n_boards, uint8_t* __restrict__ act, uint8_t* __restrict__ bucket, RebuildPlan plan, DeviceStatus* status) {
     __shared__ WarpScratch scratch[kWarpsPerCta];
     __shared__ uint32_t parked[kWarpsPerCta][16][32]; /* one perspective's registers, parked between passes */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1059,7 +1059,9 @@ ft_games_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, const u
     const FeatureTables& t = *net.tables;
     const uint32_t stride = gridDim.x * kWarpsPerCta;
     for (uint32_t g = blockIdx.x * kWarpsPerCta + warp; g < n_games; g += stride) {
-        const size_t first = game_start[g], last = game_start[g + 1];
+        /* the scratch rows are sized from the caller's n_boards: offsets past it are reported, never followed */
+        if (game_start[g + 1] > n_boards && lane == 0) flag_error(status, kErrBadSlot);
+        const size_t first = min(static_cast<size_t>(game_start[g]), n_boards), last = min(static_cast<size_t>(game_start[g + 1]), n_boards);
         uint32_t v[16];
         int in_regs = 0; /* which perspective `v` currently holds */
         BoardView prev{};
@@ -1171,9 +1173,10 @@ struct HeadShared {
 /* ---- counting sort of a launch's positions by output bucket (three tiny kernels) */
 __device__ __forceinline__ void head_span(const uint32_t* range, uint32_t range_len, size_t& first, size_t& n) {
     first = 0;
-    if (range) { /* positions [range[0], range[range_len]) */
-        first = range[0];
-        n = range[range_len] - first;
+    if (range) { /* positions [range[0], range[range_len]), never past the n boards the caller says exist */
+        const size_t bound = n, last = range[range_len] < bound ? range[range_len] : bound;
+        first = range[0] < last ? range[0] : last;
+        n = last - first;
     }
 }
 
@@ -1917,6 +1920,44 @@ __global__ void adjust_kernel(const SpPackedBoard* __restrict__ boards, const in
     }
 }
 
+/* wdl::normalizeScore<false> and wdl::wdlModel for a batch, src/wdl.cpp:28-80.  The material is
+ * Position::classicalMaterial (position.h:515-523) counted from the record's nibbles.  Every double operation is
+ * an explicitly rounded one (no contraction into FMAs), so the normalised score is the reference's bit for bit;
+ * the win / loss per-mille figures go through exp(), whose last bit may differ between libm and the device
+ * (tests allow one per mille). */
+__global__ void wdl_kernel(const SpPackedBoard* __restrict__ boards, const int32_t* __restrict__ scores, size_t n,
+                           int32_t* __restrict__ normalized, int32_t* __restrict__ win, int32_t* __restrict__ loss) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const uint4* rec = reinterpret_cast<const uint4*>(boards + i);
+        const uint4 lo = __ldg(rec), hi = __ldg(rec + 1);
+        const int n_pieces = __popcll(static_cast<uint64_t>(lo.y) << 32 | lo.x);
+        const uint32_t words[4] = {lo.z, lo.w, hi.x, hi.y};
+        int material = 0;
+        for (int k = 0; k < n_pieces && k < 32; ++k) {
+            const uint32_t type = (words[k >> 3] >> ((k & 7) * 4)) & 7;
+            material += (0x5095331 >> (4 * type)) & 0xF; /* P 1, N 3, B 3, R 5, Q 9, K 0, castling rook (6) 5 */
+        }
+        const int32_t score = scores[i];
+        const double m = static_cast<double>(min(max(material, 17), 78)) / 58.0;
+        auto cubic = [m](double c0, double c1, double c2, double c3) {
+            double v = __dadd_rn(__dmul_rn(c0, m), c1);
+            v = __dadd_rn(__dmul_rn(v, m), c2);
+            return __dadd_rn(__dmul_rn(v, m), c3);
+        };
+        const double a = cubic(-244.97139595, 687.39969858, -654.38002091, 608.47087786);
+        if (normalized) {
+            const bool keep = score == 0 || abs(score) > 25000; /* zero or decisive: core.h:722-724 */
+            normalized[i] = keep ? score : static_cast<int32_t>(round(__dmul_rn(100.0, __ddiv_rn(static_cast<double>(score), a))));
+        }
+        if (win && loss) {
+            const double b = cubic(68.24072080, -111.17718819, 74.50316570, 71.16566713);
+            const double x = static_cast<double>(score);
+            win[i] = static_cast<int32_t>(round(__ddiv_rn(1000.0, __dadd_rn(1.0, exp(__ddiv_rn(__dsub_rn(a, x), b))))));
+            loss[i] = static_cast<int32_t>(round(__ddiv_rn(1000.0, __dadd_rn(1.0, exp(__ddiv_rn(__dadd_rn(a, x), b))))));
+        }
+    }
+}
+
 int grid_for(size_t n_warp_items, int warps_per_cta, int sm_count, int ctas_per_sm) {
     const size_t want = (n_warp_items + warps_per_cta - 1) / warps_per_cta;
     const size_t cap = static_cast<size_t>(sm_count) * ctas_per_sm;
@@ -1962,11 +2003,11 @@ void launch_ft_slots(
 }
 
 void launch_plan_rebuilds(
-    const DeviceNet& net, RebuildPlan plan, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, int sm_count,
-    cudaStream_t stream) {
+    const DeviceNet& net, RebuildPlan plan, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, size_t n_boards,
+    int sm_count, cudaStream_t stream) {
     if (!n_games) return;
     const unsigned grid = static_cast<unsigned>(std::min<size_t>((n_games + 7) / 8, static_cast<size_t>(sm_count) * 8));
-    plan_rebuilds_kernel<<<grid, 256, 0, stream>>>(net, plan, boards, game_start, n_games);
+    plan_rebuilds_kernel<<<grid, 256, 0, stream>>>(net, plan, boards, game_start, n_games, n_boards);
 }
 
 void launch_run_rebuilds(
@@ -1976,11 +2017,11 @@ void launch_run_rebuilds(
 }
 
 void launch_ft_games(
-    const DeviceNet& net, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, uint8_t* act,
+    const DeviceNet& net, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, size_t n_boards, uint8_t* act,
     uint8_t* bucket, RebuildPlan plan, DeviceStatus* status, int sm_count, cudaStream_t stream) {
     if (!n_games) return;
     ft_games_kernel<<<grid_for(n_games, kWarpsPerCta, sm_count, SP_GAMES_MIN_BLOCKS), kThreads, 0, stream>>>(
-        net, boards, game_start, n_games, act, bucket, plan, status);
+        net, boards, game_start, n_games, n_boards, act, bucket, plan, status);
 }
 
 void launch_slot_activate(
@@ -1999,10 +2040,10 @@ static bool head_uses_tiles() {
     return tiles;
 }
 
-void launch_head(
+cudaError_t launch_head(
     const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, const uint32_t* range, HeadSort sort,
     int sm_count, cudaStream_t stream, uint32_t range_len) {
-    if (!n) return;
+    if (!n) return cudaSuccess;
     const size_t slots = std::min(sort.capacity, n + kHeadGroupPad * SP_OUTPUT_BUCKETS); /* n bounds the rows of this launch */
     if (n <= kHeadSortSmall) {
         head_sort_small_kernel<<<1, 1024, 0, stream>>>(bucket, n, range, range_len, sort, out);
@@ -2017,8 +2058,10 @@ void launch_head(
     int device = 0;
     cudaGetDevice(&device);
     if (!((configured.load(std::memory_order_relaxed) >> (device & 63)) & 1)) {
-        cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadShared)));
-        cudaFuncSetAttribute(head_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadStreamShared)));
+        /* fails with "no kernel image" on a device this sm_100a-only library cannot run on: report it here, not at the launch */
+        cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadShared)));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(head_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadStreamShared)));
+        if (e != cudaSuccess) return e;
         configured.fetch_or(uint64_t{1} << (device & 63), std::memory_order_relaxed);
     }
     if (head_uses_tiles()) {
@@ -2028,14 +2071,23 @@ void launch_head(
         const unsigned grid = static_cast<unsigned>(std::min<size_t>((slots + kTileRows - 1) / kTileRows, static_cast<size_t>(sm_count)));
         head_stream_kernel<<<grid, kStreamThreads, sizeof(HeadStreamShared), stream>>>(net, act, out, sort);
     }
+    return cudaPeekAtLastError();
 }
 
 void launch_adjust(
     const SpPackedBoard* boards, const int32_t* raw, const int32_t* correction, size_t n, const SpAdjustParams& params,
-    int32_t* out, cudaStream_t stream) {
+    int32_t* out, int sm_count, cudaStream_t stream) {
     if (!n) return;
-    const unsigned grid = static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 148 * 16));
+    const unsigned grid = static_cast<unsigned>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(sm_count) * 16));
     adjust_kernel<<<grid, 256, 0, stream>>>(boards, raw, correction, n, params, out);
+}
+
+void launch_wdl(
+    const SpPackedBoard* boards, const int32_t* scores, size_t n, int32_t* normalized, int32_t* win, int32_t* loss, int sm_count,
+    cudaStream_t stream) {
+    if (!n) return;
+    const unsigned grid = static_cast<unsigned>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(sm_count) * 16));
+    wdl_kernel<<<grid, 256, 0, stream>>>(boards, scores, n, normalized, win, loss);
 }
 
 } // namespace sp::gpu

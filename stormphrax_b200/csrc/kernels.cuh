@@ -115,15 +115,15 @@ struct RebuildPlan {
 };
 void launch_plan_rebuilds(
     const DeviceNet& net, RebuildPlan plan, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games,
-    int sm_count, cudaStream_t stream);
+    size_t n_boards, int sm_count, cudaStream_t stream);
 void launch_run_rebuilds(
     const DeviceNet& net, RebuildPlan plan, const SpPackedBoard* boards, DeviceStatus* status, int sm_count, cudaStream_t stream);
 
 /* one warp walks one game; act/bucket rows are indexed like boards.  plan.slot == nullptr: every
  * rebuild happens inside the walker. */
 void launch_ft_games(
-    const DeviceNet& net, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, uint8_t* act,
-    uint8_t* bucket, RebuildPlan plan, DeviceStatus* status, int sm_count, cudaStream_t stream);
+    const DeviceNet& net, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, size_t n_boards,
+    uint8_t* act, uint8_t* bucket, RebuildPlan plan, DeviceStatus* status, int sm_count, cudaStream_t stream);
 
 /* slots[i] -> act[i], bucket[i]; stm may be nullptr (use the stored board's side to move) */
 void launch_slot_activate(
@@ -145,7 +145,7 @@ constexpr int kHeadSortCounters = 32;
  * a position whose board was rejected: out[i] = INT32_MIN.
  * range == nullptr: positions [0, n).  Otherwise positions [range[0], range[range_len]) read on the
  * device (a span of a game_start array) and n is only an upper bound of their count for the grids. */
-void launch_head(
+cudaError_t launch_head(
     const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, const uint32_t* range,
     HeadSort sort, int sm_count, cudaStream_t stream, uint32_t range_len = 0);
 
@@ -153,7 +153,13 @@ void launch_head(
  * `correction` may be null. */
 void launch_adjust(
     const SpPackedBoard* boards, const int32_t* raw, const int32_t* correction, size_t n, const SpAdjustParams& params,
-    int32_t* out, cudaStream_t stream);
+    int32_t* out, int sm_count, cudaStream_t stream);
+
+/* scores -> wdl::normalizeScore<false> and / or wdl::wdlModel per mille (src/wdl.cpp:28-80); one thread per position.
+ * `normalized` may be null; `win` and `loss` are both given or both null. */
+void launch_wdl(
+    const SpPackedBoard* boards, const int32_t* scores, size_t n, int32_t* normalized, int32_t* win, int32_t* loss, int sm_count,
+    cudaStream_t stream);
 
 } // namespace sp::gpu
 

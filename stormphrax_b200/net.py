@@ -112,8 +112,6 @@ def validate_header(buf: bytes | memoryview) -> None:
         raise NetworkFormatError(f"wrong number of input buckets {in_b & 0x7F} (expected: {IN_BUCKETS})")
     if out_b != OUT_BUCKETS:
         raise NetworkFormatError(f"wrong number of output buckets {out_b} (expected: {OUT_BUCKETS})")
-    if flags & FLAG_ZSTD:
-        raise NetworkFormatError("zstd-compressed networks must be decompressed before upload")
 
 
 @dataclasses.dataclass
@@ -154,6 +152,18 @@ def from_bytes(buf: bytes | np.ndarray) -> Network:
         raise NetworkFormatError(f"network too small? {image.size - HEADER_BYTES} < {PAYLOAD_BYTES}")
     image = image[:FILE_BYTES]
     return Network(image=image, **_views(image))
+
+
+def compressed(net: "Network", level: int = 3) -> np.ndarray:
+    """The same network as a zstd-flagged file image (header flag kZstdCompressed + one zstd frame of the arrays,
+    what the reference's release builds embed: src/eval/nnue.cpp:215-247).  Test helper; needs pyarrow's zstd codec."""
+    import pyarrow as pa
+
+    body = pa.compress(net.image[HEADER_BYTES:].tobytes(), codec="zstd", asbytes=True)
+    hdr = bytearray(net.image[:HEADER_BYTES].tobytes())
+    flags = struct.unpack_from("<H", hdr, 6)[0] | FLAG_ZSTD
+    struct.pack_into("<H", hdr, 6, flags)
+    return np.frombuffer(bytes(hdr) + body, dtype=np.uint8)
 
 
 def load(path: str) -> Network:

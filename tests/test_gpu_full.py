@@ -262,3 +262,28 @@ def test_dense_head_l2_paths(net, stress_net, monkeypatch):
                     assert (got[pick] == want).all(), (narrow, name)
     finally:
         oracle.load_net(net.image)  # the C oracle keeps one global network
+
+
+def test_zstd_flagged_network_loads_and_evaluates_identically(net, golden):
+    """sp_nnue_create on a zstd-compressed image (eval::init, src/eval/nnue.cpp:215-247) = the raw network."""
+    pytest.importorskip("pyarrow")
+    with api.Nnue(N.compressed(net), 0) as ctx:
+        assert (ctx.eval_full(golden["boards"][:512]) == golden["evals"][:512]).all()
+    damaged = N.compressed(net)[:100000]
+    with pytest.raises(api.NnueError) as e:
+        api.Nnue(damaged, 0)
+    assert e.value.status == api.SP_ERR_BAD_NETWORK
+
+
+def test_wdl_on_device_matches_reference_golden(gpu_ctx):
+    """sp_nnue_wdl = wdl::normalizeScore<false> (bit-exact) and wdl::wdlModel (per mille; exp() may differ in its last
+    bit between libm and the device: tolerance 1) on the reference-generated vectors (tests/golden/make_datagen_golden.py)."""
+    import os
+
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "datagen_seed42.npz"))
+    norm, win, loss = gpu_ctx.wdl(d["norm_boards"], d["norm_scores"])
+    assert np.array_equal(norm, d["norm_out"].astype(np.int32))
+    want = d["wdl_model"].astype(np.int64)
+    assert np.abs(win.astype(np.int64) - want[:, 0]).max() <= 1 and np.abs(loss.astype(np.int64) - want[:, 1]).max() <= 1
+    only_norm, none_w, none_l = gpu_ctx.wdl(d["norm_boards"], d["norm_scores"], model=False)
+    assert np.array_equal(only_norm, norm) and none_w is None and none_l is None

@@ -179,3 +179,20 @@ def test_host_adjust_eval_matches_reference_golden():
     inside = np.abs(base) < 24999  # where the golden value was not clamped, the pre-clamp value is known
     got = api.host_adjust(boards, raw, api.AdjustParams.defaults(), correction=corr)
     assert (got[inside] == want[inside]).all()
+
+
+def test_zstd_flagged_network_decodes_to_the_same_payload(net):
+    """eval::init accepts a zstd-compressed network (src/eval/nnue.cpp:215-247): header uncompressed, the arrays one
+    zstd frame.  The loader's host half must return the identical logical payload; damage must be reported."""
+    from stormphrax_b200 import net as N
+
+    pytest.importorskip("pyarrow")
+    z = N.compressed(net)
+    assert z.size < net.image.size // 1.5 and z[6] & 1
+    assert np.array_equal(api.net_payload(z), net.image[64:])
+    assert np.array_equal(api.net_payload(net.image), net.image[64:])
+    with pytest.raises(api.NnueError):
+        api.net_payload(z[: z.size // 2])  # truncated frame
+    short = N.compressed(type(net)(image=net.image[: 64 + 4096], **{k: getattr(net, k) for k in ("psq_w", "thr_w", "ft_b", "l1_w", "l1_b", "l2_w", "l2_b", "l3_w", "l3_b")}))
+    with pytest.raises(api.NnueError):
+        api.net_payload(short)  # a valid frame that inflates to too few bytes (nnue.cpp:243-246)

@@ -55,11 +55,111 @@ void run(const char* name, int sms, int mhz) {
     cudaFree(out);
 }
 
-int main() {
+// ---- on-chip bandwidth probes: the denominators of roofline.onchip in bench.py (profiles/onchip_peaks.json)
+// mode 0: L2 -> SM, ld.global.cg.v4 (no L1 allocation) over a 64 MiB buffer that stays L2-resident
+// mode 1: L1 hits, ld.global.ca.v4 over a 64 KiB window per CTA
+// mode 2: shared memory, ld.shared.v4
+// mode 3: L2 -> shared memory, cp.async.cg 16 B per lane (LDGSTS.BYPASS), the path ft_group_kernel stages rows with
+template <int MODE>
+__global__ void __launch_bounds__(512) bw_probe(const uint4* __restrict__ buf, size_t n_vec, int passes, uint32_t* out) {
+    __shared__ __align__(16) uint4 tile[2048]; /* 32 KiB */
+    uint32_t acc = 0;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    if (MODE == 2)
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) tile[i] = make_uint4(i, 1, 2, 3);
+    __syncthreads();
+    for (int pass = 0; pass < passes; ++pass) {
+        if (MODE == 0) {
+            for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i + 3 * stride < n_vec; i += 4 * stride) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(buf + i + u * stride));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc += v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+            }
+        } else if (MODE == 1) {
+            const uint4* win = buf + static_cast<size_t>(blockIdx.x % 64) * 4096; /* 64 KiB window */
+            for (int rep = 0; rep < 64; ++rep)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    uint4 v;
+                    asm volatile("ld.global.ca.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(win + u * 512 + threadIdx.x));
+                    acc += v.x ^ v.y ^ v.z ^ v.w;
+                }
+        } else if (MODE == 2) {
+            for (int rep = 0; rep < 256; ++rep)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                 : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(&tile[(u * 512 + threadIdx.x + rep) & 2047]))));
+                    acc += v.x ^ v.y ^ v.z ^ v.w;
+                }
+        } else {
+            for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i + 3 * stride < n_vec; i += 4 * stride) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&tile[u * 512 + threadIdx.x]))), "l"(buf + i + u * stride) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 2;" ::: "memory");
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            acc += tile[threadIdx.x].x;
+        }
+    }
+    if (acc == 0x12345678) out[0] = acc;
+}
+
+template <int MODE>
+double run_bw(const char* name, int sms, double* clk_bytes, int mhz) {
+    const size_t bytes = 64ull << 20, n_vec = bytes / 16;
+    uint4* buf;
+    uint32_t* out;
+    cudaMalloc(&buf, bytes), cudaMalloc(&out, 4);
+    cudaMemset(buf, 1, bytes);
+    const int blocks = sms * (MODE == 3 ? 4 : 2), threads = 512, passes = MODE == 0 || MODE == 3 ? 20 : 200;
+    bw_probe<MODE><<<blocks, threads>>>(buf, n_vec, 2, out); /* warms L2 */
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    bw_probe<MODE><<<blocks, threads>>>(buf, n_vec, passes, out);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double moved;
+    if (MODE == 0 || MODE == 3) moved = double(passes) * (n_vec / (4ull * blocks * threads)) * (4ull * blocks * threads) * 16;
+    else if (MODE == 1) moved = double(passes) * 64 * 8 * 16.0 * blocks * threads;
+    else moved = double(passes) * 256 * 4 * 16.0 * blocks * threads;
+    const double gbs = moved / (ms * 1e-3) / 1e9;
+    *clk_bytes = moved / (ms * 1e-3 * mhz * 1e6) / sms;
+    printf("%-28s %8.3f ms  %9.1f GB/s  %6.1f B/clk/SM (at the nominal clock)\n", name, ms, gbs, *clk_bytes);
+    cudaFree(buf), cudaFree(out);
+    return gbs;
+}
+
+int main(int argc, char** argv) {
     cudaDeviceProp p;
     cudaGetDeviceProperties(&p, 0);
     int mhz = p.clockRate / 1000;
     printf("%s, %d SMs, %d MHz nominal (rates assume the nominal clock)\n", p.name, p.multiProcessorCount, mhz);
+    {
+        double c[4];
+        const double l2 = run_bw<0>("L2 -> SM (ld.global.cg.v4)", p.multiProcessorCount, &c[0], mhz);
+        const double l1 = run_bw<1>("L1 hit (ld.global.ca.v4)", p.multiProcessorCount, &c[1], mhz);
+        const double sm = run_bw<2>("shared memory (ld.shared.v4)", p.multiProcessorCount, &c[2], mhz);
+        const double cp = run_bw<3>("L2 -> smem (cp.async.cg 16 B)", p.multiProcessorCount, &c[3], mhz);
+        if (argc > 1) { /* argv[1] = path of the JSON record bench.py reads */
+            if (FILE* f = fopen(argv[1], "w")) {
+                fprintf(f, "{\"gpu\": \"%s\", \"sms\": %d, \"nominal_mhz\": %d, \"l2_read_gbs\": %.1f, \"l1_read_gbs\": %.1f, \"smem_read_gbs\": %.1f, "
+                           "\"l2_to_smem_cp_async_gbs\": %.1f, \"how\": \"tools/ubench.cu: 64 MiB L2-resident buffer (ld.global.cg.v4 / cp.async.cg), 64 KiB window per CTA "
+                           "(ld.global.ca.v4), 32 KiB tile (ld.shared.v4); CUDA events, 2 to 4 CTAs of 512 threads per SM\"}\n",
+                        p.name, p.multiProcessorCount, mhz, l2, l1, sm, cp);
+                fclose(f);
+            }
+        }
+    }
     run<0>("VIADD.16x2", p.multiProcessorCount, mhz);
     run<1>("IADD3", p.multiProcessorCount, mhz);
     run<2>("PRMT", p.multiProcessorCount, mhz);
