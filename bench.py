@@ -237,7 +237,34 @@ def run_reference(args, rank: int, world: int):
         pb, pm, ps = api.playouts(42, 4096, MAX_PLIES)
         prate, pinfo, _ = cpu_arm(pb, pm, ps, "playouts", 6.0)
         line["workloads"] = {"playouts": {"value": prate / 1e6, "unit": UNIT, **{k: pinfo[k] for k in ("cores", "kind", "sample", "isa")}}}
+        line["workloads"]["engine_bench"] = engine_bench()
     print(json.dumps(line), flush=True)
+
+
+def engine_bench(depth: int = 3):
+    """BASELINE configs[0]: the reference's built-in `bench` (src/bench.cpp:95-170) on ONE CPU thread -- its own search on
+    its own CPU evaluation (oracle/_ref/sp_engine_cpu, built from the unmodified sources by oracle/engine/Makefile).  The
+    network is the tame synthetic one (scores a search can work with); the node count is this build's determinism
+    signature, not comparable with upstream's (different network)."""
+    import re
+    import subprocess
+    import tempfile
+
+    from stormphrax_b200 import net as N
+
+    engine = os.path.join(ROOT, "oracle", "_ref", "sp_engine_cpu")
+    if not os.path.exists(engine):
+        return {"unavailable": "oracle/_ref/sp_engine_cpu not built"}
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "tame.nnue")
+        N.synthetic(7, tame=True).image.tofile(path)
+        try:
+            out = subprocess.run([engine, path, "bench", str(depth)], capture_output=True, text=True, timeout=300).stdout
+            m = re.search(r"^(\d+) nodes (\d+) nps", out, re.M)
+            return {"config": f"`bench` depth {depth}, 52 positions, 16 MiB hash, 1 thread (BASELINE configs[0]); synthetic tame network seed 7",
+                    "nodes": int(m.group(1)), "nps": int(m.group(2)), "unit": "nodes/s", "threads": 1}
+        except Exception as e:  # pragma: no cover
+            return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 # ------------------------------------------------------------------ GPU side

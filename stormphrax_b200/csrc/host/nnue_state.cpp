@@ -140,11 +140,27 @@ void NnueState::applyPacked(const SpPackedBoard& board) {
     m_stale[m_top] = 0;
 }
 
-/* evaluate, nnue_state.cpp:598-610 + ensureUpToDate :636-697 */
+/* evaluate, nnue_state.cpp:598-610 + ensureUpToDate :636-697.  The usual case -- the level is dirty and the wanted side
+ * is the board's side to move -- is ONE submission: update (or rebuild) and evaluate together. */
 i32 NnueState::evaluatePacked(const SpPackedBoard& board, Color stm) {
     const uint32_t dst = slot(m_top);
-    if (!m_clean[m_top] || m_stale[m_top]) applyPacked(board);
     i32 out = 0;
+    const bool dirty = !m_clean[m_top] || m_stale[m_top];
+    const bool boardStm = stm == ((board.stm_ep & 0x80) ? kBlack : kWhite);
+    if (dirty && boardStm) {
+        const int from = cleanAncestor();
+        int rc;
+        if (from < 0) {
+            rc = sp_nnue_batch(m_network, &dst, &board, 1, &out, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr);
+        } else {
+            const uint32_t src = slot(static_cast<uint32_t>(from));
+            rc = sp_nnue_update_eval(m_network, &src, &dst, &board, 1, &out);
+        }
+        m_clean[m_top] = report("NnueState::evaluate", m_network, rc);
+        m_stale[m_top] = 0;
+        return out;
+    }
+    if (dirty) applyPacked(board);
     const uint8_t side = static_cast<uint8_t>(stm);
     report("NnueState::evaluate", m_network, sp_nnue_eval_slots(m_network, &dst, &side, 1, &out));
     return out;

@@ -170,13 +170,16 @@ def load(path: str) -> Network:
     return from_bytes(np.fromfile(path, dtype=np.uint8))
 
 
-def synthetic(seed: int = 1234, stress: bool = False) -> Network:
+def synthetic(seed: int = 1234, stress: bool = False, tame: bool = False) -> Network:
     """Random network in the reference's format.
 
     ``stress=False`` uses the ranges from SURVEY.md section 8(d): both sides of every clamp are
     exercised and ``x*x`` occasionally wraps in 32 bits.  ``stress=True`` uses full-range FT and
     dense-layer weights so that the int16 accumulators and the int32 L2/L3 sums wrap constantly --
-    a bit-exactness torture test, not a plausible network.
+    a bit-exactness torture test, not a plausible network.  ``tame=True`` keeps the default ranges but shrinks the
+    output layer so that evaluations stay within a few hundred centipawns: the default network's outputs reach
+    +-50,000, beyond the engine's win score (25,000, src/core.h:708), which sends the reference's alpha-beta search
+    into pathological trees -- the search-level tests (oracle/engine) need scores a search can work with.
     """
     rng = np.random.default_rng(seed)
     image = np.zeros(FILE_BYTES, dtype=np.uint8)
@@ -192,6 +195,8 @@ def synthetic(seed: int = 1234, stress: bool = False) -> Network:
         v["l2_b"][...] = rng.integers(-100000, 100001, v["l2_b"].shape, dtype=np.int32)
         v["l3_w"][...] = rng.integers(-300, 300, v["l3_w"].shape, dtype=np.int32)
         v["l3_b"][...] = rng.integers(-1000000, 1000001, v["l3_b"].shape, dtype=np.int32)
+        if tame:
+            v["l3_w"][...] = rng.integers(-3, 4, v["l3_w"].shape, dtype=np.int32)
     else:
         v["psq_w"][...] = rng.integers(-32768, 32768, v["psq_w"].shape, dtype=np.int16)
         v["thr_w"][...] = rng.integers(-128, 128, v["thr_w"].shape, dtype=np.int8)

@@ -1,0 +1,83 @@
+"""The drop-in claim, tested with the reference engine's OWN search: oracle/engine/Makefile compiles the reference's
+search.cpp / thread.cpp / position.cpp / bench.cpp / datagen.cpp / uci.cpp (where they lie, unmodified) twice -- against
+its stock CPU evaluation (sp_engine_cpu) and against this library through the adapter of INTEGRATION.md section 3
+(sp_engine_b200).  Evaluations are exact integers, so both engines must walk the same trees: identical `bench` node counts
+(src/bench.cpp:149-150, the engine's own determinism signature) and identical evaluation checksums along playouts, with
+datagen's invariant staticEvalOnce == staticEval(nnueState) (src/datagen/datagen.cpp:262) holding at every ply.
+"""
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+from stormphrax_b200 import net as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "engine_seed7.json")
+
+
+def _engine(name):
+    path = os.path.join(REF_DIR, name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} not built (make -C oracle/engine, where /root/reference exists)")
+    return path
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(GOLDEN) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def net_path(tmp_path_factory, golden):
+    path = tmp_path_factory.mktemp("engine") / "tame.nnue"
+    N.synthetic(golden["net"]["seed"], tame=True).image.tofile(path)
+    return str(path)
+
+
+def _run(engine, net_path, *args, timeout=600):
+    p = subprocess.run([engine, net_path, *map(str, args)], capture_output=True, text=True, timeout=timeout)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return p.stdout
+
+
+def _bench_nodes(out):
+    return int(re.search(r"^(\d+) nodes (\d+) nps", out, re.M).group(1))
+
+
+def _evalcheck(out):
+    m = re.search(r"evalcheck: (\d+) positions, (\d+) mismatches, checksum ([0-9a-f]+)", out)
+    return int(m.group(1)), int(m.group(2)), m.group(3)
+
+
+def test_reference_engine_cpu_reproduces_its_golden_signature(net_path, golden):
+    """The CPU build of the reference engine is deterministic: the committed golden values are what it prints here."""
+    from oracle.bind import ref_isa_available
+
+    if "avx2" not in ref_isa_available():
+        pytest.skip("host cannot run the AVX2 build of the reference")
+    cpu = _engine("sp_engine_cpu")
+    assert _bench_nodes(_run(cpu, net_path, "bench", 1)) == golden["bench_nodes"]["1"]
+    e = golden["evalcheck"]
+    assert _evalcheck(_run(cpu, net_path, "evalcheck", e["games"], e["seed"])) == (e["positions"], 0, e["checksum"])
+
+
+@pytest.mark.gpu
+def test_reference_search_on_the_b200_evaluator_walks_the_same_tree(net_path, golden):
+    """The reference's own search, every static evaluation answered by the GPU: same node counts as on the CPU."""
+    b200 = _engine("sp_engine_b200")
+    for depth in ("1", "2"):
+        assert _bench_nodes(_run(b200, net_path, "bench", depth)) == golden["bench_nodes"][depth], f"depth {depth}"
+
+
+@pytest.mark.gpu
+def test_datagen_invariant_and_eval_checksum_on_the_b200_evaluator(net_path, golden):
+    """applyMove<BoardObserver> + applyImmediately + staticEval == staticEvalOnce at every ply (datagen.cpp:257-262), and the
+    evaluations are the CPU engine's, value for value (checksum)."""
+    b200 = _engine("sp_engine_b200")
+    e = golden["evalcheck"]
+    assert _evalcheck(_run(b200, net_path, "evalcheck", e["games"], e["seed"])) == (e["positions"], 0, e["checksum"])
