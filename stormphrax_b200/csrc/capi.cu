@@ -49,6 +49,8 @@ struct SpNnue {
     RebuildPlan plan{};          /* scratch of that scheme, sized for the largest stream seen */
     size_t plan_boards = 0;
     bool split = false;          /* full refresh as extract + accumulate kernels instead of the fused ft_full kernel (SP_NNUE_SPLIT=1) */
+    bool group = true;           /* full refresh on the tensor cores, 16 positions per group (ft_group_kernel); SP_NNUE_FT=warp: ft_full_kernel */
+    uint32_t* d_group_overflow[2] = {nullptr, nullptr}; /* per scratch buffer: groups ft_group_kernel hands to ft_full_kernel */
     void* d_lists[2] = {nullptr, nullptr};
     /* whole-stream scratch of the playout walker (one activation row per board) */
     uint8_t* d_act_big = nullptr;
@@ -119,10 +121,11 @@ constexpr size_t align256(size_t x) { return (x + 255) & ~size_t{255}; }
 
 /* Device layout of the network. Offsets into one allocation. */
 struct NetLayout {
-    size_t psq, thr, l1_w, l1_b, l2_w, l2_limbs, l2_frags, l2_b, l3_w, l3_b, total;
+    size_t psq, psq_planes, thr, l1_w, l1_b, l2_w, l2_limbs, l2_frags, l2_b, l3_w, l3_b, total;
     NetLayout() {
         size_t o = 0;
         psq = o;  o = align256(o + size_t{kPsqRows} * SP_L1_SIZE * 2);
+        psq_planes = o; o = align256(o + size_t{kPsqRows} * SP_L1_SIZE * 2);
         thr = o;  o = align256(o + size_t{kThrRows} * SP_L1_SIZE);
         l1_w = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * SP_L1_SIZE * SP_L2_SIZE);
         l1_b = o; o = align256(o + size_t{SP_OUTPUT_BUCKETS} * SP_L2_SIZE * 4);
@@ -153,6 +156,21 @@ void build_device_image(const uint8_t* payload, const NetLayout& L, uint8_t* img
     for (int r = 0; r < SP_PSQ_FEATURES; ++r) permute_row(psq_w + size_t(r) * SP_L1_SIZE, psq + size_t(r) * SP_L1_SIZE);
     permute_row(ft_b, psq + size_t{kPsqBiasRow} * SP_L1_SIZE);
     std::memset(psq + size_t{kPsqZeroRow} * SP_L1_SIZE, 0, SP_L1_SIZE * 2);
+
+    /* byte planes of the same rows (bias row and zero row included) in natural column order */
+    {
+        uint8_t* planes = img + L.psq_planes;
+        auto split_row = [&](const int16_t* src, uint8_t* dst) {
+            for (int i = 0; i < SP_L1_SIZE; ++i) {
+                const uint16_t v = static_cast<uint16_t>(src[i]);
+                dst[i] = static_cast<uint8_t>(v & 0xFF);
+                dst[SP_L1_SIZE + i] = static_cast<uint8_t>(v >> 8);
+            }
+        };
+        for (int r = 0; r < SP_PSQ_FEATURES; ++r) split_row(psq_w + size_t(r) * SP_L1_SIZE, planes + size_t(r) * 2 * SP_L1_SIZE);
+        split_row(ft_b, planes + size_t{kPsqBiasRow} * 2 * SP_L1_SIZE);
+        std::memset(planes + size_t{kPsqZeroRow} * 2 * SP_L1_SIZE, 0, 2 * SP_L1_SIZE);
+    }
 
     uint8_t* thr = img + L.thr;
     const size_t thr_bytes = size_t{SP_THREAT_FEATURES} * SP_L1_SIZE;
@@ -334,6 +352,10 @@ int eval_full_device(
                 launch_accumulate(ctx->net, ctx->d_lists[buf], m, ctx->d_act2[buf], ctx->d_bucket2[buf], ctx->sm_count, stream);
             }
             ctx->counters[SP_CTR_LAUNCHES] += 1;
+        } else if (ctx->group) {
+            Timed timed{ctx, stream, SP_KERNEL_FT_FULL};
+            SP_CUDA(ctx, launch_ft_group(ctx->net, d_boards + off, m, ctx->d_act2[buf], ctx->d_bucket2[buf], ctx->d_status, ctx->d_group_overflow[buf], ctx->sm_count, stream));
+            ctx->counters[SP_CTR_LAUNCHES] += 1;
         } else {
             Timed timed{ctx, stream, SP_KERNEL_FT_FULL};
             launch_ft_full(ctx->net, d_boards + off, m, ctx->d_act2[buf], ctx->d_bucket2[buf], ctx->d_status, ctx->sm_count, stream);
@@ -442,11 +464,13 @@ static int create_impl(const void* net_image, size_t len, int device, SpNnue** o
     }
     if (const char* env = std::getenv("SP_NNUE_OVERLAP")) ctx->overlap = std::atoi(env) != 0;
     if (const char* env = std::getenv("SP_NNUE_SPLIT")) ctx->split = std::atoi(env) != 0;
+    if (const char* env = std::getenv("SP_NNUE_FT")) ctx->group = std::strcmp(env, "warp") != 0; /* warp: one warp per position (ft_full_kernel) */
     if (const char* env = std::getenv("SP_NNUE_PLAN_REBUILDS")) ctx->plan_rebuilds = std::atoi(env) != 0;
     for (int b = 0; b < 2; ++b) {
         SP_CUDA(nullptr, cudaMalloc(&ctx->d_act2[b], ctx->chunk * SP_L1_SIZE));
         SP_CUDA(nullptr, cudaMalloc(&ctx->d_bucket2[b], ctx->chunk));
         if (ctx->split) SP_CUDA(nullptr, cudaMalloc(&ctx->d_lists[b], row_list_bytes(ctx->chunk)));
+        SP_CUDA(nullptr, cudaMalloc(&ctx->d_group_overflow[b], ft_group_scratch_words(ctx->chunk) * sizeof(uint32_t)));
         SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_ft[b], cudaEventDisableTiming));
         SP_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->ev_head[b], cudaEventDisableTiming));
     }
@@ -461,6 +485,7 @@ static int create_impl(const void* net_image, size_t len, int device, SpNnue** o
     uint8_t* b = ctx->d_net_blob;
     ctx->net.psq = reinterpret_cast<const uint4*>(b + L.psq);
     ctx->net.thr = reinterpret_cast<const uint4*>(b + L.thr);
+    ctx->net.psq_planes = b + L.psq_planes;
     ctx->net.l1_w = reinterpret_cast<const int8_t*>(b + L.l1_w);
     ctx->net.l1_b = reinterpret_cast<const int32_t*>(b + L.l1_b);
     ctx->net.l2_w = reinterpret_cast<const int32_t*>(b + L.l2_w);
@@ -498,6 +523,7 @@ void sp_nnue_destroy(SpNnue* ctx) {
         cudaFree(ctx->d_act2[b]);
         cudaFree(ctx->d_bucket2[b]);
         cudaFree(ctx->d_lists[b]);
+        cudaFree(ctx->d_group_overflow[b]);
         if (ctx->ev_ft[b]) cudaEventDestroy(ctx->ev_ft[b]);
         if (ctx->ev_head[b]) cudaEventDestroy(ctx->ev_head[b]);
     }
@@ -606,8 +632,16 @@ int sp_nnue_activations_device(SpNnue* ctx, const SpPackedBoard* d_boards, size_
     if ((reinterpret_cast<uintptr_t>(d_boards) | reinterpret_cast<uintptr_t>(d_act)) & 15)
         return fail(ctx, SP_ERR_INVALID, "d_boards and d_act must be 16-byte aligned");
     DeviceGuard guard{ctx->device};
-    launch_ft_full(ctx->net, d_boards, n, d_act, d_bucket, ctx->d_status, ctx->sm_count, pick(ctx, stream));
-    ctx->counters[SP_CTR_LAUNCHES] += 1;
+    if (ctx->group) { /* chunk by chunk: the overflow scratch is sized for one chunk (launches are stream-ordered) */
+        for (size_t off = 0; off < n; off += ctx->chunk) {
+            const size_t m = std::min(ctx->chunk, n - off);
+            SP_CUDA(ctx, launch_ft_group(ctx->net, d_boards + off, m, d_act + off * SP_L1_SIZE, d_bucket + off, ctx->d_status, ctx->d_group_overflow[0], ctx->sm_count, pick(ctx, stream)));
+            ctx->counters[SP_CTR_LAUNCHES] += 2;
+        }
+    } else {
+        launch_ft_full(ctx->net, d_boards, n, d_act, d_bucket, ctx->d_status, ctx->sm_count, pick(ctx, stream));
+        ctx->counters[SP_CTR_LAUNCHES] += 1;
+    }
     ctx->counters[SP_CTR_FULL_REFRESH] += 2 * n;
     SP_CUDA(ctx, cudaGetLastError());
     return SP_OK;

@@ -184,13 +184,16 @@ __device__ __forceinline__ int nth_piece_square(uint64_t bits, int n) {
 }
 
 /* Append `task` from every lane where `valid` (ballot compaction, no atomics). Returns the new count. */
-__device__ __forceinline__ int enqueue(WarpScratch& ws, int n_tasks, bool valid, uint32_t task, int lane) {
+__device__ __forceinline__ int enqueue(uint32_t* tasks, int n_tasks, bool valid, uint32_t task, int lane) {
     const unsigned m = __ballot_sync(kFull, valid);
     if (valid) {
         const int at = n_tasks + __popc(m & ((1u << lane) - 1));
-        if (at < kTaskCap) ws.tasks[at] = task;
+        if (at < kTaskCap) tasks[at] = task;
     }
     return n_tasks + __popc(m);
+}
+__device__ __forceinline__ int enqueue(WarpScratch& ws, int n_tasks, bool valid, uint32_t task, int lane) {
+    return enqueue(ws.tasks, n_tasks, valid, task, lane);
 }
 
 __device__ __forceinline__ uint32_t pawn_pair_task(int a_color, int asq, int b_color, int bsq) {
@@ -216,17 +219,11 @@ __device__ __forceinline__ int enqueue_pawn_pairs(
 
 /* Whole-board enumeration (nnue_state.cpp:309-354, 440-449), lane-per-piece: eight uniform rounds, round k
  * looks along ray k (sliders, pawns) or at knight offset k; then the pawn pairs. */
+/* The threat / pawn-pair half of the enumeration: lane l looks from piece l (`sq`, `piece`; `has` = the lane has one). */
 template <typename Flush>
-__device__ __forceinline__ int enqueue_board(
-    const FeatureTables& t, const BoardView& b, int n_pieces, int rebuild, int lane, WarpScratch& ws, int n_tasks, Flush&& flush) {
-    const bool has = lane < n_pieces;
-    const int sq = has ? nth_piece_square(b.occ, lane) : 0;
-    const int piece = has ? b.mailbox[sq] : kNoPiece;
+__device__ __forceinline__ int enqueue_board_threats(
+    const FeatureTables& t, const BoardView& b, bool has, int sq, int piece, int lane, uint32_t* tasks, int n_tasks, Flush&& flush) {
     const int type = piece >> 1;
-    if (has) {
-        if (rebuild & 1) ws.psq_add[kBlack][lane] = psq_index(t, kBlack, piece, sq, b.king[kBlack]) * kPsqVecs;
-        if (rebuild & 2) ws.psq_add[kWhite][lane] = psq_index(t, kWhite, piece, sq, b.king[kWhite]) * kPsqVecs;
-    }
     const bool attacker = has && type != kKing;
 #if SP_ENQ_PREFETCH
     const bool slider_like = attacker && type != kKnight; /* pawns look along rays too */
@@ -257,7 +254,7 @@ __device__ __forceinline__ int enqueue_board(
         int victim = kNoPiece;
         if (target != kNoSquare) victim = b.mailbox[target];
         const bool valid = victim != kNoPiece && (victim >> 1) != kKing;
-        n_tasks = enqueue(ws, n_tasks, valid, pack_candidate(piece, sq, victim, target) | kTaskFull, lane);
+        n_tasks = enqueue(tasks, n_tasks, valid, pack_candidate(piece, sq, victim, target) | kTaskFull, lane);
         if (n_tasks > kTaskCap - 32) n_tasks = flush(n_tasks); /* the next round might not fit: index what is queued */
     }
     /* every unordered pawn pair within one file of each other, once: partner on a higher square */
@@ -272,10 +269,23 @@ __device__ __forceinline__ int enqueue_board(
             partners &= partners - 1;
             task = pawn_pair_task(piece & 1, sq, b.mailbox[o] & 1, o) | kTaskFull;
         }
-        n_tasks = enqueue(ws, n_tasks, valid, task, lane);
+        n_tasks = enqueue(tasks, n_tasks, valid, task, lane);
         if (n_tasks > kTaskCap - 32) n_tasks = flush(n_tasks);
     }
     return n_tasks;
+}
+
+template <typename Flush>
+__device__ __forceinline__ int enqueue_board(
+    const FeatureTables& t, const BoardView& b, int n_pieces, int rebuild, int lane, WarpScratch& ws, int n_tasks, Flush&& flush) {
+    const bool has = lane < n_pieces;
+    const int sq = has ? nth_piece_square(b.occ, lane) : 0;
+    const int piece = has ? b.mailbox[sq] : kNoPiece;
+    if (has) {
+        if (rebuild & 1) ws.psq_add[kBlack][lane] = psq_index(t, kBlack, piece, sq, b.king[kBlack]) * kPsqVecs;
+        if (rebuild & 2) ws.psq_add[kWhite][lane] = psq_index(t, kWhite, piece, sq, b.king[kWhite]) * kPsqVecs;
+    }
+    return enqueue_board_threats(t, b, has, sq, piece, lane, ws.tasks, n_tasks, flush);
 }
 
 /* Changed-square enumeration (sp_delta.h): line items lane = unit * 8 + k, then one square item per unit. */
@@ -678,13 +688,17 @@ __device__ __forceinline__ void flag_error(DeviceStatus* status, int bits) { ato
 
 __global__ void __launch_bounds__(kThreads, SP_FULL_MIN_BLOCKS)
 ft_full_kernel(DeviceNet net, const SpPackedBoard* __restrict__ boards, size_t n, uint8_t* __restrict__ act,
-               uint8_t* __restrict__ bucket, DeviceStatus* status) {
+               uint8_t* __restrict__ bucket, DeviceStatus* status, const uint32_t* __restrict__ groups = nullptr) {
     __shared__ WarpScratch scratch[kWarpsPerCta];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& ws = scratch[warp];
     const FeatureTables& t = *net.tables;
     const size_t stride = static_cast<size_t>(gridDim.x) * kWarpsPerCta;
-    for (size_t pos = static_cast<size_t>(blockIdx.x) * kWarpsPerCta + warp; pos < n; pos += stride) {
+    /* `groups` (ft_group_kernel's overflow list: [0] = count, [1..] = indices of 16-position groups): only those positions */
+    const size_t items = groups ? static_cast<size_t>(groups[0]) * 16 : n;
+    for (size_t item = static_cast<size_t>(blockIdx.x) * kWarpsPerCta + warp; item < items; item += stride) {
+        const size_t pos = groups ? static_cast<size_t>(groups[1 + item / 16]) * 16 + item % 16 : item;
+        if (pos >= n) continue;
         const Decoded d = decode_board(boards + pos, lane, ws.mailbox[0]);
         int err = d.ok ? 0 : kErrBadBoard;
         if (!err && build_lists(t, nullptr, d, lane, ws) < 0) err = kErrCapacity;
@@ -1958,6 +1972,8 @@ __global__ void wdl_kernel(const SpPackedBoard* __restrict__ boards, const int32
     }
 }
 
+#include "ft_group.inc"
+
 int grid_for(size_t n_warp_items, int warps_per_cta, int sm_count, int ctas_per_sm) {
     const size_t want = (n_warp_items + warps_per_cta - 1) / warps_per_cta;
     const size_t cap = static_cast<size_t>(sm_count) * ctas_per_sm;
@@ -1971,6 +1987,35 @@ void launch_ft_full(
     int sm_count, cudaStream_t stream) {
     if (!n) return;
     ft_full_kernel<<<grid_for(n, kWarpsPerCta, sm_count, SP_FULL_MIN_BLOCKS), kThreads, 0, stream>>>(net, boards, n, act, bucket, status);
+}
+
+size_t ft_group_scratch_words(size_t n_positions) { return 1 + (n_positions + kGroupN - 1) / kGroupN; }
+
+cudaError_t launch_ft_group(
+    const DeviceNet& net, const SpPackedBoard* boards, size_t n, uint8_t* act, uint8_t* bucket, DeviceStatus* status, uint32_t* overflow,
+    int sm_count, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    constexpr int kSmem = static_cast<int>(sizeof(GroupShared)) + 1024;
+    static std::atomic<uint64_t> configured{0};
+    int device = 0;
+    cudaGetDevice(&device);
+    if (!((configured.load(std::memory_order_relaxed) >> (device & 63)) & 1)) {
+        const cudaError_t e = cudaFuncSetAttribute(ft_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (e != cudaSuccess) return e;
+        configured.fetch_or(uint64_t{1} << (device & 63), std::memory_order_relaxed);
+    }
+    cudaMemsetAsync(overflow, 0, sizeof(uint32_t), stream);
+    const size_t n_groups = (n + kGroupN - 1) / kGroupN;
+    const unsigned grid = static_cast<unsigned>(std::min<size_t>(n_groups, static_cast<size_t>(sm_count) * 2));
+    /* SP_NNUE_GROUP_LIMIT=<threat rows>: a smaller union bound, so that tests can drive groups down the overflow path */
+    static const uint32_t thr_limit = [] {
+        const char* v = std::getenv("SP_NNUE_GROUP_LIMIT");
+        return v ? static_cast<uint32_t>(std::min<long>(std::max<long>(std::atol(v), 1), kThrSetLimit)) : static_cast<uint32_t>(kThrSetLimit);
+    }();
+    ft_group_kernel<<<grid, kGroupThreads, kSmem, stream>>>(net, boards, n, act, bucket, status, overflow, kPsqSetLimit, thr_limit);
+    /* groups whose row union did not fit the shared-memory sets: the per-position kernel (normally none: it returns at once) */
+    ft_full_kernel<<<sm_count * SP_FULL_MIN_BLOCKS, kThreads, 0, stream>>>(net, boards, n, act, bucket, status, overflow);
+    return cudaPeekAtLastError();
 }
 
 size_t row_list_bytes(size_t n_positions) { return n_positions * 2 * sizeof(RowListRecord); }

@@ -26,6 +26,8 @@ constexpr int kSlotVec = kSlotBytes / 16;           /* uint4 per slot */
 struct DeviceNet {
     const uint4* psq;   /* [kPsqRows][128]: int16 rows in lane order (see lane_order_element) */
     const uint4* thr;   /* [kThrRows][64] : int8 rows + 128 (stored unsigned), natural order */
+    const uint8_t* psq_planes; /* [kPsqRows][2][1024]: the same int16 rows as two byte planes (low bytes, high bytes), natural
+                                  column order: tensor-core operands of ft_group_kernel (u8 x u8 -> s32, recombined mod 2^16) */
     const int8_t* l1_w; /* [8][256][32][4] reference order (multilayer.h:180-196) */
     const int32_t* l1_b;
     const int32_t* l2_w; /* [8][64][64] */
@@ -83,6 +85,13 @@ inline int l2_fragment_index(int limb, int nt, int ks, int lane, int reg) { retu
 /* boards[i] -> act[i][1024], bucket[i]; every position rebuilt from scratch */
 void launch_ft_full(
     const DeviceNet& net, const SpPackedBoard* boards, size_t n, uint8_t* act, uint8_t* bucket, DeviceStatus* status,
+    int sm_count, cudaStream_t stream);
+
+/* The same on the tensor cores (ft_group.inc): groups of 16 positions, every weight row of a group's union fetched once,
+ * summed by tcgen05.mma.kind::i8.  `overflow` = ft_group_scratch_words(n) uint32 of scratch (groups handed to ft_full_kernel). */
+size_t ft_group_scratch_words(size_t n_positions);
+cudaError_t launch_ft_group(
+    const DeviceNet& net, const SpPackedBoard* boards, size_t n, uint8_t* act, uint8_t* bucket, DeviceStatus* status, uint32_t* overflow,
     int sm_count, cudaStream_t stream);
 
 /* The same in two kernels: boards -> row lists (row_list_bytes(n) of scratch) -> activations. */

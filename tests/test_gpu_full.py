@@ -287,3 +287,38 @@ def test_wdl_on_device_matches_reference_golden(gpu_ctx):
     assert np.abs(win.astype(np.int64) - want[:, 0]).max() <= 1 and np.abs(loss.astype(np.int64) - want[:, 1]).max() <= 1
     only_norm, none_w, none_l = gpu_ctx.wdl(d["norm_boards"], d["norm_scores"], model=False)
     assert np.array_equal(only_norm, norm) and none_w is None and none_l is None
+
+
+def test_warp_per_position_kernel_still_bit_exact(net, golden, monkeypatch):
+    """SP_NNUE_FT=warp: ft_full_kernel (one warp per position, ALU summation) instead of the tensor-core group kernel."""
+    monkeypatch.setenv("SP_NNUE_FT", "warp")
+    with api.Nnue(net.image, 0) as ctx:
+        assert (ctx.eval_full(golden["boards"]) == golden["evals"]).all()
+        assert (ctx.eval_full(golden["dfrc_boards"]) == golden["dfrc_evals"]).all()
+
+
+def test_group_kernel_on_shuffled_positions_and_stress_network(golden):
+    """The group kernel must not depend on neighbours sharing rows: shuffled positions (large unions), ragged tails,
+    and the full-range network (every int16 wrap of the byte-plane recombination)."""
+    import os
+
+    stress = np.load(os.path.join(os.path.dirname(__file__), "golden", "stress_seed99.npz"))
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(golden["boards"]))
+    with api.Nnue(N.synthetic(99, stress=True).image, 0) as ctx:
+        for n in (len(perm), 1, 15, 16, 17, 1000):
+            assert (ctx.eval_full(golden["boards"][perm[:n]]) == stress["evals"][perm[:n]]).all(), n
+
+
+def test_group_kernel_overflow_path(net, golden, monkeypatch):
+    """SP_NNUE_GROUP_LIMIT caps a group's threat-row union far below what 16 positions need: most groups overflow and are
+    redone by the per-position kernel; results stay exact and malformed boards are still reported."""
+    monkeypatch.setenv("SP_NNUE_GROUP_LIMIT", "70")
+    with api.Nnue(net.image, 0) as ctx:
+        assert (ctx.eval_full(golden["boards"]) == golden["evals"]).all()
+        bad = golden["boards"][:40].copy()
+        bad["occupancy"][19] = 0
+        out = np.zeros(40, dtype=np.int32)
+        with pytest.raises(api.NnueError):
+            ctx.eval_full(bad, out)
+        assert out[19] == INT32_MIN and (np.delete(out, 19) == np.delete(golden["evals"][:40], 19)).all()
