@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -50,6 +51,9 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef SP_ENQ_PREFETCH
 #define SP_ENQ_PREFETCH 0 /* 1 (prepared, NOT yet run on a GPU): the board enumeration fetches round k + 1's ray while round k works
                              (today one dependent 64-bit table load per round: 2.7 % of ft_full's samples wait on it) */
+#endif
+#ifndef SP_GROUP_TIMING
+#define SP_GROUP_TIMING 0 /* 1: ft_group_kernel prints CTA 0's clocks per phase (diagnostics; tools/gpu scripts) */
 #endif
 #ifndef SP_FULL_MIN_BLOCKS
 #define SP_FULL_MIN_BLOCKS 4

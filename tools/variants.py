@@ -18,6 +18,8 @@ VARIANTS = {
     # slot update kernel (self-play path): CTAs per SM
     "slots3": {"SP_SLOTS_MIN_BLOCKS": 3},
     "slots4": {"SP_SLOTS_MIN_BLOCKS": 4},
+    # tensor-core full refresh: CTA 0 prints its clocks per phase
+    "group_timing": {"SP_GROUP_TIMING": 1},
 }
 
 
