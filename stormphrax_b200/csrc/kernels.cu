@@ -224,7 +224,7 @@ __device__ __forceinline__ int enqueue_pawn_pairs(
 /* Whole-board enumeration (nnue_state.cpp:309-354, 440-449), lane-per-piece: eight uniform rounds, round k
  * looks along ray k (sliders, pawns) or at knight offset k; then the pawn pairs. */
 /* The threat / pawn-pair half of the enumeration: lane l looks from piece l (`sq`, `piece`; `has` = the lane has one). */
-template <typename Flush>
+template <int kUnroll = kEnqUnroll, typename Flush>
 __device__ __forceinline__ int enqueue_board_threats(
     const FeatureTables& t, const BoardView& b, bool has, int sq, int piece, int lane, uint32_t* tasks, int n_tasks, Flush&& flush) {
     const int type = piece >> 1;
@@ -233,7 +233,7 @@ __device__ __forceinline__ int enqueue_board_threats(
     const bool slider_like = attacker && type != kKnight; /* pawns look along rays too */
     uint64_t next_ray = slider_like ? t.rays[0][sq] : 0;
 #endif
-#pragma unroll kEnqUnroll
+#pragma unroll kUnroll
     for (int k = 0; k < 8; ++k) {
 #if SP_ENQ_PREFETCH
         const uint64_t ray = next_ray;
@@ -2010,7 +2010,11 @@ cudaError_t launch_ft_group(
     }
     cudaMemsetAsync(overflow, 0, sizeof(uint32_t), stream);
     const size_t n_groups = (n + kGroupN - 1) / kGroupN;
-    const unsigned grid = static_cast<unsigned>(std::min<size_t>(n_groups, static_cast<size_t>(sm_count) * 2));
+    static const int ctas_per_sm = [] { /* experiments: SP_NNUE_GROUP_CTAS=1 leaves every CTA an SM of its own */
+        const char* v = std::getenv("SP_NNUE_GROUP_CTAS");
+        return v && std::atoi(v) == 1 ? 1 : 2;
+    }();
+    const unsigned grid = static_cast<unsigned>(std::min<size_t>(n_groups, static_cast<size_t>(sm_count) * ctas_per_sm));
     /* SP_NNUE_GROUP_LIMIT=<threat rows>: a smaller union bound, so that tests can drive groups down the overflow path */
     static const uint32_t thr_limit = [] {
         const char* v = std::getenv("SP_NNUE_GROUP_LIMIT");

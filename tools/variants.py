@@ -20,6 +20,9 @@ VARIANTS = {
     "slots4": {"SP_SLOTS_MIN_BLOCKS": 4},
     # tensor-core full refresh: CTA 0 prints its clocks per phase
     "group_timing": {"SP_GROUP_TIMING": 1},
+    "group_timing_unroll2": {"SP_GROUP_TIMING": 1, "SP_ENQ_UNROLL": 2},
+    "group_unroll2": {"SP_ENQ_UNROLL": 2},
+    "group_unroll8": {"SP_ENQ_UNROLL": 8},
 }
 
 
