@@ -783,12 +783,15 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+/* The suspend-time hint lets the hardware park the warp until the phase completes (or the hint expires) instead of
+ * returning at once: without it a waiting warp spins -- in ft_group_kernel a third of ALL executed instructions were
+ * TRYWAIT / BRA / YIELD of such loops (ncu, profiles/r2_ft_group_ncu_v1.md), stealing issue slots from the working warps. */
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(smem_addr(bar)), "r"(parity)
+        : "r"(smem_addr(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return done != 0;
 }

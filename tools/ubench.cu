@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(512) bw_probe(const uint4* __restrict__ buf, s
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     uint4 v;
-                    asm volatile("ld.global.ca.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(win + u * 512 + threadIdx.x));
+                    asm volatile("ld.global.ca.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                 : "l"(win + ((u * 512 + threadIdx.x + rep * 32) & 4095)) : "memory");
                     acc += v.x ^ v.y ^ v.z ^ v.w;
                 }
         } else if (MODE == 2) {
