@@ -581,6 +581,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the evaluator has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL's version banner goes to stdout, which carries the ONE JSON line
     D.init("nccl", local_rank)
     g = Gpu(local_rank)
     ctx = g.ctx
