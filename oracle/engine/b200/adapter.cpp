@@ -5,8 +5,15 @@
  */
 #include <eval/nnue_state.h> // angle brackets throughout: these must be found through the shadow tree, not next to this file
 
+#include <eval/batch.h>
+
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
+
+#include <sys/mman.h>
+#include <ucontext.h>
 
 #include <datagen/marlinformat.h>
 #include <position.h>
@@ -18,6 +25,37 @@ namespace mirror = sp::host::eval;
 namespace stormphrax::eval {
     namespace {
         std::atomic<u32> s_nextSlot{0};
+
+        // ---- fibers: one scheduler per host thread
+        struct Fiber {
+            ucontext_t context{};
+            void* stack{};
+            usize stackBytes{};
+            std::function<void()>* job{};
+            bool done{false};
+        };
+
+        struct Scheduler {
+            ucontext_t main{};
+            Fiber* current{};
+            mirror::EvalBatch* batch{};
+            u64 queued{};
+        };
+
+        thread_local Scheduler* t_scheduler = nullptr;
+
+        void fiberEntry() {
+            auto* self = t_scheduler->current;
+            (*self->job)();
+            self->done = true;
+            swapcontext(&self->context, &t_scheduler->main);
+        }
+
+        // called from NnueState::evaluate inside a fiber: back to the scheduler until the round's batch has been flushed
+        void yieldToScheduler() {
+            auto* self = t_scheduler->current;
+            swapcontext(&self->context, &t_scheduler->main);
+        }
 
         SpPackedBoard pack(const Position& pos) {
             const auto board = datagen::marlinformat::PackedBoard::pack(pos, 0);
@@ -68,6 +106,10 @@ namespace stormphrax::eval {
     }
 
     void NnueState::reset(const Position& pos) {
+        if (t_scheduler) {
+            m_impl->state.invalidate(); // lazily: the next evaluation rebuilds from its own board, inside the round's batch
+            return;
+        }
         m_impl->state.resetPacked(pack(pos));
     }
 
@@ -81,14 +123,76 @@ namespace stormphrax::eval {
     }
 
     void NnueState::applyImmediately(const UpdateContext&, const Position& pos) {
+        if (t_scheduler) {
+            m_impl->state.applyLazily();
+            return;
+        }
         m_impl->state.applyPacked(pack(pos));
     }
 
     i32 NnueState::evaluate(const Position& pos, Color stm) {
+        if (t_scheduler) {
+            i32 out = 0;
+            m_impl->state.evaluateAsyncPacked(*t_scheduler->batch, pack(pos), stm.raw(), &out);
+            ++t_scheduler->queued;
+            yieldToScheduler(); // resumed after EvalBatch::flush() has written `out`
+            return out;
+        }
         return m_impl->state.evaluatePacked(pack(pos), stm.raw());
     }
 
     i32 NnueState::evaluateOnce(const Position& pos, Color stm) {
         return mirror::NnueState::evaluateOncePacked(pack(pos), stm.raw());
     }
+    namespace batch {
+        Stats runFibers(std::vector<std::function<void()>>& jobs, usize stackBytes) {
+            Stats stats{};
+            Scheduler scheduler{};
+            mirror::EvalBatch evalBatch{mirror::getNetwork()};
+            scheduler.batch = &evalBatch;
+            std::vector<Fiber> fibers(jobs.size());
+            for (usize i = 0; i < jobs.size(); ++i) {
+                auto& f = fibers[i];
+                f.job = &jobs[i];
+                f.stackBytes = stackBytes;
+                f.stack = mmap(nullptr, stackBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK | MAP_NORESERVE, -1, 0);
+                if (f.stack == MAP_FAILED) {
+                    eprintln("runFibers: cannot map a fiber stack");
+                    std::abort();
+                }
+                getcontext(&f.context);
+                f.context.uc_stack.ss_sp = f.stack;
+                f.context.uc_stack.ss_size = stackBytes;
+                f.context.uc_link = nullptr;
+                makecontext(&f.context, fiberEntry, 0);
+            }
+            t_scheduler = &scheduler;
+            usize live = fibers.size();
+            while (live > 0) {
+                for (auto& f : fibers) {
+                    if (f.done) {
+                        continue;
+                    }
+                    scheduler.current = &f;
+                    swapcontext(&scheduler.main, &f.context); // until it asks for an evaluation or finishes
+                    if (f.done) {
+                        --live;
+                    }
+                }
+                if (evalBatch.pending() > 0) {
+                    if (evalBatch.flush() != SP_OK) {
+                        eprintln("runFibers: EvalBatch::flush failed: {}", mirror::lastError());
+                        std::abort();
+                    }
+                    ++stats.rounds;
+                }
+            }
+            stats.evaluations = scheduler.queued;
+            t_scheduler = nullptr;
+            for (auto& f : fibers) {
+                munmap(f.stack, f.stackBytes);
+            }
+            return stats;
+        }
+    } // namespace batch
 } // namespace stormphrax::eval

@@ -10,6 +10,14 @@
  *                                                   playouts: staticEvalOnce == staticEval(nnueState) after
  *                                                   applyMove<BoardObserver> + applyImmediately; prints an eval checksum
  *   <binary> <network.nnue> datagen <dir> <seconds>  the engine's own datagen::run (one thread), interrupted after <seconds>
+ *   <binary> <network.nnue> searches <n> <depth> <fibers 0|1>
+ *                                                   n independent fixed-depth searches (own Searcher each, roots = random playouts):
+ *                                                   one after the other, or (sp_engine_b200, fibers = 1) as fibers of one thread whose
+ *                                                   evaluations are answered in device batches; prints the node count of each search
+ *   <binary> <network.nnue> games <n> <nodes> <plies> <seed> <fibers 0|1>
+ *                                                   BASELINE configs[4] in miniature: n concurrent self-play games, datagen's per-move
+ *                                                   search (runDatagenSearch, soft node limit <nodes>), <plies> moves each; prints
+ *                                                   nodes, nodes/s, a checksum of (move, score) and the batch statistics
  *
  * Bit-exact evaluations make both binaries walk the same search trees: their bench node counts must be identical.
  */
@@ -21,6 +29,9 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+#include <functional>
+#include <memory>
 
 #include "bench.h"
 #include "cuckoo.h"
@@ -35,10 +46,25 @@
 
 using namespace stormphrax;
 
-#ifndef SP_EVAL_B200
+#ifdef SP_EVAL_B200
+    #include "eval/batch.h"
+#else
 namespace stormphrax::eval {
     bool oracleLoadNetwork(const std::byte* payload, usize size);
-}
+
+    namespace batch { // the CPU build has nothing to batch: same entry point, jobs run one after the other
+        struct Stats {
+            u64 rounds{};
+            u64 evaluations{};
+        };
+        inline Stats runFibers(std::vector<std::function<void()>>& jobs, usize = 0) {
+            for (auto& job : jobs) {
+                job();
+            }
+            return {};
+        }
+    } // namespace batch
+} // namespace stormphrax::eval
 #endif
 
 namespace {
@@ -78,6 +104,152 @@ namespace {
         println("evalcheck: {} positions, {} mismatches, checksum {:016x}", positions, mismatches, checksum);
         return mismatches ? 1 : 0;
     }
+    // a random legal playout from the start position (the reference's own generator and RNG): `plies` moves
+    Position randomPosition(u64 seed, u32 plies, std::vector<u64>* keys = nullptr) {
+        util::rng::Jsf64Rng rng{seed};
+        auto pos = Position::startpos();
+        for (u32 ply = 0; ply < plies; ++ply) {
+            ScoredMoveList moves;
+            generateAll(moves, pos);
+            StaticVector<Move, 256> legal;
+            for (const auto [move, score] : moves) {
+                if (pos.isLegal(move)) {
+                    legal.push(move);
+                }
+            }
+            if (legal.empty()) {
+                break;
+            }
+            if (keys) {
+                keys->push_back(pos.key());
+            }
+            pos = pos.applyMove(legal[rng.nextU32(static_cast<u32>(legal.size()))]);
+        }
+        return pos;
+    }
+
+    int searches(u32 n, i32 depth, bool fibers) {
+        opts::mutableOpts().chess960 = false;
+        util::rng::SeedGenerator seeds{1234};
+        std::vector<std::unique_ptr<search::Searcher>> searchers(n);
+        std::vector<usize> nodes(n, 0);
+        std::vector<std::function<void()>> jobs;
+        for (u32 i = 0; i < n; ++i) {
+            searchers[i] = std::make_unique<search::Searcher>(1);
+            auto& searcher = *searchers[i];
+            searcher.setSilent(true);
+            searcher.setLimiter(limit::SearchLimiter{util::Instant::now()});
+            searcher.setMaxDepth(depth);
+            auto& thread = searcher.take();
+            searcher.newGame();
+            thread.rootPos = randomPosition(seeds.nextSeed(), 16 + i % 24);
+            jobs.emplace_back([&searcher, &nodes, i] {
+                search::BenchData data{};
+                searcher.runBenchSearch(data); // src/search.cpp:241-266: reset + searchRoot, as `bench` runs it
+                nodes[i] = data.nodes;
+            });
+        }
+        const auto start = util::Instant::now();
+        eval::batch::Stats stats{};
+        if (fibers) {
+            stats = eval::batch::runFibers(jobs);
+        } else {
+            for (auto& job : jobs) {
+                job();
+            }
+        }
+        const auto seconds = start.elapsed();
+        usize total = 0;
+        print("search nodes:");
+        for (const auto count : nodes) {
+            print(" {}", count);
+            total += count;
+        }
+        println();
+        println(
+            "searches: {} searches depth {} {} nodes {:.3f} seconds {} nps rounds {} evaluations {}",
+            n,
+            depth,
+            total,
+            seconds,
+            static_cast<usize>(static_cast<f64>(total) / seconds),
+            stats.rounds,
+            stats.evaluations
+        );
+        return 0;
+    }
+
+    int games(u32 n, usize softNodes, u32 plies, u64 seed, bool fibers) {
+        opts::mutableOpts().chess960 = false;
+        util::rng::SeedGenerator seeds{seed};
+        std::vector<std::unique_ptr<search::Searcher>> searchers(n);
+        std::vector<usize> nodes(n, 0);
+        std::vector<u64> sums(n, 0);
+        std::vector<std::function<void()>> jobs;
+        for (u32 i = 0; i < n; ++i) {
+            searchers[i] = std::make_unique<search::Searcher>(1);
+            auto& searcher = *searchers[i];
+            searcher.setSilent(true);
+            auto& thread = searcher.take();
+            thread.datagen = true;
+            limit::SearchLimiter limiter{util::Instant::now()}; // datagen.cpp:113-121
+            limiter.setHardNodes(softNodes * 40);
+            limiter.setSoftNodes(softNodes);
+            searcher.setLimiter(limiter);
+            searcher.setMaxDepth(kMaxDepth);
+            searcher.newGame();
+            thread.search = search::SearchData{};
+            thread.keyHistory.clear();
+            thread.rootPos = randomPosition(seeds.nextSeed(), 8 + i % 2, &thread.keyHistory); // datagen.cpp:153-171: 8 or 9 random plies
+            jobs.emplace_back([&searcher, &thread, &nodes, &sums, i, plies] {
+                auto& pos = thread.rootPos;
+                thread.nnueState.reset(pos); // datagen.cpp:179
+                for (u32 ply = 0; ply < plies; ++ply) {
+                    const auto [score, normScore] = searcher.runDatagenSearch(); // datagen.cpp:206
+                    nodes[i] += thread.search.loadNodes();
+                    thread.search = search::SearchData{};
+                    const auto move = thread.rootMoves[0].pv.moves[0];
+                    if (!move) {
+                        break;
+                    }
+                    sums[i] = sums[i] * 0x100000001B3ull + (static_cast<u64>(move.data()) << 32 | static_cast<u32>(score));
+                    eval::UpdateContext ctx{};
+                    thread.keyHistory.push_back(pos.key());
+                    pos = pos.applyMove(move, eval::BoardObserver{ctx}); // datagen.cpp:257-260
+                    thread.nnueState.applyImmediately(ctx, pos);
+                }
+            });
+        }
+        const auto start = util::Instant::now();
+        eval::batch::Stats stats{};
+        if (fibers) {
+            stats = eval::batch::runFibers(jobs);
+        } else {
+            for (auto& job : jobs) {
+                job();
+            }
+        }
+        const auto seconds = start.elapsed();
+        usize total = 0;
+        u64 checksum = 0;
+        for (u32 i = 0; i < n; ++i) {
+            total += nodes[i];
+            checksum = checksum * 0x9E3779B97F4A7C15ull + sums[i];
+        }
+        println(
+            "games: {} games {} plies soft {} nodes: {} nodes {:.3f} seconds {} nps checksum {:016x} rounds {} evaluations {}",
+            n,
+            plies,
+            softNodes,
+            total,
+            seconds,
+            static_cast<usize>(static_cast<f64>(total) / seconds),
+            checksum,
+            stats.rounds,
+            stats.evaluations
+        );
+        return 0;
+    }
 } // namespace
 
 int main(int argc, char** argv) {
@@ -115,6 +287,16 @@ int main(int argc, char** argv) {
         bench::run(argc > 3 ? std::atoi(argv[3]) : bench::kDefaultBenchDepth, bench::kDefaultBenchTtSize);
     } else if (cmd == "evalcheck") {
         rc = evalCheck(argc > 3 ? static_cast<u32>(std::atoi(argv[3])) : 4, argc > 4 ? std::strtoull(argv[4], nullptr, 10) : 42);
+    } else if (cmd == "searches" && argc > 5) {
+        rc = searches(static_cast<u32>(std::atoi(argv[3])), std::atoi(argv[4]), std::atoi(argv[5]) != 0);
+    } else if (cmd == "games" && argc > 7) {
+        rc = games(
+            static_cast<u32>(std::atoi(argv[3])),
+            static_cast<usize>(std::atol(argv[4])),
+            static_cast<u32>(std::atoi(argv[5])),
+            std::strtoull(argv[6], nullptr, 10),
+            std::atoi(argv[7]) != 0
+        );
     } else if (cmd == "datagen" && argc > 4) {
         const int seconds = std::atoi(argv[4]);
         std::thread timer{[seconds] {

@@ -36,6 +36,11 @@ def main():
             out["bench_nodes"][str(depth)] = int(m.group(1))
         m = re.search(r"evalcheck: (\d+) positions, (\d+) mismatches, checksum ([0-9a-f]+)", run(net_path, "evalcheck", 20, 42))
         out["evalcheck"] = {"games": 20, "seed": 42, "positions": int(m.group(1)), "mismatches": int(m.group(2)), "checksum": m.group(3)}
+        # independent fixed-depth searches and miniature self-play games: what the fiber scheduler must reproduce in batches
+        m = re.search(r"search nodes:((?: \d+)+)", run(net_path, "searches", 24, 3, 0))
+        out["searches"] = {"n": 24, "depth": 3, "nodes": [int(x) for x in m.group(1).split()]}
+        m = re.search(r"games: .* nodes: (\d+) nodes .* checksum ([0-9a-f]+)", run(net_path, "games", 16, 400, 4, 42, 0))
+        out["games"] = {"n": 16, "soft_nodes": 400, "plies": 4, "seed": 42, "nodes": int(m.group(1)), "checksum": m.group(2)}
     with open(os.path.join(ROOT, "tests", "golden", "engine_seed7.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps(out))

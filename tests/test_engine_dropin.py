@@ -81,3 +81,46 @@ def test_datagen_invariant_and_eval_checksum_on_the_b200_evaluator(net_path, gol
     b200 = _engine("sp_engine_b200")
     e = golden["evalcheck"]
     assert _evalcheck(_run(b200, net_path, "evalcheck", e["games"], e["seed"])) == (e["positions"], 0, e["checksum"])
+
+
+def _searches(out):
+    return [int(x) for x in re.search(r"search nodes:((?: \d+)+)", out).group(1).split()]
+
+
+def _games(out):
+    m = re.search(r"games: .* nodes: (\d+) nodes .* checksum ([0-9a-f]+) rounds (\d+) evaluations (\d+)", out)
+    return int(m.group(1)), m.group(2), int(m.group(3)), int(m.group(4))
+
+
+def test_reference_engine_cpu_reproduces_its_search_and_game_goldens(net_path, golden):
+    from oracle.bind import ref_isa_available
+
+    if "avx2" not in ref_isa_available():
+        pytest.skip("host cannot run the AVX2 build of the reference")
+    cpu = _engine("sp_engine_cpu")
+    s, g = golden["searches"], golden["games"]
+    assert _searches(_run(cpu, net_path, "searches", s["n"], s["depth"], 0)) == s["nodes"]
+    nodes, checksum, _, _ = _games(_run(cpu, net_path, "games", g["n"], g["soft_nodes"], g["plies"], g["seed"], 0))
+    assert (nodes, checksum) == (g["nodes"], g["checksum"])
+
+
+@pytest.mark.gpu
+def test_batched_reference_searches_as_fibers_walk_the_same_trees(net_path, golden):
+    """SURVEY 8 f4, "host fibers first": many searches of the UNMODIFIED reference Searcher run as fibers of one host thread;
+    every NnueState::evaluate yields, and each round's requests are answered by one sp_nnue_batch submission.  Node counts per
+    search must equal the CPU engine's, searched one after the other."""
+    b200 = _engine("sp_engine_b200")
+    s = golden["searches"]
+    assert _searches(_run(b200, net_path, "searches", s["n"], s["depth"], 1)) == s["nodes"]
+    assert _searches(_run(b200, net_path, "searches", s["n"], s["depth"], 0)) == s["nodes"]  # the synchronous path too
+
+
+@pytest.mark.gpu
+def test_batched_reference_selfplay_games_as_fibers(net_path, golden):
+    """Concurrent self-play games with datagen's per-move search (runDatagenSearch + applyImmediately, datagen.cpp:206-260):
+    same moves and scores as on the CPU (checksum), evaluations answered in batches."""
+    b200 = _engine("sp_engine_b200")
+    g = golden["games"]
+    nodes, checksum, rounds, evaluations = _games(_run(b200, net_path, "games", g["n"], g["soft_nodes"], g["plies"], g["seed"], 1))
+    assert (nodes, checksum) == (g["nodes"], g["checksum"])
+    assert rounds > 0 and evaluations / rounds > g["n"] / 2  # really batched: most games contribute to a round
