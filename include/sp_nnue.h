@@ -98,8 +98,11 @@ int sp_nnue_update(
 int sp_nnue_eval_slots(SpNnue* ctx, const uint32_t* slots, const uint8_t* stm, size_t n, int32_t* out);
 /* One round of a batched driver (many NnueStates, one evaluation each) in ONE submission and one wait:
  * a refresh group, an update group -- each also evaluated, with the side to move of its boards, when its
- * output array is given -- and an evaluate-only group (stm as in sp_nnue_eval_slots).  The groups must not
- * depend on each other (different states).  Any group may be empty. */
+ * output array is given -- and an evaluate-only group (stm as in sp_nnue_eval_slots).  No item may read or
+ * write a slot that another item of the same call writes (different states; an in-place update src == dst is
+ * one item).  Any group may be empty.  Up to 1,024 items run as ONE kernel launch (small_batch_kernel: slot
+ * update, activation and the dense head per warp) between one host-to-device and one device-to-host copy --
+ * the size of a round of a few hundred searches; SP_NNUE_SMALL=0 sends them through the general kernels. */
 int sp_nnue_batch(
     SpNnue* ctx, const uint32_t* refresh_slots, const SpPackedBoard* refresh_boards, size_t n_refresh, int32_t* refresh_out,
     const uint32_t* src_slots, const uint32_t* dst_slots, const SpPackedBoard* after, size_t n_update, int32_t* update_out,

@@ -283,6 +283,26 @@ class Nnue:
         self._check(self._lib.sp_nnue_update_eval(self._h, src.ctypes.data, dst.ctypes.data, after.ctypes.data, src.size, out.ctypes.data))
         return out
 
+    def batch(self, refresh=None, update=None, evaluate=None):
+        """One round of a batched driver (sp_nnue_batch): refresh = (slots, boards), update = (src, dst, boards),
+        evaluate = (slots, stm or None).  Returns (refresh evals, update evals, evaluate evals); absent groups give None."""
+        u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)
+        r_slots = r_boards = r_out = u_src = u_dst = u_boards = u_out = e_slots = e_stm = e_out = None
+        n_r = n_u = n_e = 0
+        if refresh is not None:
+            r_slots, r_boards = u32(refresh[0]), _boards(refresh[1])
+            n_r, r_out = r_slots.size, np.empty(r_slots.size, dtype=np.int32)
+        if update is not None:
+            u_src, u_dst, u_boards = u32(update[0]), u32(update[1]), _boards(update[2])
+            n_u, u_out = u_src.size, np.empty(u_src.size, dtype=np.int32)
+        if evaluate is not None:
+            e_slots = u32(evaluate[0])
+            e_stm = None if evaluate[1] is None else np.ascontiguousarray(evaluate[1], dtype=np.uint8)
+            n_e, e_out = e_slots.size, np.empty(e_slots.size, dtype=np.int32)
+        self._check(self._lib.sp_nnue_batch(self._h, _ptr(r_slots), _ptr(r_boards), n_r, _ptr(r_out), _ptr(u_src), _ptr(u_dst), _ptr(u_boards), n_u, _ptr(u_out),
+                                            _ptr(e_slots), _ptr(e_stm), n_e, _ptr(e_out)))
+        return r_out, u_out, e_out
+
     def refresh_device(self, d_slots, d_boards, n: int, stream: int | None = None) -> None:
         self._check(self._lib.sp_nnue_refresh_device(self._h, _ptr(d_slots), _ptr(d_boards), n, stream))
 

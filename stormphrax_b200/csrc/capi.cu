@@ -63,6 +63,13 @@ struct SpNnue {
     uint8_t* d_stm = nullptr;
     size_t cap = 0;
 
+    /* search-sized rounds (small_batch_kernel): one pinned host block and its device twin, inputs | error word | results */
+    bool small = true;           /* SP_NNUE_SMALL=0: always take the general kernels */
+    size_t small_mapped = 64;    /* SP_NNUE_SMALL_MAPPED: up to this many items (<= 64) the kernel works on the host block directly (zero-copy) */
+    uint8_t* h_small = nullptr;
+    uint8_t* h_small_dev = nullptr; /* device address of h_small */
+    uint8_t* d_small = nullptr;
+
     SlotStore slots{};
     uint64_t counters[SP_NUM_COUNTERS] = {};
     std::string error;
@@ -464,6 +471,8 @@ static int create_impl(const void* net_image, size_t len, int device, SpNnue** o
     }
     if (const char* env = std::getenv("SP_NNUE_OVERLAP")) ctx->overlap = std::atoi(env) != 0;
     if (const char* env = std::getenv("SP_NNUE_SPLIT")) ctx->split = std::atoi(env) != 0;
+    if (const char* env = std::getenv("SP_NNUE_SMALL")) ctx->small = std::atoi(env) != 0;
+    if (const char* env = std::getenv("SP_NNUE_SMALL_MAPPED")) ctx->small_mapped = std::min<size_t>(64, std::strtoul(env, nullptr, 10));
     if (const char* env = std::getenv("SP_NNUE_FT")) ctx->group = std::strcmp(env, "warp") != 0; /* warp: one warp per position (ft_full_kernel) */
     if (const char* env = std::getenv("SP_NNUE_PLAN_REBUILDS")) ctx->plan_rebuilds = std::atoi(env) != 0;
     for (int b = 0; b < 2; ++b) {
@@ -547,6 +556,8 @@ void sp_nnue_destroy(SpNnue* ctx) {
     cudaFree(ctx->d_stm);
     cudaFree(ctx->slots.acc);
     cudaFree(ctx->slots.boards);
+    cudaFree(ctx->d_small);
+    cudaFreeHost(ctx->h_small);
     for (const auto& span : ctx->spans) cudaEventDestroy(span.a), cudaEventDestroy(span.b);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->stream && ctx->owns_stream) cudaStreamDestroy(ctx->stream);

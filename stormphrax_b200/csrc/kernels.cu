@@ -1980,6 +1980,7 @@ __global__ void wdl_kernel(const SpPackedBoard* __restrict__ boards, const int32
 }
 
 #include "ft_group.inc"
+#include "small_batch.inc"
 
 int grid_for(size_t n_warp_items, int warps_per_cta, int sm_count, int ctas_per_sm) {
     const size_t want = (n_warp_items + warps_per_cta - 1) / warps_per_cta;
@@ -1994,6 +1995,13 @@ void launch_ft_full(
     int sm_count, cudaStream_t stream) {
     if (!n) return;
     ft_full_kernel<<<grid_for(n, kWarpsPerCta, sm_count, SP_FULL_MIN_BLOCKS), kThreads, 0, stream>>>(net, boards, n, act, bucket, status);
+}
+
+void launch_small_batch(const DeviceNet& net, SlotStore slots, const SmallBatchArgs& a, int sm_count, cudaStream_t stream) {
+    const uint32_t total = a.n_refresh + a.n_update + a.n_eval;
+    if (!total) return;
+    SmallBatch sb{a.boards, a.dst, a.src, a.stm, a.out, a.error, a.item_error, a.n_refresh, a.n_update, a.n_eval, a.want};
+    small_batch_kernel<<<grid_for(total, kWarpsPerCta, sm_count, 2), kThreads, 0, stream>>>(net, slots, sb);
 }
 
 size_t ft_group_scratch_words(size_t n_positions) { return 1 + (n_positions + kGroupN - 1) / kGroupN; }

@@ -134,6 +134,21 @@ void launch_ft_games(
     const DeviceNet& net, const SpPackedBoard* boards, const uint32_t* game_start, uint32_t n_games, size_t n_boards,
     uint8_t* act, uint8_t* bucket, RebuildPlan plan, DeviceStatus* status, int sm_count, cudaStream_t stream);
 
+/* A search-sized round in ONE launch (small_batch.inc): refresh items [0, n_refresh), update items, evaluate-only items; a warp
+ * takes an item from the board record to the evaluation.  All pointers are device pointers (one staged block). */
+struct SmallBatchArgs {
+    const SpPackedBoard* boards;
+    const uint32_t* dst;
+    const uint32_t* src;
+    const uint8_t* stm;
+    int32_t* out;
+    int* error;
+    uint8_t* item_error;
+    uint32_t n_refresh, n_update, n_eval;
+    uint32_t want; /* bit 0: evaluate refresh items, bit 1: evaluate update items */
+};
+void launch_small_batch(const DeviceNet& net, SlotStore slots, const SmallBatchArgs& args, int sm_count, cudaStream_t stream);
+
 /* slots[i] -> act[i], bucket[i]; stm may be nullptr (use the stored board's side to move) */
 void launch_slot_activate(
     SlotStore slots, const uint32_t* slot_ids, const uint8_t* stm, size_t n, uint8_t* act, uint8_t* bucket,

@@ -140,3 +140,55 @@ def test_walker_rebuild_plan_variants(net, golden, monkeypatch, env):
             assert (out == golden[key + "evals"]).all(), (env, key)
         # a second call reuses the plan scratch
         assert (ctx.eval_playouts(golden["boards"], golden["starts"]) == golden["evals"]).all()
+
+
+@pytest.mark.parametrize("small", ["1", "copies", "0"])
+def test_search_sized_rounds_small_kernel_and_general_kernels(golden, monkeypatch, small):
+    """sp_nnue_batch and the slot entry points with a few dozen items: SP_NNUE_SMALL=1 (default) takes them through ONE fused
+    launch (small_batch_kernel: slot update + activation + dp4a L1 + L2 + L3 per warp), SP_NNUE_SMALL=0 through the general
+    kernels.  Both must give the reference's values -- here on the STRESS network, whose int16 / int32 sums wrap everywhere."""
+    import os
+
+    from stormphrax_b200 import net as N
+
+    stress = np.load(os.path.join(os.path.dirname(__file__), "golden", "stress_seed99.npz"))
+    boards, starts, evals = golden["boards"], golden["starts"], stress["evals"]
+    assert (np.diff(starts) >= 3).all()
+    monkeypatch.setenv("SP_NNUE_SMALL", "0" if small == "0" else "1")
+    if small == "copies":  # the staged block goes through cudaMemcpyAsync instead of being read in place (rounds above 64 items)
+        monkeypatch.setenv("SP_NNUE_SMALL_MAPPED", "0")
+    with api.Nnue(N.synthetic(99, stress=True).image, 0) as ctx:
+        n = len(starts) - 1
+        first = starts[:-1].astype(np.int64)
+        ctx.slots_reserve(3 * n)
+        ids = np.arange(n, dtype=np.uint32)
+        launches0 = int(ctx.counters()[api.CTR_LAUNCHES])
+        r, _, _ = ctx.batch(refresh=(ids, boards[first]))
+        assert (r == evals[first]).all()
+        if small != "0":
+            assert int(ctx.counters()[api.CTR_LAUNCHES]) - launches0 == 1  # one kernel for the whole round
+        # one round with all three groups: refresh other slots, advance the first ones, evaluate-only with both sides
+        stm_board = np.where(boards[first]["stm_ep"] & 0x80, 0, 1).astype(np.uint8)
+        r, u, e = ctx.batch(refresh=(ids + 2 * n, boards[first + 2]), update=(ids, ids + n, boards[first + 1]), evaluate=(ids, stm_board))
+        assert (r == evals[first + 2]).all() and (u == evals[first + 1]).all() and (e == evals[first]).all()
+        # push / pop: the parents are untouched, children of children work, explicit side to move differs from the stored one
+        assert (ctx.eval_slots(ids) == evals[first]).all()
+        assert (ctx.update_eval(ids + n, ids + n, boards[first + 2]) == evals[first + 2]).all()
+        flipped = ctx.eval_slots(ids[:4], stm=1 - stm_board[:4])
+        from oracle.bind import COracle
+
+        o = COracle()
+        o.load_net(N.synthetic(99, stress=True).image)
+        for k in range(4):
+            b = boards[first[k] : first[k] + 1]
+            psq, thr = o.accumulators(b)
+            bucket = (bin(int(b["occupancy"][0])).count("1") - 2) // 4
+            assert flipped[k] == o.forward_acc(psq, thr, int(1 - stm_board[k]), bucket)
+        # errors: a slot out of range, an update from a slot that was never filled
+        with pytest.raises(api.NnueError) as err:
+            ctx.batch(refresh=([1 << 30], boards[:1]))
+        assert err.value.status == api.SP_ERR_INVALID
+        ctx.slots_reserve(3 * n + 16)
+        with pytest.raises(api.NnueError) as err:
+            ctx.update_eval([3 * n + 8], [3 * n + 9], boards[:1])
+        assert err.value.status == api.SP_ERR_BAD_BOARD

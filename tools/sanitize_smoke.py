@@ -28,18 +28,24 @@ def main():
     with api.Nnue(net.image, 0) as ctx:
         assert np.array_equal(ctx.eval_full(boards), want), "full refresh"
         assert np.array_equal(ctx.eval_playouts(boards, starts), want), "playouts"
-        n = len(starts) - 1
-        ctx.slots_reserve(2 * n)
-        first = starts[:-1].astype(np.int64)
-        ids = np.arange(n, dtype=np.uint32)
-        ctx.refresh(2 * ids, boards[first])
-        assert np.array_equal(ctx.eval_slots(2 * ids), want[first]), "slot refresh + evaluate"
-        got = ctx.update_eval(2 * ids, 2 * ids + 1, boards[first + 1])
-        assert np.array_equal(got, want[first + 1]), "slot update + evaluate"
         adj = ctx.adjust(boards[:64], want[:64])
         assert adj.shape == (64,)
         norm, win, loss = ctx.wdl(boards[:64], want[:64])
         assert norm.shape == win.shape == loss.shape == (64,)
+    n = len(starts) - 1
+    first = starts[:-1].astype(np.int64)
+    ids = np.arange(n, dtype=np.uint32)
+    for small in ("1", "0"):  # the one-launch kernel for search-sized rounds, then the general slot kernels
+        os.environ["SP_NNUE_SMALL"] = small
+        with api.Nnue(net.image, 0) as ctx:
+            ctx.slots_reserve(3 * n)
+            ctx.refresh(2 * n + ids, boards[first])
+            ctx.refresh(2 * ids, boards[first])
+            assert np.array_equal(ctx.eval_slots(2 * ids), want[first]), "slot refresh + evaluate"
+            got = ctx.update_eval(2 * ids, 2 * ids + 1, boards[first + 1])
+            assert np.array_equal(got, want[first + 1]), "slot update + evaluate"
+            r, u, e = ctx.batch(refresh=(2 * ids, boards[first + 2]), update=(2 * ids + 1, 2 * ids + 1, boards[first + 2]), evaluate=(2 * n + ids, None))
+            assert np.array_equal(r, want[first + 2]) and np.array_equal(u, want[first + 2]) and np.array_equal(e, want[first]), "batch"
     print(f"sanitize_smoke ok: {len(boards)} positions, {n} games")
 
 
