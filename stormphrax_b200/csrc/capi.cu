@@ -472,6 +472,8 @@ static int create_impl(const void* net_image, size_t len, int device, SpNnue** o
     if (const char* env = std::getenv("SP_NNUE_OVERLAP")) ctx->overlap = std::atoi(env) != 0;
     if (const char* env = std::getenv("SP_NNUE_SPLIT")) ctx->split = std::atoi(env) != 0;
     if (const char* env = std::getenv("SP_NNUE_SMALL")) ctx->small = std::atoi(env) != 0;
+    ctx->head_sort.variant = head_variant_from_env();
+    ctx->head_sort.direct_max = head_direct_max_from_env();
     if (const char* env = std::getenv("SP_NNUE_SMALL_MAPPED")) ctx->small_mapped = std::min<size_t>(64, std::strtoul(env, nullptr, 10));
     if (const char* env = std::getenv("SP_NNUE_FT")) ctx->group = std::strcmp(env, "warp") != 0; /* warp: one warp per position (ft_full_kernel) */
     if (const char* env = std::getenv("SP_NNUE_PLAN_REBUILDS")) ctx->plan_rebuilds = std::atoi(env) != 0;

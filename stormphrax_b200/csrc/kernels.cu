@@ -1604,6 +1604,165 @@ __device__ __noinline__ void head_issue_fill(HeadStreamShared& sh, const uint8_t
     }
 }
 
+/* Everything after L1 for a warp's 32 rows (two m16 tiles), shared by head_stream_kernel (L1 by mma.sync) and head_umma_kernel (L1 by
+ * tcgen05, read back with tcgen05.ld.16x256b -- the same C-fragment layout): c[mt][nt][2 hrow + cc] = L1 sum of row 16 mt + g + 8 hrow,
+ * output 8 t + 4 cc + nt.  w2_frags = the bucket's L2 weights in shared memory (l2_fragment_index). */
+__device__ __forceinline__ void head_tail(
+    const DeviceNet& net, int b, bool narrow_w2, const int (&c)[2][4][4], const uint32_t (&row_id)[2][2], const uint2* w2_frags,
+    int32_t* __restrict__ out, int lane) {
+    const int t = lane & 3;
+    /* ---- L1 epilogue (multilayer.h:219-256), skip term of L3, L2 inputs as byte limbs in A-fragment order:
+     * register index hrow + 2 cc = a0..a3 of an IMMA (row g | g+8, k-slots 4t.. | 16+4t..) */
+    uint32_t cr_l[2][2][4], sq_l[2][4][4], skip_dot[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            uint32_t dot = 0;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                uint32_t in_cr[4], in_sq[4];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int o = 8 * t + 4 * cc + nt;
+                    const int x = static_cast<int>(static_cast<uint32_t>(c[mt][nt][hrow * 2 + cc] >> 2)
+                                                   + static_cast<uint32_t>(__ldg(net.l1_b + b * SP_L2_SIZE + o)));
+                    const int cr = min(max(x, 0), 4096);
+                    int sq = static_cast<int>(static_cast<uint32_t>(x) * static_cast<uint32_t>(x)); /* wraps BEFORE the min */
+                    sq = min(sq, 16777216);
+                    dot += static_cast<uint32_t>(cr << 6) * static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + o))
+                         + static_cast<uint32_t>(sq >> 6) * static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + SP_L2_SIZE + o));
+                    in_cr[nt] = static_cast<uint32_t>(cr);       /* (cr << 6) >> 6: at most 0x1000 */
+                    in_sq[nt] = static_cast<uint32_t>(sq >> 12); /* (sq >> 6) >> 6, arithmetic */
+                }
+                /* 4 x 4 byte transposes: word `limb` = byte `limb` of the four values */
+                {
+                    const uint32_t lo01 = __byte_perm(in_cr[0], in_cr[1], 0x5140), lo23 = __byte_perm(in_cr[2], in_cr[3], 0x5140);
+                    cr_l[mt][0][hrow + 2 * cc] = __byte_perm(lo01, lo23, 0x5410);
+                    cr_l[mt][1][hrow + 2 * cc] = __byte_perm(lo01, lo23, 0x7632);
+                }
+                {
+                    const uint32_t lo01 = __byte_perm(in_sq[0], in_sq[1], 0x5140), lo23 = __byte_perm(in_sq[2], in_sq[3], 0x5140);
+                    const uint32_t hi01 = __byte_perm(in_sq[0], in_sq[1], 0x7362), hi23 = __byte_perm(in_sq[2], in_sq[3], 0x7362);
+                    sq_l[mt][0][hrow + 2 * cc] = __byte_perm(lo01, lo23, 0x5410);
+                    sq_l[mt][1][hrow + 2 * cc] = __byte_perm(lo01, lo23, 0x7632);
+                    sq_l[mt][2][hrow + 2 * cc] = __byte_perm(hi01, hi23, 0x5410);
+                    sq_l[mt][3][hrow + 2 * cc] = __byte_perm(hi01, hi23, 0x7632);
+                }
+            }
+            dot += __shfl_xor_sync(kFull, dot, 1);
+            dot += __shfl_xor_sync(kFull, dot, 2);
+            skip_dot[mt][hrow] = dot;
+        }
+
+    /* ---- L2 (multilayer.h:261-343) by Horner over the limb weight; lane (g, t) ends up with outputs
+     * 8 nt + 2t, + 1 of rows g and g + 8 */
+    int acc[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[mt][nt][k] = 0;
+    const uint2* w2 = w2_frags + lane;
+    auto shl8 = [&]() {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[mt][nt][k] = static_cast<int>(static_cast<uint32_t>(acc[mt][nt][k]) << 8);
+    };
+    /* The squared half of the inputs is negative only after a wrapped square (|x| > 46340): without
+     * one in this tile its limbs 2 and 3 are zero like those of the CReLU half. */
+    uint32_t high = 0;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) high |= sq_l[mt][2][r] | sq_l[mt][3][r];
+    const bool wide_inputs = __any_sync(kFull, high != 0);
+    if (narrow_w2 && !wide_inputs) {
+        /* Weights that fit int16 (true of the whole bucket, found at upload) are lo + 256 hi with lo = byte 0
+         * unsigned and hi = byte 1 SIGNED -- the same stored bytes, read by a u8 x s8 IMMA -- and inputs below
+         * 2^16 are a0 + 256 a1: in * w = a0 lo + 2^8 (a0 hi + a1 lo) + 2^16 a1 hi, four contractions per
+         * k-half instead of ten / seven. */
+#pragma unroll
+        for (int level = 2; level >= 0; --level) {
+            if (level < 2) shl8();
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int j = level - i; /* input limb i with weight limb j */
+                if (j < 0 || j > 1) continue;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint2 wf = w2[((j * 8 + nt) * 2 + ks) * 32];
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+                            const uint32_t* a = ks == 0 ? cr_l[mt][i] : sq_l[mt][i];
+                            if (j == 1) mma_u8s8(acc[mt][nt], a[0], a[1], a[2], a[3], wf.x, wf.y);
+                            else mma_u8u8(acc[mt][nt], a[0], a[1], a[2], a[3], wf.x, wf.y);
+                        }
+                    }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int shift = 3; shift >= 0; --shift) {
+            if (shift < 3) shl8();
+#pragma unroll
+            for (int i = 0; i <= shift; ++i) { /* input limb i with weight limb shift - i */
+                const int j = shift - i;
+                if (i >= 2 && !wide_inputs) continue; /* warp-uniform */
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    if (i < 2) {
+                        const uint2 wf = w2[((j * 8 + nt) * 2 + 0) * 32];
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+                            mma_u8u8(acc[mt][nt], cr_l[mt][i][0], cr_l[mt][i][1], cr_l[mt][i][2], cr_l[mt][i][3], wf.x, wf.y);
+                    }
+                    const uint2 wf = w2[((j * 8 + nt) * 2 + 1) * 32];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+                        mma_u8u8(acc[mt][nt], sq_l[mt][i][0], sq_l[mt][i][1], sq_l[mt][i][2], sq_l[mt][i][3], wf.x, wf.y);
+                }
+            }
+        }
+    }
+
+    /* ---- L3 + scale, multilayer.h:345-447, 484-489 */
+    uint32_t dot[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t b2a = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + nt * 8 + 2 * t));
+        const uint32_t b2b = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + nt * 8 + 2 * t + 1));
+        const uint32_t w3a = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + nt * 8 + 2 * t));
+        const uint32_t w3b = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + nt * 8 + 2 * t + 1));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int va = static_cast<int>(static_cast<uint32_t>(acc[mt][nt][2 * hrow]) + b2a);
+                const int vb = static_cast<int>(static_cast<uint32_t>(acc[mt][nt][2 * hrow + 1]) + b2b);
+                dot[mt][hrow] += static_cast<uint32_t>(min(max(va, 0), 262144)) * w3a + static_cast<uint32_t>(min(max(vb, 0), 262144)) * w3b;
+            }
+    }
+    const uint32_t bias3 = static_cast<uint32_t>(__ldg(net.l3_b + b));
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            uint32_t d = dot[mt][hrow];
+            d += __shfl_xor_sync(kFull, d, 1);
+            d += __shfl_xor_sync(kFull, d, 2);
+            const int32_t l3 = static_cast<int32_t>(d + skip_dot[mt][hrow] + bias3);
+            /* the final division truncates toward zero */
+            if (t == 0 && row_id[mt][hrow] != kHeadNoRow) out[row_id[mt][hrow]] = static_cast<int32_t>(static_cast<int64_t>(l3) * 400 / 16777216);
+        }
+}
+
 __global__ void __launch_bounds__(kStreamThreads, 1)
 head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __restrict__ out, HeadSort sort) {
     extern __shared__ __align__(16) unsigned char head_smem[];
@@ -1751,156 +1910,7 @@ head_stream_kernel(DeviceNet net, const uint8_t* __restrict__ act, int32_t* __re
             if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&sh.gen[stage]) = n / kHeadStages + 1;
             if (refill < my_tiles) issue_fill(refill, refill_row);
 
-            /* ---- L1 epilogue (multilayer.h:219-256), skip term of L3, L2 inputs as byte limbs in A-fragment order:
-             * register index hrow + 2 cc = a0..a3 of an IMMA (row g | g+8, k-slots 4t.. | 16+4t..) */
-            uint32_t cr_l[2][2][4], sq_l[2][4][4], skip_dot[2][2];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int hrow = 0; hrow < 2; ++hrow) {
-                    uint32_t dot = 0;
-#pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        uint32_t in_cr[4], in_sq[4];
-#pragma unroll
-                        for (int nt = 0; nt < 4; ++nt) {
-                            const int o = 8 * t + 4 * cc + nt;
-                            const int x = static_cast<int>(static_cast<uint32_t>(c[mt][nt][hrow * 2 + cc] >> 2)
-                                                           + static_cast<uint32_t>(__ldg(net.l1_b + b * SP_L2_SIZE + o)));
-                            const int cr = min(max(x, 0), 4096);
-                            int sq = static_cast<int>(static_cast<uint32_t>(x) * static_cast<uint32_t>(x)); /* wraps BEFORE the min */
-                            sq = min(sq, 16777216);
-                            dot += static_cast<uint32_t>(cr << 6) * static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + o))
-                                 + static_cast<uint32_t>(sq >> 6) * static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + SP_L2_SIZE + o));
-                            in_cr[nt] = static_cast<uint32_t>(cr);       /* (cr << 6) >> 6: at most 0x1000 */
-                            in_sq[nt] = static_cast<uint32_t>(sq >> 12); /* (sq >> 6) >> 6, arithmetic */
-                        }
-                        /* 4 x 4 byte transposes: word `limb` = byte `limb` of the four values */
-                        {
-                            const uint32_t lo01 = __byte_perm(in_cr[0], in_cr[1], 0x5140), lo23 = __byte_perm(in_cr[2], in_cr[3], 0x5140);
-                            cr_l[mt][0][hrow + 2 * cc] = __byte_perm(lo01, lo23, 0x5410);
-                            cr_l[mt][1][hrow + 2 * cc] = __byte_perm(lo01, lo23, 0x7632);
-                        }
-                        {
-                            const uint32_t lo01 = __byte_perm(in_sq[0], in_sq[1], 0x5140), lo23 = __byte_perm(in_sq[2], in_sq[3], 0x5140);
-                            const uint32_t hi01 = __byte_perm(in_sq[0], in_sq[1], 0x7362), hi23 = __byte_perm(in_sq[2], in_sq[3], 0x7362);
-                            sq_l[mt][0][hrow + 2 * cc] = __byte_perm(lo01, lo23, 0x5410);
-                            sq_l[mt][1][hrow + 2 * cc] = __byte_perm(lo01, lo23, 0x7632);
-                            sq_l[mt][2][hrow + 2 * cc] = __byte_perm(hi01, hi23, 0x5410);
-                            sq_l[mt][3][hrow + 2 * cc] = __byte_perm(hi01, hi23, 0x7632);
-                        }
-                    }
-                    dot += __shfl_xor_sync(kFull, dot, 1);
-                    dot += __shfl_xor_sync(kFull, dot, 2);
-                    skip_dot[mt][hrow] = dot;
-                }
-
-            /* ---- L2 (multilayer.h:261-343) by Horner over the limb weight; lane (g, t) ends up with outputs
-             * 8 nt + 2t, + 1 of rows g and g + 8 */
-            int acc[2][8][4];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) acc[mt][nt][k] = 0;
-            const uint2* w2 = sh.w2 + lane;
-            auto shl8 = [&]() {
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) acc[mt][nt][k] = static_cast<int>(static_cast<uint32_t>(acc[mt][nt][k]) << 8);
-            };
-            /* The squared half of the inputs is negative only after a wrapped square (|x| > 46340): without
-             * one in this tile its limbs 2 and 3 are zero like those of the CReLU half. */
-            uint32_t high = 0;
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) high |= sq_l[mt][2][r] | sq_l[mt][3][r];
-            const bool wide_inputs = __any_sync(kFull, high != 0);
-            if (narrow_w2 && !wide_inputs) {
-                /* Weights that fit int16 (true of the whole bucket, found at upload) are lo + 256 hi with lo = byte 0
-                 * unsigned and hi = byte 1 SIGNED -- the same stored bytes, read by a u8 x s8 IMMA -- and inputs below
-                 * 2^16 are a0 + 256 a1: in * w = a0 lo + 2^8 (a0 hi + a1 lo) + 2^16 a1 hi, four contractions per
-                 * k-half instead of ten / seven. */
-#pragma unroll
-                for (int level = 2; level >= 0; --level) {
-                    if (level < 2) shl8();
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int j = level - i; /* input limb i with weight limb j */
-                        if (j < 0 || j > 1) continue;
-#pragma unroll
-                        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {
-                                const uint2 wf = w2[((j * 8 + nt) * 2 + ks) * 32];
-#pragma unroll
-                                for (int mt = 0; mt < 2; ++mt) {
-                                    const uint32_t* a = ks == 0 ? cr_l[mt][i] : sq_l[mt][i];
-                                    if (j == 1) mma_u8s8(acc[mt][nt], a[0], a[1], a[2], a[3], wf.x, wf.y);
-                                    else mma_u8u8(acc[mt][nt], a[0], a[1], a[2], a[3], wf.x, wf.y);
-                                }
-                            }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int shift = 3; shift >= 0; --shift) {
-                    if (shift < 3) shl8();
-#pragma unroll
-                    for (int i = 0; i <= shift; ++i) { /* input limb i with weight limb shift - i */
-                        const int j = shift - i;
-                        if (i >= 2 && !wide_inputs) continue; /* warp-uniform */
-#pragma unroll
-                        for (int nt = 0; nt < 8; ++nt) {
-                            if (i < 2) {
-                                const uint2 wf = w2[((j * 8 + nt) * 2 + 0) * 32];
-#pragma unroll
-                                for (int mt = 0; mt < 2; ++mt)
-                                    mma_u8u8(acc[mt][nt], cr_l[mt][i][0], cr_l[mt][i][1], cr_l[mt][i][2], cr_l[mt][i][3], wf.x, wf.y);
-                            }
-                            const uint2 wf = w2[((j * 8 + nt) * 2 + 1) * 32];
-#pragma unroll
-                            for (int mt = 0; mt < 2; ++mt)
-                                mma_u8u8(acc[mt][nt], sq_l[mt][i][0], sq_l[mt][i][1], sq_l[mt][i][2], sq_l[mt][i][3], wf.x, wf.y);
-                        }
-                    }
-                }
-            }
-
-            /* ---- L3 + scale, multilayer.h:345-447, 484-489 */
-            uint32_t dot[2][2] = {{0, 0}, {0, 0}};
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                const uint32_t b2a = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + nt * 8 + 2 * t));
-                const uint32_t b2b = static_cast<uint32_t>(__ldg(net.l2_b + b * SP_L3_SIZE + nt * 8 + 2 * t + 1));
-                const uint32_t w3a = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + nt * 8 + 2 * t));
-                const uint32_t w3b = static_cast<uint32_t>(__ldg(net.l3_w + b * SP_L3_SIZE + nt * 8 + 2 * t + 1));
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                    for (int hrow = 0; hrow < 2; ++hrow) {
-                        const int va = static_cast<int>(static_cast<uint32_t>(acc[mt][nt][2 * hrow]) + b2a);
-                        const int vb = static_cast<int>(static_cast<uint32_t>(acc[mt][nt][2 * hrow + 1]) + b2b);
-                        dot[mt][hrow] += static_cast<uint32_t>(min(max(va, 0), 262144)) * w3a + static_cast<uint32_t>(min(max(vb, 0), 262144)) * w3b;
-                    }
-            }
-            const uint32_t bias3 = static_cast<uint32_t>(__ldg(net.l3_b + b));
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int hrow = 0; hrow < 2; ++hrow) {
-                    uint32_t d = dot[mt][hrow];
-                    d += __shfl_xor_sync(kFull, d, 1);
-                    d += __shfl_xor_sync(kFull, d, 2);
-                    const int32_t l3 = static_cast<int32_t>(d + skip_dot[mt][hrow] + bias3);
-                    /* the final division truncates toward zero */
-                    if (t == 0 && row_id[mt][hrow] != kHeadNoRow) out[row_id[mt][hrow]] = static_cast<int32_t>(static_cast<int64_t>(l3) * 400 / 16777216);
-                }
+            head_tail(net, b, narrow_w2, c, row_id, sh.w2, out, lane);
         }
         cur = seg_end;
     }
@@ -1981,6 +1991,7 @@ __global__ void wdl_kernel(const SpPackedBoard* __restrict__ boards, const int32
 
 #include "ft_group.inc"
 #include "small_batch.inc"
+#include "head_umma.inc"
 
 int grid_for(size_t n_warp_items, int warps_per_cta, int sm_count, int ctas_per_sm) {
     const size_t want = (n_warp_items + warps_per_cta - 1) / warps_per_cta;
@@ -2095,19 +2106,28 @@ void launch_slot_activate(
     slot_activate_kernel<<<grid_for(n, kWarpsPerCta, sm_count, 4), kThreads, 0, stream>>>(slots, slot_ids, stm, n, act, bucket, status);
 }
 
-/* SP_NNUE_HEAD=tiles selects the earlier head_kernel (A/B measurements); default is head_stream_kernel. */
-static bool head_uses_tiles() {
-    static const bool tiles = [] {
-        const char* v = std::getenv("SP_NNUE_HEAD");
-        return v && std::strcmp(v, "tiles") == 0;
-    }();
-    return tiles;
+/* SP_NNUE_HEAD: umma (default) = head_umma_kernel (L1 on tcgen05), stream = head_stream_kernel (L1 by mma.sync from bulk-copied
+ * rows), tiles = the first head_kernel; the older two are kept for A/B measurements and as cross-checks in the tests. */
+int head_variant_from_env() {
+    const char* v = std::getenv("SP_NNUE_HEAD");
+    if (v && std::strcmp(v, "tiles") == 0) return 2;
+    if (v && std::strcmp(v, "stream") == 0) return 1;
+    return 0;
+}
+/* SP_NNUE_HEAD_DIRECT: up to this many positions take the one-launch warp-per-position kernel (0 = never) */
+uint32_t head_direct_max_from_env() {
+    const char* v = std::getenv("SP_NNUE_HEAD_DIRECT");
+    return v ? static_cast<uint32_t>(std::strtoul(v, nullptr, 10)) : 2048u;
 }
 
 cudaError_t launch_head(
     const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, const uint32_t* range, HeadSort sort,
     int sm_count, cudaStream_t stream, uint32_t range_len) {
     if (!n) return cudaSuccess;
+    if (n <= sort.direct_max) {
+        head_direct_kernel<<<grid_for(n, kWarpsPerCta, sm_count, 2), kThreads, 0, stream>>>(net, act, bucket, n, range, range_len, out);
+        return cudaPeekAtLastError();
+    }
     const size_t slots = std::min(sort.capacity, n + kHeadGroupPad * SP_OUTPUT_BUCKETS); /* n bounds the rows of this launch */
     if (n <= kHeadSortSmall) {
         head_sort_small_kernel<<<1, 1024, 0, stream>>>(bucket, n, range, range_len, sort, out);
@@ -2125,12 +2145,16 @@ cudaError_t launch_head(
         /* fails with "no kernel image" on a device this sm_100a-only library cannot run on: report it here, not at the launch */
         cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadShared)));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(head_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadStreamShared)));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(head_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HeadUmmaShared) + 1024));
         if (e != cudaSuccess) return e;
         configured.fetch_or(uint64_t{1} << (device & 63), std::memory_order_relaxed);
     }
-    if (head_uses_tiles()) {
+    if (sort.variant == 2) {
         const unsigned grid = static_cast<unsigned>((slots + kHeadRows - 1) / kHeadRows);
         head_kernel<<<grid, kHeadWarps * 32, sizeof(HeadShared), stream>>>(net, act, bucket, out, sort);
+    } else if (sort.variant == 0) {
+        const unsigned grid = static_cast<unsigned>(std::min<size_t>((slots + kUmmaRows - 1) / kUmmaRows, static_cast<size_t>(sm_count)));
+        head_umma_kernel<<<grid, kUmmaThreads, sizeof(HeadUmmaShared) + 1024, stream>>>(net, act, out, sort);
     } else {
         const unsigned grid = static_cast<unsigned>(std::min<size_t>((slots + kTileRows - 1) / kTileRows, static_cast<size_t>(sm_count)));
         head_stream_kernel<<<grid, kStreamThreads, sizeof(HeadStreamShared), stream>>>(net, act, out, sort);

@@ -160,9 +160,13 @@ struct HeadSort {
     uint32_t* order;    /* [capacity]: position indices grouped by bucket, each group padded to kHeadGroupPad with kHeadNoRow */
     uint32_t* counters; /* [0..7] rows per bucket, [8..15] scatter cursors, [16..24] group starts (24 = padded total) */
     size_t capacity;    /* entries in `order`: at least n + kHeadGroupPad * 8 */
+    int variant = 0;    /* SP_NNUE_HEAD at sp_nnue_create: 0 umma (default), 1 stream, 2 tiles */
+    uint32_t direct_max = 2048; /* SP_NNUE_HEAD_DIRECT: launches of up to this many positions skip the sort (head_direct_kernel) */
 };
+int head_variant_from_env();
+uint32_t head_direct_max_from_env();
 constexpr uint32_t kHeadNoRow = 0xFFFFFFFFu;
-constexpr uint32_t kHeadGroupPad = 32; /* rows of a head tile: groups are padded to whole tiles */
+constexpr uint32_t kHeadGroupPad = 128; /* rows of a head tile (head_umma_kernel: M of the MMA): groups are padded to whole tiles */
 constexpr int kHeadSortCounters = 32;
 
 /* act[i], bucket[i] -> out[i] : L1 (int8 IMMA) + L2 (byte-limb IMMA) + L3 + scale.  bucket[i] > 7 marks

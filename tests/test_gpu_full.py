@@ -75,24 +75,35 @@ def test_ft_activations_match_oracle(gpu_ctx, c_oracle, small_playouts):
         assert (act[i] == want).all(), i
 
 
-def test_dense_head_matches_oracle_on_arbitrary_activations(gpu_ctx, c_oracle):
-    """Config 4's isolated head: full u8 range (the FT only produces 0..127), all buckets, ragged n."""
+HEAD_KERNELS = [("umma", "2048"), ("umma", "0"), ("stream", "0"), ("tiles", "0")]
+
+
+@pytest.mark.parametrize("kernel,direct", HEAD_KERNELS)
+def test_dense_head_matches_oracle_on_arbitrary_activations(net, c_oracle, monkeypatch, kernel, direct):
+    """Config 4's isolated head: full u8 range (the FT only produces 0..127), all buckets, ragged n.  Every head kernel: the
+    warp-per-position kernel small launches take by default (SP_NNUE_HEAD_DIRECT=2048), and with that switched off the sorted
+    tensor-core kernels -- head_umma_kernel (tcgen05 L1, default), head_stream_kernel and head_kernel (mma.sync L1)."""
     import torch
 
+    monkeypatch.setenv("SP_NNUE_HEAD", kernel)
+    monkeypatch.setenv("SP_NNUE_HEAD_DIRECT", direct)
     rng = np.random.default_rng(3)
-    for n in (1, 15, 16, 17, 333):
-        act = rng.integers(0, 256, (n, 1024), dtype=np.uint8)
-        act[0] = 0
-        if n > 1:
-            act[1] = 255
-        bucket = rng.integers(0, 8, n, dtype=np.uint8)
-        d_out = torch.empty(n, dtype=torch.int32, device="cuda")
-        s = _stream()
-        gpu_ctx.forward_device(_dev(act), _dev(bucket), n, d_out, s)
-        gpu_ctx.sync(s)
-        got = d_out.cpu().numpy()
-        want = np.array([c_oracle.forward(act[i], int(bucket[i])) for i in range(n)], dtype=np.int32)
-        assert (got == want).all(), n
+    with api.Nnue(net.image, 0) as ctx:
+        for n in (1, 15, 16, 17, 333, 1500):
+            act = rng.integers(0, 256, (n, 1024), dtype=np.uint8)
+            act[0] = 0
+            if n > 1:
+                act[1] = 255
+            bucket = rng.integers(0, 8, n, dtype=np.uint8)
+            if n > 100:
+                bucket[7] = 0xFF  # a board the feature transformer rejected
+            d_out = torch.empty(n, dtype=torch.int32, device="cuda")
+            s = _stream()
+            ctx.forward_device(_dev(act), _dev(bucket), n, d_out, s)
+            ctx.sync(s)
+            got = d_out.cpu().numpy()
+            want = np.array([c_oracle.forward(act[i], int(bucket[i])) if bucket[i] < 8 else INT32_MIN for i in range(n)], dtype=np.int32)
+            assert (got == want).all(), n
 
 
 def test_matches_oracle_on_seeded_playouts(gpu_ctx, c_oracle, small_playouts):
@@ -205,11 +216,14 @@ def test_adjust_eval_matches_reference_golden(gpu_ctx):
     assert (got[inside] == want[inside]).all()
 
 
-def test_dense_head_large_mixed_buckets(gpu_ctx, c_oracle):
+@pytest.mark.parametrize("kernel", ["umma", "stream"])
+def test_dense_head_large_mixed_buckets(net, c_oracle, monkeypatch, kernel):
     """Config-4 size with rows of all eight buckets interleaved at random plus rejected rows: exercises the
     bucket grouping (counting sort, group padding, CTAs that straddle two groups) and the byte-limb L2."""
     import torch
 
+    monkeypatch.setenv("SP_NNUE_HEAD", kernel)
+    gpu_ctx = api.Nnue(net.image, 0)
     rng = np.random.default_rng(11)
     n = (1 << 16) + 17
     act = rng.integers(0, 128, (n, 1024), dtype=np.uint8)
@@ -230,9 +244,11 @@ def test_dense_head_large_mixed_buckets(gpu_ctx, c_oracle):
     gpu_ctx.forward_device(_dev(act[perm]), _dev(bucket[perm]), n, d_out, s)
     gpu_ctx.sync(s)
     assert (d_out.cpu().numpy() == got[perm]).all()
+    gpu_ctx.close()
 
 
-def test_dense_head_l2_paths(net, stress_net, monkeypatch):
+@pytest.mark.parametrize("kernel,direct", [("umma", "0"), ("stream", "0"), ("umma", "2048")])
+def test_dense_head_l2_paths(net, stress_net, monkeypatch, kernel, direct):
     """The streaming head picks its L2 form per tile: int16-range weights + inputs below 2^16 (two limbs each),
     the general four-limb form without the zero input limbs, and the full form after a wrapped square.
     All three must agree with the oracle: normal net (narrow weights) with FT-range and full-range activations,
@@ -241,8 +257,10 @@ def test_dense_head_l2_paths(net, stress_net, monkeypatch):
 
     from oracle.bind import COracle
 
+    monkeypatch.setenv("SP_NNUE_HEAD", kernel)
+    monkeypatch.setenv("SP_NNUE_HEAD_DIRECT", direct)
     rng = np.random.default_rng(17)
-    n = 2500
+    n = 2000
     acts = {"ft_range": rng.integers(0, 128, (n, 1024), dtype=np.uint8), "full_range": rng.integers(0, 256, (n, 1024), dtype=np.uint8)}
     bucket = rng.integers(0, 8, n, dtype=np.uint8)
     s = _stream()

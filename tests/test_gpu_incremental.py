@@ -143,7 +143,7 @@ def test_walker_rebuild_plan_variants(net, golden, monkeypatch, env):
 
 
 @pytest.mark.parametrize("small", ["1", "copies", "0"])
-def test_search_sized_rounds_small_kernel_and_general_kernels(golden, monkeypatch, small):
+def test_search_sized_rounds_small_kernel_and_general_kernels(net, c_oracle, golden, monkeypatch, small):
     """sp_nnue_batch and the slot entry points with a few dozen items: SP_NNUE_SMALL=1 (default) takes them through ONE fused
     launch (small_batch_kernel: slot update + activation + dp4a L1 + L2 + L3 per warp), SP_NNUE_SMALL=0 through the general
     kernels.  Both must give the reference's values -- here on the STRESS network, whose int16 / int32 sums wrap everywhere."""
@@ -175,15 +175,15 @@ def test_search_sized_rounds_small_kernel_and_general_kernels(golden, monkeypatc
         assert (ctx.eval_slots(ids) == evals[first]).all()
         assert (ctx.update_eval(ids + n, ids + n, boards[first + 2]) == evals[first + 2]).all()
         flipped = ctx.eval_slots(ids[:4], stm=1 - stm_board[:4])
-        from oracle.bind import COracle
-
-        o = COracle()
-        o.load_net(N.synthetic(99, stress=True).image)
-        for k in range(4):
-            b = boards[first[k] : first[k] + 1]
-            psq, thr = o.accumulators(b)
-            bucket = (bin(int(b["occupancy"][0])).count("1") - 2) // 4
-            assert flipped[k] == o.forward_acc(psq, thr, int(1 - stm_board[k]), bucket)
+        c_oracle.load_net(N.synthetic(99, stress=True).image)  # the C oracle keeps ONE global network: put the session's back afterwards
+        try:
+            for k in range(4):
+                b = boards[first[k] : first[k] + 1]
+                psq, thr = c_oracle.accumulators(b)
+                bucket = (bin(int(b["occupancy"][0])).count("1") - 2) // 4
+                assert flipped[k] == c_oracle.forward_acc(psq, thr, int(1 - stm_board[k]), bucket)
+        finally:
+            c_oracle.load_net(net.image)
         # errors: a slot out of range, an update from a slot that was never filled
         with pytest.raises(api.NnueError) as err:
             ctx.batch(refresh=([1 << 30], boards[:1]))

@@ -25,6 +25,11 @@ def main():
     oracle = COracle()
     oracle.load_net(net.image)
     want = oracle.eval_once(boards)
+    for kernel in ("stream", "umma"):  # the sorted tensor-core heads (small launches would take the warp-per-position kernel)
+        os.environ["SP_NNUE_HEAD"], os.environ["SP_NNUE_HEAD_DIRECT"] = kernel, "0"
+        with api.Nnue(net.image, 0) as ctx:
+            assert np.array_equal(ctx.eval_full(boards), want), "full refresh, head " + kernel
+    os.environ["SP_NNUE_HEAD_DIRECT"] = "2048"
     with api.Nnue(net.image, 0) as ctx:
         assert np.array_equal(ctx.eval_full(boards), want), "full refresh"
         assert np.array_equal(ctx.eval_playouts(boards, starts), want), "playouts"
