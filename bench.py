@@ -409,6 +409,7 @@ def roofline_of(g: Gpu, workload: str, r: dict, boards, starts, steps: int, cloc
                  "workloads.head_sweep for the one kernel that streams from HBM"),
     }
     # DRAM traffic per launch from the committed ncu capture of this kernel (profiles/traffic.json)
+    entry = None
     try:
         entry = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel)
         roofline["traffic"] = entry["dram_bytes_per_position"] * n * steps / max(k_launches, 1)
@@ -424,7 +425,19 @@ def roofline_of(g: Gpu, workload: str, r: dict, boards, starts, steps: int, cloc
         }
     # what binds these cache-resident kernels is on-chip: measured L2 -> SM and shared-memory bandwidth (tools/ubench.cu)
     onchip = measured_onchip()
-    if onchip:
+    if onchip and workload == "full" and entry and entry.get("staged_bytes_per_position"):
+        # the tensor-core full refresh stages the UNION of a group's rows once (cp.async, L2 -> shared memory): bytes from the ncu capture
+        cp = onchip.get("l2_to_smem_cp_async_gbs")
+        staged = entry["staged_bytes_per_position"] * n * steps / (k_ms * 1e-3) / 1e9 if k_ms else 0.0
+        roofline["onchip"] = {"limit": "L2 -> shared memory staging (cp.async.cg 16 B), measured peak (tools/ubench.cu)", "peak": cp, "unit": "GB/s",
+                              "achieved": staged, "frac": staged / cp if cp else None,
+                              "staged_bytes_per_position": entry["staged_bytes_per_position"],
+                              "issue_active_pct": entry.get("issue_active_pct"),
+                              "warp_instructions_per_position": entry.get("warp_instructions_per_position"),
+                              "note": "neither byte stream binds: the kernel is bound by instruction issue (ncu: issue slots 69 % busy) and the "
+                                      "barriers between its phases; see profiles/r2_ft_group_ncu_v2.md and profiles/r2_ft_group_timing.md",
+                              "measured": onchip}
+    elif onchip:
         l2 = onchip.get("l2_read_gbs")
         roofline["onchip"] = {"limit": "L2 -> SM read bandwidth, measured (tools/ubench.cu)", "peak": l2, "unit": "GB/s",
                               "frac": achieved / l2 if l2 else None, "measured": onchip}
