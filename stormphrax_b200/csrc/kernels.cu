@@ -1201,23 +1201,69 @@ __device__ __forceinline__ void head_span(const uint32_t* range, uint32_t range_
     }
 }
 
+/* Sixteen consecutive bucket bytes of this lane (rows i .. i + 15 of the span; 0xFE past the end), as per-bucket counts packed in 16-bit
+ * fields: lo = buckets 0..3, hi = buckets 4..7.  One 128-bit load when the span allows it. */
+struct Buckets16 {
+    uint8_t b[16];
+};
+__device__ __forceinline__ Buckets16 load_buckets16(const uint8_t* __restrict__ p, size_t i, size_t n) {
+    Buckets16 r;
+    if (i + 16 <= n && (reinterpret_cast<uintptr_t>(p + i) & 15) == 0) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) r.b[k] = static_cast<uint8_t>(w[k >> 2] >> (8 * (k & 3)));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) r.b[k] = i + k < n ? __ldg(p + i + k) : 0xFE;
+    }
+    return r;
+}
+__device__ __forceinline__ void count_buckets16(const Buckets16& r, uint64_t& lo, uint64_t& hi) {
+    lo = hi = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t b = r.b[k];
+        if (b < 4) lo += uint64_t{1} << (16 * b);
+        else if (b < SP_OUTPUT_BUCKETS) hi += uint64_t{1} << (16 * (b - 4));
+    }
+}
+constexpr int kSortRowsPerWarp = 512; /* 16 rows per lane and iteration */
+
+/* Counting sort, pass 1: rows per bucket.  A warp counts 512 rows per iteration in registers (no atomics), a block adds its eight
+ * totals to the global counters once. */
 __global__ void head_hist_kernel(const uint8_t* __restrict__ bucket, size_t n, const uint32_t* __restrict__ range, uint32_t range_len,
                                  HeadSort sort) {
     __shared__ unsigned hist[SP_OUTPUT_BUCKETS];
     size_t first;
     head_span(range, range_len, first, n);
+    const int lane = threadIdx.x & 31;
     if (threadIdx.x < SP_OUTPUT_BUCKETS) hist[threadIdx.x] = 0;
     __syncthreads();
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int b = bucket[first + i];
-        if (b < SP_OUTPUT_BUCKETS) atomicAdd(&hist[b], 1u);
+    uint32_t mine[SP_OUTPUT_BUCKETS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t warp_global = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, n_warps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+    for (size_t base = warp_global * kSortRowsPerWarp; base < n; base += n_warps * kSortRowsPerWarp) {
+        uint64_t lo, hi;
+        count_buckets16(load_buckets16(bucket + first, base + 16 * lane, n), lo, hi);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) mine[b] += static_cast<uint32_t>(lo >> (16 * b)) & 0xFFFFu, mine[4 + b] += static_cast<uint32_t>(hi >> (16 * b)) & 0xFFFFu;
+    }
+#pragma unroll
+    for (int b = 0; b < SP_OUTPUT_BUCKETS; ++b) {
+        uint32_t v = mine[b];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+        if (lane == 0 && v) atomicAdd(&hist[b], v);
     }
     __syncthreads();
     if (threadIdx.x < SP_OUTPUT_BUCKETS && hist[threadIdx.x]) atomicAdd(&sort.counters[threadIdx.x], hist[threadIdx.x]);
 }
 
-/* Group starts (each group padded to whole tiles) from the histogram; every block derives them for itself,
- * block 0 publishes them for the head kernel and fills the padding slots. */
+/* Pass 2.  Group starts (each group padded to whole tiles) from the histogram; every block derives them for itself, block 0
+ * publishes them for the head kernel and fills the padding slots.  A warp then places 512 rows per iteration: per-lane counts ->
+ * exclusive prefix over the lanes (packed 16-bit fields, five shuffle steps) -> ONE reservation per bucket for the whole warp (the
+ * first version reserved per warp and 32 rows: 262,144 atomics on eight addresses at M = 2^20, 26 us) -> each lane writes its 16
+ * rows. */
 __global__ void head_scatter_kernel(const uint8_t* __restrict__ bucket, size_t n, const uint32_t* __restrict__ range, uint32_t range_len,
                                     HeadSort sort, int32_t* __restrict__ out) {
     __shared__ uint32_t start[SP_OUTPUT_BUCKETS + 1];
@@ -1240,19 +1286,44 @@ __global__ void head_scatter_kernel(const uint8_t* __restrict__ bucket, size_t n
     size_t first;
     head_span(range, range_len, first, n);
     const int lane = threadIdx.x & 31;
-    const size_t n_round = (n + 31) & ~size_t{31}; /* whole warps stay together for the match */
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_round; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int b = i < n ? bucket[first + i] : 0xFE;
-        const unsigned peers = __match_any_sync(kFull, b);
-        if (b < SP_OUTPUT_BUCKETS) {
-            /* one reservation per bucket per warp */
-            const int leader = __ffs(peers) - 1;
-            uint32_t slot = 0;
-            if (lane == leader) slot = atomicAdd(&sort.counters[8 + b], static_cast<uint32_t>(__popc(peers)));
-            slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1));
-            sort.order[start[b] + slot] = static_cast<uint32_t>(first + i);
-        } else if (i < n) {
-            out[first + i] = INT32_MIN; /* rejected board */
+    const size_t warp_global = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, n_warps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+    for (size_t base = warp_global * kSortRowsPerWarp; base < n; base += n_warps * kSortRowsPerWarp) {
+        const size_t i0 = base + 16 * lane;
+        const Buckets16 rows = load_buckets16(bucket + first, i0, n);
+        uint64_t lo, hi;
+        count_buckets16(rows, lo, hi);
+        /* inclusive prefix over the lanes; a field holds at most 512 */
+        uint64_t plo = lo, phi = hi;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t qlo = __shfl_up_sync(kFull, plo, d), qhi = __shfl_up_sync(kFull, phi, d);
+            if (lane >= d) plo += qlo, phi += qhi;
+        }
+        const uint64_t tlo = __shfl_sync(kFull, plo, 31), thi = __shfl_sync(kFull, phi, 31); /* the warp's totals */
+        /* lane b reserves the warp's rows of bucket b */
+        uint32_t reserved = 0;
+        if (lane < SP_OUTPUT_BUCKETS) {
+            const uint32_t total = static_cast<uint32_t>((lane < 4 ? tlo : thi) >> (16 * (lane & 3))) & 0xFFFFu;
+            if (total) reserved = atomicAdd(&sort.counters[8 + lane], total);
+        }
+        uint32_t at[SP_OUTPUT_BUCKETS]; /* where this lane's next row of bucket b goes */
+#pragma unroll
+        for (int b = 0; b < SP_OUTPUT_BUCKETS; ++b) {
+            const uint32_t before = (static_cast<uint32_t>(((b < 4 ? plo : phi) - (b < 4 ? lo : hi)) >> (16 * (b & 3)))) & 0xFFFFu;
+            at[b] = start[b] + __shfl_sync(kFull, reserved, b) + before;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t b = rows.b[k];
+            if (b < SP_OUTPUT_BUCKETS) {
+                uint32_t slot = 0;
+#pragma unroll
+                for (int j = 0; j < SP_OUTPUT_BUCKETS; ++j)
+                    if (b == static_cast<uint32_t>(j)) slot = at[j]++;
+                sort.order[slot] = static_cast<uint32_t>(first + i0 + k);
+            } else if (i0 + k < n) {
+                out[first + i0 + k] = INT32_MIN; /* rejected board */
+            }
         }
     }
 }
@@ -2133,7 +2204,7 @@ cudaError_t launch_head(
         head_sort_small_kernel<<<1, 1024, 0, stream>>>(bucket, n, range, range_len, sort, out);
     } else {
         cudaMemsetAsync(sort.counters, 0, kHeadSortCounters * sizeof(uint32_t), stream);
-        const unsigned sort_grid = static_cast<unsigned>(std::min<size_t>((n + 1023) / 1024, static_cast<size_t>(sm_count) * 4));
+        const unsigned sort_grid = static_cast<unsigned>(std::min<size_t>((n + 4095) / 4096, static_cast<size_t>(sm_count) * 4)); /* 8 warps x 512 rows */
         head_hist_kernel<<<sort_grid, 256, 0, stream>>>(bucket, n, range, range_len, sort);
         head_scatter_kernel<<<sort_grid, 256, 0, stream>>>(bucket, n, range, range_len, sort, out);
     }

@@ -26,12 +26,10 @@ VARIANTS = {
     # tcgen05 head: which side bounds it?  (results are wrong by construction: timing only)
     "umma_notail": {"SP_HEAD_UMMA_NOTAIL": 1},
     "umma_nogather": {"SP_HEAD_UMMA_NOGATHER": 1},
-    "umma_stages11": {"SP_HEAD_UMMA_STAGES": 11},
     "umma_k1": {"SP_HEAD_UMMA_KATOMS": 1},
-    "umma_k4": {"SP_HEAD_UMMA_KATOMS": 4, "SP_HEAD_UMMA_STAGES": 2, "SP_HEAD_UMMA_PENDING": 1},
-    "umma_notail_k4": {"SP_HEAD_UMMA_NOTAIL": 1, "SP_HEAD_UMMA_KATOMS": 4, "SP_HEAD_UMMA_STAGES": 2, "SP_HEAD_UMMA_PENDING": 1},
-    "umma_notail_k2p4": {"SP_HEAD_UMMA_NOTAIL": 1, "SP_HEAD_UMMA_PENDING": 4},
-    "umma_notail_k1": {"SP_HEAD_UMMA_NOTAIL": 1, "SP_HEAD_UMMA_KATOMS": 1},
+    "umma_loaders3": {"SP_HEAD_UMMA_LOADERS": 3},
+    "umma_loaders5": {"SP_HEAD_UMMA_LOADERS": 5},
+    "umma_notail_loaders3": {"SP_HEAD_UMMA_NOTAIL": 1, "SP_HEAD_UMMA_LOADERS": 3},
 }
 
 
