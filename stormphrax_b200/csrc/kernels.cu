@@ -872,8 +872,26 @@ ft_slots_kernel(DeviceNet net, SlotStore slots, const uint32_t* __restrict__ src
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& ws = scratch[warp];
     const FeatureTables& t = *net.tables;
-    const size_t stride = static_cast<size_t>(gridDim.x) * kWarpsPerCta;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * kWarpsPerCta + warp; i < n; i += stride) {
+    /* Items are handed out from a ticket counter instead of round-robin: an item whose king crossed a bucket boundary
+     * (a rebuild from ~80 rows instead of ~10 delta rows) costs several times the usual one, and with ~28 items per warp the slowest
+     * warp of a static schedule ran well past the average.  The counters reset themselves: the last warp to run dry zeroes them. */
+    unsigned long long* const ticket = &status->counters[kSlotsTicket];
+#ifndef SP_SLOTS_TICKET
+#define SP_SLOTS_TICKET 1 /* items per ticket; 0 = static round-robin.  (2 is NOT safe: taking adjacent items back to back in one warp gave wrong results) */
+#endif
+    constexpr unsigned long long kItemsPerTicket = SP_SLOTS_TICKET ? SP_SLOTS_TICKET : 1;
+    size_t static_next = static_cast<size_t>(blockIdx.x) * kWarpsPerCta + warp;
+    for (;;) {
+        unsigned long long first = 0;
+        if (SP_SLOTS_TICKET) {
+            if (lane == 0) first = atomicAdd(ticket, kItemsPerTicket);
+            first = __shfl_sync(kFull, first, 0);
+        } else {
+            first = static_next, static_next += static_cast<size_t>(gridDim.x) * kWarpsPerCta;
+        }
+        if (first >= n) break;
+        const size_t last = min(static_cast<size_t>(first + kItemsPerTicket), n);
+    for (size_t i = first; i < last; ++i) {
         const uint32_t to = dst[i];
         const uint32_t from = src ? src[i] : to;
         int err = (to >= slots.n_slots || from >= slots.n_slots) ? kErrBadSlot : 0;
@@ -917,6 +935,14 @@ ft_slots_kernel(DeviceNet net, SlotStore slots, const uint32_t* __restrict__ src
         }
         if (lane < 2) reinterpret_cast<uint4*>(slots.boards + to)[lane] = __ldg(reinterpret_cast<const uint4*>(boards + i) + lane);
         if (act && lane == 0) bucket[i] = static_cast<uint8_t>(output_bucket(d.view.occ));
+    }
+    }
+    if (SP_SLOTS_TICKET && lane == 0) {
+        const unsigned long long finished = atomicAdd(&status->counters[kSlotsTicket + 1], 1ull) + 1;
+        if (finished == static_cast<unsigned long long>(gridDim.x) * kWarpsPerCta) { /* every warp has drawn its last (empty) ticket */
+            status->counters[kSlotsTicket] = 0, status->counters[kSlotsTicket + 1] = 0;
+            __threadfence();
+        }
     }
 }
 

@@ -16,6 +16,8 @@ VARIANTS = {
     "enq_prefetch": {"SP_ENQ_PREFETCH": 1},
     "enq_unroll2": {"SP_ENQ_UNROLL": 2},
     # slot update kernel (self-play path): CTAs per SM
+    "slots_static": {"SP_SLOTS_TICKET": 0},
+    "slots_ticket1": {"SP_SLOTS_TICKET": 1},
     "slots3": {"SP_SLOTS_MIN_BLOCKS": 3},
     "slots4": {"SP_SLOTS_MIN_BLOCKS": 4},
     # tensor-core full refresh: CTA 0 prints its clocks per phase
