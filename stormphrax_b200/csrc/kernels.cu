@@ -892,6 +892,7 @@ ft_slots_kernel(DeviceNet net, SlotStore slots, const uint32_t* __restrict__ src
         if (first >= n) break;
         const size_t last = min(static_cast<size_t>(first + kItemsPerTicket), n);
     for (size_t i = first; i < last; ++i) {
+        __syncwarp(); /* the previous item's readers of the warp's scratch are done */
         const uint32_t to = dst[i];
         const uint32_t from = src ? src[i] : to;
         int err = (to >= slots.n_slots || from >= slots.n_slots) ? kErrBadSlot : 0;

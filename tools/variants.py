@@ -18,7 +18,6 @@ VARIANTS = {
     # slot update kernel (self-play path): CTAs per SM
     "slots_static": {"SP_SLOTS_TICKET": 0},
     "slots_ticket1": {"SP_SLOTS_TICKET": 1},
-    "slots_ticket2": {"SP_SLOTS_TICKET": 2},
     "slots3": {"SP_SLOTS_MIN_BLOCKS": 3},
     "slots4": {"SP_SLOTS_MIN_BLOCKS": 4},
     # tensor-core full refresh: CTA 0 prints its clocks per phase
