@@ -512,8 +512,23 @@ def extra_head_sweep(g: Gpu, boards):
             times.append(e0.elapsed_time(e1))
         us = float(np.median(times)) * 1e3
         pos_s = m / (us * 1e-6)
-        rows.append({"M": m, "us": us, "Mpos_s": pos_s / 1e6, "int8_TOPs": pos_s * 131072 / 1e12, "GBps": pos_s * 1029 / 1e9, "hbm_frac": pos_s * 1029 / 1e9 / peak})
-    return {"config": "dense head alone: u8[M][1024] activations + bucket -> i32 (BASELINE configs[3]); sort + head kernels, L2 flushed before each call",
+        row = {"M": m, "us": us, "Mpos_s": pos_s / 1e6, "int8_TOPs": pos_s * 131072 / 1e12, "GBps": pos_s * 1029 / 1e9, "hbm_frac": pos_s * 1029 / 1e9 / peak}
+        # the head kernel proper (without the counting sort in front of it): CUDA events recorded by the library around that launch
+        ctx.profile(True)
+        ctx.profile_read()
+        for _ in range(3):
+            g.flush.fill_(0)
+            ctx.forward_device(d_act, d_bucket, m, d_out, s)
+        ctx.sync(s)
+        k_ms, k_launches = ctx.profile_read().get("head_main", (0.0, 0))
+        ctx.profile(False)
+        if k_launches:
+            k_us = k_ms / k_launches * 1e3
+            row["kernel_us"] = k_us
+            row["kernel_hbm_frac"] = m * 1029 / (k_us * 1e-6) / 1e9 / peak
+        rows.append(row)
+    return {"config": "dense head alone: u8[M][1024] activations + bucket -> i32 (BASELINE configs[3]); `us` = the whole sp_nnue_forward_device call (counting sort + "
+                      "head kernel), `kernel_us` = the head kernel alone (head_umma_kernel above 2,048 positions, head_direct_kernel up to there); L2 flushed before each call",
             "bytes_per_position": 1029, "hbm_peak_gbs": peak, "per_gpu": rows}
 
 

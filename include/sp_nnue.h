@@ -208,7 +208,8 @@ enum {
     SP_KERNEL_EXTRACT = 4,  /* boards -> row lists (split full refresh) */
     SP_KERNEL_ACCUMULATE = 5, /* row lists -> activations (split full refresh) */
     SP_KERNEL_REBUILDS = 6, /* playout walker: planning + computing the rebuilt accumulators ahead of the walk */
-    SP_NUM_KERNEL_CLASSES = 7
+    SP_KERNEL_HEAD_MAIN = 7, /* sp_nnue_forward_device only: the head kernel proper, without the counting sort in front of it (SP_KERNEL_HEAD spans both) */
+    SP_NUM_KERNEL_CLASSES = 8
 };
 int sp_nnue_profile(SpNnue* ctx, int enable);
 int sp_nnue_profile_read(SpNnue* ctx, double ms[SP_NUM_KERNEL_CLASSES], uint64_t launches[SP_NUM_KERNEL_CLASSES]);

@@ -30,7 +30,7 @@ SP_OK, SP_ERR_INVALID, SP_ERR_BAD_NETWORK, SP_ERR_CUDA, SP_ERR_NO_DEVICE, SP_ERR
 STATUS_NAMES = ["SP_OK", "SP_ERR_INVALID", "SP_ERR_BAD_NETWORK", "SP_ERR_CUDA", "SP_ERR_NO_DEVICE", "SP_ERR_BAD_BOARD", "SP_ERR_CAPACITY"]
 NUM_COUNTERS = 8
 CTR_EVALS, CTR_FULL_REFRESH, CTR_INCREMENTAL, CTR_LAUNCHES = 0, 1, 2, 3
-KERNEL_CLASSES = ["ft_full", "head", "ft_slots", "ft_games", "extract", "accumulate", "rebuilds"]
+KERNEL_CLASSES = ["ft_full", "head", "ft_slots", "ft_games", "extract", "accumulate", "rebuilds", "head_main"]
 NUM_KERNEL_CLASSES = len(KERNEL_CLASSES)
 
 _vp = C.c_void_p

@@ -667,7 +667,18 @@ int sp_nnue_forward_device(SpNnue* ctx, const uint8_t* d_act, const uint8_t* d_b
     if (reinterpret_cast<uintptr_t>(d_act) & 15) return fail(ctx, SP_ERR_INVALID, "d_act must be 16-byte aligned");
     DeviceGuard guard{ctx->device};
     if (const int rc = ensure_head_sort(ctx, n)) return rc;
-    SP_CUDA(ctx, launch_head(ctx->net, d_act, d_bucket, n, d_out, nullptr, ctx->head_sort, ctx->sm_count, pick(ctx, stream)));
+    {
+        cudaStream_t st = pick(ctx, stream);
+        Timed timed{ctx, st, SP_KERNEL_HEAD};
+        HeadSort sort = ctx->head_sort;
+        SpNnue::Span main{};
+        if (ctx->profiling) { /* the head kernel proper, without the counting sort: what the roofline of this kernel is measured on */
+            main = {take_event(ctx), take_event(ctx), SP_KERNEL_HEAD_MAIN};
+            sort.ev_main_begin = main.a, sort.ev_main_end = main.b;
+        }
+        SP_CUDA(ctx, launch_head(ctx->net, d_act, d_bucket, n, d_out, nullptr, sort, ctx->sm_count, st));
+        if (ctx->profiling) ctx->spans.push_back(main);
+    }
     ctx->counters[SP_CTR_LAUNCHES] += 3;
     ctx->counters[SP_CTR_EVALS] += n;
     SP_CUDA(ctx, cudaGetLastError());

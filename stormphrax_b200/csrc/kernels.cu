@@ -2223,7 +2223,9 @@ cudaError_t launch_head(
     int sm_count, cudaStream_t stream, uint32_t range_len) {
     if (!n) return cudaSuccess;
     if (n <= sort.direct_max) {
+        if (sort.ev_main_begin) cudaEventRecord(sort.ev_main_begin, stream);
         head_direct_kernel<<<grid_for(n, kWarpsPerCta, sm_count, 2), kThreads, 0, stream>>>(net, act, bucket, n, range, range_len, out);
+        if (sort.ev_main_end) cudaEventRecord(sort.ev_main_end, stream);
         return cudaPeekAtLastError();
     }
     const size_t slots = std::min(sort.capacity, n + kHeadGroupPad * SP_OUTPUT_BUCKETS); /* n bounds the rows of this launch */
@@ -2247,6 +2249,7 @@ cudaError_t launch_head(
         if (e != cudaSuccess) return e;
         configured.fetch_or(uint64_t{1} << (device & 63), std::memory_order_relaxed);
     }
+    if (sort.ev_main_begin) cudaEventRecord(sort.ev_main_begin, stream);
     if (sort.variant == 2) {
         const unsigned grid = static_cast<unsigned>((slots + kHeadRows - 1) / kHeadRows);
         head_kernel<<<grid, kHeadWarps * 32, sizeof(HeadShared), stream>>>(net, act, bucket, out, sort);
@@ -2257,6 +2260,7 @@ cudaError_t launch_head(
         const unsigned grid = static_cast<unsigned>(std::min<size_t>((slots + kTileRows - 1) / kTileRows, static_cast<size_t>(sm_count)));
         head_stream_kernel<<<grid, kStreamThreads, sizeof(HeadStreamShared), stream>>>(net, act, out, sort);
     }
+    if (sort.ev_main_end) cudaEventRecord(sort.ev_main_end, stream);
     return cudaPeekAtLastError();
 }
 

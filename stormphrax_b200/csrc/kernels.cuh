@@ -163,6 +163,7 @@ struct HeadSort {
     size_t capacity;    /* entries in `order`: at least n + kHeadGroupPad * 8 */
     int variant = 0;    /* SP_NNUE_HEAD at sp_nnue_create: 0 umma (default), 1 stream, 2 tiles */
     uint32_t direct_max = 2048; /* SP_NNUE_HEAD_DIRECT: launches of up to this many positions skip the sort (head_direct_kernel) */
+    cudaEvent_t ev_main_begin = nullptr, ev_main_end = nullptr; /* when set: recorded around the head kernel proper (profiling) */
 };
 int head_variant_from_env();
 uint32_t head_direct_max_from_env();
