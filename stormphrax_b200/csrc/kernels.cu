@@ -1233,16 +1233,18 @@ __device__ __forceinline__ void head_span(const uint32_t* range, uint32_t range_
 struct Buckets16 {
     uint8_t b[16];
 };
-__device__ __forceinline__ Buckets16 load_buckets16(const uint8_t* __restrict__ p, size_t i, size_t n) {
+/* `p` is 16-byte aligned; the span's rows are bytes [lead, n) of it (lead < 16: a span may start anywhere, e.g. at a game boundary of
+ * a playout stream, and is then read from the aligned address below it) */
+__device__ __forceinline__ Buckets16 load_buckets16(const uint8_t* __restrict__ p, size_t i, size_t lead, size_t n) {
     Buckets16 r;
-    if (i + 16 <= n && (reinterpret_cast<uintptr_t>(p + i) & 15) == 0) {
+    if (i >= lead && i + 16 <= n) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i));
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 16; ++k) r.b[k] = static_cast<uint8_t>(w[k >> 2] >> (8 * (k & 3)));
     } else {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) r.b[k] = i + k < n ? __ldg(p + i + k) : 0xFE;
+        for (int k = 0; k < 16; ++k) r.b[k] = (i + k >= lead && i + k < n) ? __ldg(p + i + k) : 0xFE;
     }
     return r;
 }
@@ -1269,9 +1271,11 @@ __global__ void head_hist_kernel(const uint8_t* __restrict__ bucket, size_t n, c
     __syncthreads();
     uint32_t mine[SP_OUTPUT_BUCKETS] = {0, 0, 0, 0, 0, 0, 0, 0};
     const size_t warp_global = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, n_warps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
-    for (size_t base = warp_global * kSortRowsPerWarp; base < n; base += n_warps * kSortRowsPerWarp) {
+    const size_t lead = reinterpret_cast<uintptr_t>(bucket + first) & 15, end = lead + n; /* byte range of the span below its aligned base */
+    const uint8_t* const aligned = bucket + first - lead;
+    for (size_t base = warp_global * kSortRowsPerWarp; base < end; base += n_warps * kSortRowsPerWarp) {
         uint64_t lo, hi;
-        count_buckets16(load_buckets16(bucket + first, base + 16 * lane, n), lo, hi);
+        count_buckets16(load_buckets16(aligned, base + 16 * lane, lead, end), lo, hi);
 #pragma unroll
         for (int b = 0; b < 4; ++b) mine[b] += static_cast<uint32_t>(lo >> (16 * b)) & 0xFFFFu, mine[4 + b] += static_cast<uint32_t>(hi >> (16 * b)) & 0xFFFFu;
     }
@@ -1314,9 +1318,11 @@ __global__ void head_scatter_kernel(const uint8_t* __restrict__ bucket, size_t n
     head_span(range, range_len, first, n);
     const int lane = threadIdx.x & 31;
     const size_t warp_global = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, n_warps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
-    for (size_t base = warp_global * kSortRowsPerWarp; base < n; base += n_warps * kSortRowsPerWarp) {
+    const size_t lead = reinterpret_cast<uintptr_t>(bucket + first) & 15, end = lead + n;
+    const uint8_t* const aligned = bucket + first - lead;
+    for (size_t base = warp_global * kSortRowsPerWarp; base < end; base += n_warps * kSortRowsPerWarp) {
         const size_t i0 = base + 16 * lane;
-        const Buckets16 rows = load_buckets16(bucket + first, i0, n);
+        const Buckets16 rows = load_buckets16(aligned, i0, lead, end);
         uint64_t lo, hi;
         count_buckets16(rows, lo, hi);
         /* inclusive prefix over the lanes; a field holds at most 512 */
@@ -1347,9 +1353,9 @@ __global__ void head_scatter_kernel(const uint8_t* __restrict__ bucket, size_t n
 #pragma unroll
                 for (int j = 0; j < SP_OUTPUT_BUCKETS; ++j)
                     if (b == static_cast<uint32_t>(j)) slot = at[j]++;
-                sort.order[slot] = static_cast<uint32_t>(first + i0 + k);
-            } else if (i0 + k < n) {
-                out[first + i0 + k] = INT32_MIN; /* rejected board */
+                sort.order[slot] = static_cast<uint32_t>(first + i0 + k - lead);
+            } else if (i0 + k >= lead && i0 + k < end) {
+                out[first + i0 + k - lead] = INT32_MIN; /* rejected board */
             }
         }
     }

@@ -244,6 +244,12 @@ def test_dense_head_large_mixed_buckets(net, c_oracle, monkeypatch, kernel):
     gpu_ctx.forward_device(_dev(act[perm]), _dev(bucket[perm]), n, d_out, s)
     gpu_ctx.sync(s)
     assert (d_out.cpu().numpy() == got[perm]).all()
+    # a bucket array that starts at an odd address (the counting sort reads it 16 bytes at a time from the aligned address below)
+    shifted = _dev(np.concatenate([np.full(5, 0xEE, dtype=np.uint8), bucket]))[5:]
+    d_out.zero_()
+    gpu_ctx.forward_device(_dev(act), shifted, n, d_out, s)
+    gpu_ctx.sync(s)
+    assert (d_out.cpu().numpy() == got).all()
     gpu_ctx.close()
 
 
