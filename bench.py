@@ -435,7 +435,7 @@ def roofline_of(g: Gpu, workload: str, r: dict, boards, starts, steps: int, cloc
                               "issue_active_pct": entry.get("issue_active_pct"),
                               "warp_instructions_per_position": entry.get("warp_instructions_per_position"),
                               "note": "neither byte stream binds: the kernel is bound by instruction issue (ncu: issue slots 69 % busy) and the "
-                                      "barriers between its phases; see profiles/r2_ft_group_ncu_v2.md and profiles/r2_ft_group_timing.md",
+                                      "barriers between its phases; see profiles/r2_ft_group_ncu_v3.md and profiles/r2_ft_group_timing.md",
                               "measured": onchip}
     elif onchip:
         l2 = onchip.get("l2_read_gbs")
