@@ -376,7 +376,7 @@ int eval_full_device(
         {
             Timed timed{ctx, hs, SP_KERNEL_HEAD};
             SP_CUDA(ctx, launch_head(ctx->net, ctx->d_act2[buf], ctx->d_bucket2[buf], m, d_out + off, nullptr, ctx->head_sort, ctx->sm_count, hs));
-            ctx->counters[SP_CTR_LAUNCHES] += 3;
+            ctx->counters[SP_CTR_LAUNCHES] += head_kernel_launches(m, ctx->head_sort);
         }
         if (overlap) SP_CUDA(ctx, cudaEventRecord(ctx->ev_head[buf], ctx->aux));
         if (io) { /* results of this chunk go home while the next chunk computes */
@@ -679,7 +679,7 @@ int sp_nnue_forward_device(SpNnue* ctx, const uint8_t* d_act, const uint8_t* d_b
         SP_CUDA(ctx, launch_head(ctx->net, d_act, d_bucket, n, d_out, nullptr, sort, ctx->sm_count, st));
         if (ctx->profiling) ctx->spans.push_back(main);
     }
-    ctx->counters[SP_CTR_LAUNCHES] += 3;
+    ctx->counters[SP_CTR_LAUNCHES] += head_kernel_launches(n, ctx->head_sort);
     ctx->counters[SP_CTR_EVALS] += n;
     SP_CUDA(ctx, cudaGetLastError());
     return SP_OK;

@@ -2224,6 +2224,8 @@ uint32_t head_direct_max_from_env() {
     return v ? static_cast<uint32_t>(std::strtoul(v, nullptr, 10)) : 2048u;
 }
 
+int head_kernel_launches(size_t n, const HeadSort& sort) { return n <= sort.direct_max ? 1 : (n <= kHeadSortSmall ? 2 : 3); }
+
 cudaError_t launch_head(
     const DeviceNet& net, const uint8_t* act, const uint8_t* bucket, size_t n, int32_t* out, const uint32_t* range, HeadSort sort,
     int sm_count, cudaStream_t stream, uint32_t range_len) {

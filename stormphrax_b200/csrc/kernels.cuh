@@ -165,6 +165,8 @@ struct HeadSort {
     uint32_t direct_max = 2048; /* SP_NNUE_HEAD_DIRECT: launches of up to this many positions skip the sort (head_direct_kernel) */
     cudaEvent_t ev_main_begin = nullptr, ev_main_end = nullptr; /* when set: recorded around the head kernel proper (profiling) */
 };
+/* kernels launch_head starts for n positions: 1 (head_direct_kernel), 2 (single-block sort + head) or 3 (histogram, scatter, head) */
+int head_kernel_launches(size_t n, const HeadSort& sort);
 int head_variant_from_env();
 uint32_t head_direct_max_from_env();
 constexpr uint32_t kHeadNoRow = 0xFFFFFFFFu;
