@@ -62,7 +62,7 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #define SP_ACC_MIN_BLOCKS 3
 #endif
 #ifndef SP_SLOTS_MIN_BLOCKS
-#define SP_SLOTS_MIN_BLOCKS 2 /* slot update kernel: CTAs per SM it is compiled for (38 % of a self-play round: to be swept) */
+#define SP_SLOTS_MIN_BLOCKS 3 /* CTAs per SM of ft_slots_kernel: 3 (80 registers) measured +6.5 % over 2 once items came from the ticket counter (before that: +-2 %); 4 (64 registers) no better than 2 */
 #endif
 #ifndef SP_GAMES_MIN_BLOCKS
 #define SP_GAMES_MIN_BLOCKS 2
