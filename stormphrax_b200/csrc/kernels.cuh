@@ -56,9 +56,9 @@ enum : int {
 struct DeviceStatus {
     int error; /* OR of kErr* bits */
     int pad;
-    unsigned long long counters[8]; /* zero between launches; [kSlotsTicket], [kSlotsTicket + 1]: work queue of ft_slots_kernel */
+    unsigned long long counters[8]; /* zero between launches: the work queues of ft_slots_kernel ([kSlotsTicket], + 1) and ft_group_kernel ([kGroupTicket], + 1) */
 };
-constexpr int kSlotsTicket = 2;
+constexpr int kSlotsTicket = 2, kGroupTicket = 4; /* each + 1: warps / CTAs that have run dry */
 
 /* Logical element index held at (chunk k, lane l, int16 slot e) of a device PSQ row / stored
  * accumulator.  Lane l owns logical elements [16 l, 16 l + 16) ("A half") and
