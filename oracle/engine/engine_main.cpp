@@ -10,17 +10,23 @@
  *                                                   playouts: staticEvalOnce == staticEval(nnueState) after
  *                                                   applyMove<BoardObserver> + applyImmediately; prints an eval checksum
  *   <binary> <network.nnue> datagen <dir> <seconds>  the engine's own datagen::run (one thread), interrupted after <seconds>
- *   <binary> <network.nnue> searches <n> <depth> <fibers 0|1>
+ *   <binary> <network.nnue> searches <n> <depth> <fibers 0|1> [threads [width]]
  *                                                   n independent fixed-depth searches (own Searcher each, roots = random playouts):
  *                                                   one after the other, or (sp_engine_b200, fibers = 1) as fibers of one thread whose
  *                                                   evaluations are answered in device batches; prints the node count of each search
- *   <binary> <network.nnue> games <n> <nodes> <plies> <seed> <fibers 0|1>
+ *   <binary> <network.nnue> games <n> <nodes> <plies> <seed> <fibers 0|1> [threads [width]]
  *                                                   BASELINE configs[4] in miniature: n concurrent self-play games, datagen's per-move
  *                                                   search (runDatagenSearch, soft node limit <nodes>), <plies> moves each; prints
  *                                                   nodes, nodes/s, a checksum of (move, score) and the batch statistics
+ *                                                   [threads] (with fibers = 1): that many host threads share the searches / games, each
+ *                                                   a fiber scheduler with its own evaluator context on the GPU (sp_engine_cpu: plain
+ *                                                   host threads over its CPU evaluation) -- datagen's "N threads" (datagen.cpp:378-384);
+ *                                                   [width]: searches / games alive per scheduler, the rest wait in a queue shared by
+ *                                                   all schedulers (0 = all at once)
  *
  * Bit-exact evaluations make both binaries walk the same search trees: their bench node counts must be identical.
  */
+#include <atomic>
 #include <chrono>
 #include <csignal>
 #include <cstdlib>
@@ -57,9 +63,20 @@ namespace stormphrax::eval {
             u64 rounds{};
             u64 evaluations{};
         };
-        inline Stats runFibers(std::vector<std::function<void()>>& jobs, usize = 0) {
-            for (auto& job : jobs) {
-                job();
+        inline Stats runFibers(std::vector<std::function<void()>>& jobs, usize = 0, u32 threads = 1, usize = 0) {
+            std::atomic<usize> nextJob{0};
+            const auto work = [&jobs, &nextJob] {
+                for (auto job = nextJob.fetch_add(1); job < jobs.size(); job = nextJob.fetch_add(1)) {
+                    jobs[job]();
+                }
+            };
+            std::vector<std::thread> workers;
+            for (u32 t = 1; t < threads; ++t) {
+                workers.emplace_back(work);
+            }
+            work();
+            for (auto& worker : workers) {
+                worker.join();
             }
             return {};
         }
@@ -128,7 +145,7 @@ namespace {
         return pos;
     }
 
-    int searches(u32 n, i32 depth, bool fibers) {
+    int searches(u32 n, i32 depth, bool fibers, u32 threads, usize width) {
         opts::mutableOpts().chess960 = false;
         util::rng::SeedGenerator seeds{1234};
         std::vector<std::unique_ptr<search::Searcher>> searchers(n);
@@ -152,7 +169,7 @@ namespace {
         const auto start = util::Instant::now();
         eval::batch::Stats stats{};
         if (fibers) {
-            stats = eval::batch::runFibers(jobs);
+            stats = eval::batch::runFibers(jobs, usize{4} << 20, threads, width);
         } else {
             for (auto& job : jobs) {
                 job();
@@ -167,9 +184,11 @@ namespace {
         }
         println();
         println(
-            "searches: {} searches depth {} {} nodes {:.3f} seconds {} nps rounds {} evaluations {}",
+            "searches: {} searches depth {} threads {} width {} {} nodes {:.3f} seconds {} nps rounds {} evaluations {}",
             n,
             depth,
+            threads,
+            width,
             total,
             seconds,
             static_cast<usize>(static_cast<f64>(total) / seconds),
@@ -179,7 +198,7 @@ namespace {
         return 0;
     }
 
-    int games(u32 n, usize softNodes, u32 plies, u64 seed, bool fibers) {
+    int games(u32 n, usize softNodes, u32 plies, u64 seed, bool fibers, u32 threads, usize width) {
         opts::mutableOpts().chess960 = false;
         util::rng::SeedGenerator seeds{seed};
         std::vector<std::unique_ptr<search::Searcher>> searchers(n);
@@ -223,7 +242,7 @@ namespace {
         const auto start = util::Instant::now();
         eval::batch::Stats stats{};
         if (fibers) {
-            stats = eval::batch::runFibers(jobs);
+            stats = eval::batch::runFibers(jobs, usize{4} << 20, threads, width);
         } else {
             for (auto& job : jobs) {
                 job();
@@ -237,10 +256,12 @@ namespace {
             checksum = checksum * 0x9E3779B97F4A7C15ull + sums[i];
         }
         println(
-            "games: {} games {} plies soft {} nodes: {} nodes {:.3f} seconds {} nps checksum {:016x} rounds {} evaluations {}",
+            "games: {} games {} plies soft {} threads {} width {} nodes: {} nodes {:.3f} seconds {} nps checksum {:016x} rounds {} evaluations {}",
             n,
             plies,
             softNodes,
+            threads,
+            width,
             total,
             seconds,
             static_cast<usize>(static_cast<f64>(total) / seconds),
@@ -288,14 +309,22 @@ int main(int argc, char** argv) {
     } else if (cmd == "evalcheck") {
         rc = evalCheck(argc > 3 ? static_cast<u32>(std::atoi(argv[3])) : 4, argc > 4 ? std::strtoull(argv[4], nullptr, 10) : 42);
     } else if (cmd == "searches" && argc > 5) {
-        rc = searches(static_cast<u32>(std::atoi(argv[3])), std::atoi(argv[4]), std::atoi(argv[5]) != 0);
+        rc = searches(
+            static_cast<u32>(std::atoi(argv[3])),
+            std::atoi(argv[4]),
+            std::atoi(argv[5]) != 0,
+            argc > 6 ? static_cast<u32>(std::max(1, std::atoi(argv[6]))) : 1,
+            argc > 7 ? static_cast<usize>(std::max(0, std::atoi(argv[7]))) : 0
+        );
     } else if (cmd == "games" && argc > 7) {
         rc = games(
             static_cast<u32>(std::atoi(argv[3])),
             static_cast<usize>(std::atol(argv[4])),
             static_cast<u32>(std::atoi(argv[5])),
             std::strtoull(argv[6], nullptr, 10),
-            std::atoi(argv[7]) != 0
+            std::atoi(argv[7]) != 0,
+            argc > 8 ? static_cast<u32>(std::max(1, std::atoi(argv[8]))) : 1,
+            argc > 9 ? static_cast<usize>(std::max(0, std::atoi(argv[9]))) : 0
         );
     } else if (cmd == "datagen" && argc > 4) {
         const int seconds = std::atoi(argv[4]);

@@ -9,7 +9,12 @@ namespace sp::host::eval {
 
 namespace {
 SpNnue* g_network = nullptr;
-std::string g_error;
+thread_local std::string g_error; /* schedulers on several host threads report through here */
+/* the image and device of init(), kept for createContext(); the extra contexts, so that shutdown() leaves none behind */
+std::vector<uint8_t> g_image;
+int g_device = 0;
+std::vector<SpNnue*> g_extra;
+std::mutex g_extraMutex;
 
 bool report(const char* what, SpNnue* ctx, int rc) {
     if (rc == SP_OK) return true;
@@ -24,7 +29,32 @@ bool init(const void* networkImage, size_t len, int device) {
     SpNnue* ctx = nullptr;
     if (!report("eval::init", nullptr, sp_nnue_create(networkImage, len, device, &ctx))) return false;
     g_network = ctx;
+    g_image.assign(static_cast<const uint8_t*>(networkImage), static_cast<const uint8_t*>(networkImage) + len);
+    g_device = device;
     return true;
+}
+
+SpNnue* createContext() {
+    if (!g_network) {
+        g_error = "eval::createContext: no network loaded";
+        return nullptr;
+    }
+    SpNnue* ctx = nullptr;
+    std::lock_guard<std::mutex> lock{g_extraMutex};
+    if (!report("eval::createContext", nullptr, sp_nnue_create(g_image.data(), g_image.size(), g_device, &ctx))) return nullptr;
+    g_extra.push_back(ctx);
+    return ctx;
+}
+
+void destroyContext(SpNnue* ctx) {
+    if (!ctx || ctx == g_network) return;
+    std::lock_guard<std::mutex> lock{g_extraMutex};
+    for (size_t i = 0; i < g_extra.size(); ++i) {
+        if (g_extra[i] != ctx) continue;
+        g_extra.erase(g_extra.begin() + static_cast<std::ptrdiff_t>(i));
+        sp_nnue_destroy(ctx);
+        return;
+    }
 }
 
 bool initFromFile(const std::string& path, int device) {
@@ -39,8 +69,15 @@ bool initFromFile(const std::string& path, int device) {
 }
 
 void shutdown() {
+    {
+        std::lock_guard<std::mutex> lock{g_extraMutex};
+        for (SpNnue* ctx : g_extra) sp_nnue_destroy(ctx);
+        g_extra.clear();
+    }
     sp_nnue_destroy(g_network);
     g_network = nullptr;
+    g_image.clear();
+    g_image.shrink_to_fit();
 }
 
 bool isNetworkLoaded() { return g_network != nullptr; }

@@ -42,6 +42,12 @@ bool initFromFile(const std::string& path, int device = 0);
 void shutdown();
 [[nodiscard]] bool isNetworkLoaded();
 [[nodiscard]] SpNnue* getNetwork(int device = -1); /* -1: the device passed to init */
+/* One more evaluator context (network copy, stream, slot store) on the device given to init, from the same image: what a
+ * further host scheduler thread binds to.  The reference keeps one network copy per NUMA node and hands a thread the copy of
+ * its node (nnue.cpp:267-277, 314-320; search.cpp:206); here the unit is the host thread, because a context's entry points
+ * are serialised on its stream.  nullptr (and lastError()) on failure.  Contexts still alive at shutdown() are destroyed there. */
+[[nodiscard]] SpNnue* createContext();
+void destroyContext(SpNnue* ctx);
 [[nodiscard]] const char* lastError();
 
 /* The reference's UpdateContext carries the add/sub lists the observer collected

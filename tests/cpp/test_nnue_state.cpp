@@ -8,6 +8,7 @@
  */
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "../../stormphrax_b200/csrc/host/nnue_state.h"
@@ -95,6 +96,53 @@ int main(int argc, char** argv) {
             for (int g = 0; g < kGames; ++g)
                 expect(out[g] == eval::NnueState::evaluateOnce(games[g], games[g].stm()), "batched evaluate", games[g]);
         }
+    }
+    /* several host threads, each a scheduler with its own evaluator context (createContext): 16 games per thread through its own
+     * EvalBatch, all threads submitting to the GPU at once; results against the stack-free path afterwards on this thread */
+    {
+        constexpr int kThreads = 4, kGames = 16, kPlies = 24;
+        std::vector<SpNnue*> contexts(kThreads, eval::getNetwork());
+        for (int t = 1; t < kThreads; ++t) {
+            contexts[t] = eval::createContext();
+            if (!contexts[t]) return 6;
+        }
+        std::vector<std::vector<Position>> seen(kThreads);
+        std::vector<std::vector<int32_t>> values(kThreads);
+        std::vector<std::thread> workers;
+        for (int t = 0; t < kThreads; ++t) {
+            workers.emplace_back([&, t] {
+                uint64_t rng = 0xD1B54A32D192ED03ULL * static_cast<uint64_t>(t + 1);
+                const auto pick = [&rng](int n) {
+                    rng ^= rng << 13, rng ^= rng >> 7, rng ^= rng << 17;
+                    return static_cast<int>((rng >> 33) % static_cast<uint64_t>(n));
+                };
+                std::vector<eval::NnueState> states;
+                std::vector<Position> games(kGames, Position::startpos());
+                /* thread 0 shares the first context with the states above: slots past theirs */
+                const uint32_t base = t == 0 ? 64 * eval::NnueState::kStackDepth : 0;
+                for (int g = 0; g < kGames; ++g)
+                    states.emplace_back(contexts[t], base + static_cast<uint32_t>(g) * eval::NnueState::kStackDepth);
+                eval::EvalBatch batch{contexts[t]};
+                std::vector<int32_t> out(kGames);
+                for (int g = 0; g < kGames; ++g) states[g].invalidate();
+                for (int ply = 0; ply < kPlies; ++ply) {
+                    for (int g = 0; g < kGames; ++g) {
+                        Move moves[256];
+                        const int n = games[g].generateLegal(moves);
+                        if (n) games[g] = games[g].applyMove(moves[pick(n)], states[g].push());
+                        else states[g].push();
+                        states[g].evaluateAsync(batch, games[g], games[g].stm(), &out[g]);
+                    }
+                    if (batch.flush() != SP_OK) std::abort();
+                    for (int g = 0; g < kGames; ++g) seen[t].push_back(games[g]), values[t].push_back(out[g]);
+                }
+            });
+        }
+        for (auto& w : workers) w.join();
+        for (int t = 0; t < kThreads; ++t)
+            for (size_t i = 0; i < seen[t].size(); ++i)
+                expect(values[t][i] == eval::NnueState::evaluateOnce(seen[t][i], seen[t][i].stm()), "threaded contexts", seen[t][i]);
+        for (int t = 1; t < kThreads; ++t) eval::destroyContext(contexts[t]);
     }
     eval::shutdown();
     std::printf("%d checks, %d failures\n", g_checks, g_failures);

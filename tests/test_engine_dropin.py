@@ -124,3 +124,30 @@ def test_batched_reference_selfplay_games_as_fibers(net_path, golden):
     nodes, checksum, rounds, evaluations = _games(_run(b200, net_path, "games", g["n"], g["soft_nodes"], g["plies"], g["seed"], 1))
     assert (nodes, checksum) == (g["nodes"], g["checksum"])
     assert rounds > 0 and evaluations / rounds > g["n"] / 2  # really batched: most games contribute to a round
+
+
+@pytest.mark.gpu
+def test_fiber_schedulers_on_several_host_threads(net_path, golden):
+    """datagen's "N threads" (datagen.cpp:378-384) on one GPU: the searches / games are shared out to host threads, each a fiber
+    scheduler with its own evaluator context (eval::createContext: network copy, stream, slot store) submitting its own batches.
+    Same trees, whichever thread and context a search ran on."""
+    b200 = _engine("sp_engine_b200")
+    s, g = golden["searches"], golden["games"]
+    assert _searches(_run(b200, net_path, "searches", s["n"], s["depth"], 1, 3)) == s["nodes"]
+    # four searches alive per scheduler, the others queued: finished fibers take the next search and its slots are reused
+    assert _searches(_run(b200, net_path, "searches", s["n"], s["depth"], 1, 3, 4)) == s["nodes"]
+    assert _searches(_run(b200, net_path, "searches", s["n"], s["depth"], 1, 1, 5)) == s["nodes"]
+    nodes, checksum, rounds, evaluations = _games(_run(b200, net_path, "games", g["n"], g["soft_nodes"], g["plies"], g["seed"], 1, 4))
+    assert (nodes, checksum) == (g["nodes"], g["checksum"])
+    assert rounds > 0 and evaluations / rounds > g["n"] / 4 / 2  # four schedulers of four games each, still batched
+
+
+def test_reference_engine_cpu_threads_share_the_jobs(net_path, golden):
+    """The CPU build's counterpart of the threaded run (plain host threads over its own evaluation): same node counts."""
+    from oracle.bind import ref_isa_available
+
+    if "avx2" not in ref_isa_available():
+        pytest.skip("host cannot run the AVX2 build of the reference")
+    cpu = _engine("sp_engine_cpu")
+    s = golden["searches"]
+    assert _searches(_run(cpu, net_path, "searches", s["n"], s["depth"], 1, 3)) == s["nodes"]

@@ -16,7 +16,7 @@ def _compile(tmp_path) -> str:
     lib = build.build()
     exe = str(tmp_path / "test_nnue_state")
     subprocess.run(
-        ["g++", "-std=c++17", "-O2", "-o", exe, SRC, f"-L{os.path.dirname(lib)}", "-lsp_nnue", f"-Wl,-rpath,{os.path.dirname(lib)}"],
+        ["g++", "-std=c++17", "-O2", "-pthread", "-o", exe, SRC, f"-L{os.path.dirname(lib)}", "-lsp_nnue", f"-Wl,-rpath,{os.path.dirname(lib)}"],
         check=True,
     )
     return exe
