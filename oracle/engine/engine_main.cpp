@@ -224,6 +224,17 @@ namespace {
                 auto& pos = thread.rootPos;
                 thread.nnueState.reset(pos); // datagen.cpp:179
                 for (u32 ply = 0; ply < plies; ++ply) {
+                    { // a game that has ended (mate or stalemate on the board) has no root move to search
+                        ScoredMoveList moves;
+                        generateAll(moves, pos);
+                        bool anyLegal = false;
+                        for (const auto [move, score] : moves) {
+                            anyLegal = anyLegal || pos.isLegal(move);
+                        }
+                        if (!anyLegal) {
+                            break;
+                        }
+                    }
                     const auto [score, normScore] = searcher.runDatagenSearch(); // datagen.cpp:206
                     nodes[i] += thread.search.loadNodes();
                     thread.search = search::SearchData{};
