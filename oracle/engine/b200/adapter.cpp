@@ -277,6 +277,14 @@ namespace stormphrax::eval {
             }
         } // namespace
 
+        void reserveStates(u32 states) {
+            const auto slots = usize{s_nextSlot.load()} + usize{states} * mirror::NnueState::kStackDepth;
+            if (sp_nnue_slots_reserve(mirror::getNetwork(), slots) != SP_OK) {
+                eprintln("reserveStates: {}", sp_nnue_last_error(mirror::getNetwork()));
+                std::abort();
+            }
+        }
+
         Stats runFibers(std::vector<std::function<void()>>& jobs, usize stackBytes, u32 threads, usize width) {
             threads = std::max<u32>(1, std::min<u32>(threads, static_cast<u32>(std::max<usize>(jobs.size(), 1))));
             if (width == 0) {

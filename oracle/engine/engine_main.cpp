@@ -63,6 +63,7 @@ namespace stormphrax::eval {
             u64 rounds{};
             u64 evaluations{};
         };
+        inline void reserveStates(u32) {}
         inline Stats runFibers(std::vector<std::function<void()>>& jobs, usize = 0, u32 threads = 1, usize = 0) {
             std::atomic<usize> nextJob{0};
             const auto work = [&jobs, &nextJob] {
@@ -148,6 +149,7 @@ namespace {
     int searches(u32 n, i32 depth, bool fibers, u32 threads, usize width) {
         opts::mutableOpts().chess960 = false;
         util::rng::SeedGenerator seeds{1234};
+        eval::batch::reserveStates(n);
         std::vector<std::unique_ptr<search::Searcher>> searchers(n);
         std::vector<usize> nodes(n, 0);
         std::vector<std::function<void()>> jobs;
@@ -201,6 +203,7 @@ namespace {
     int games(u32 n, usize softNodes, u32 plies, u64 seed, bool fibers, u32 threads, usize width) {
         opts::mutableOpts().chess960 = false;
         util::rng::SeedGenerator seeds{seed};
+        eval::batch::reserveStates(n);
         std::vector<std::unique_ptr<search::Searcher>> searchers(n);
         std::vector<usize> nodes(n, 0);
         std::vector<u64> sums(n, 0);
