@@ -238,6 +238,7 @@ def run_reference(args, rank: int, world: int):
         prate, pinfo, _ = cpu_arm(pb, pm, ps, "playouts", 6.0)
         line["workloads"] = {"playouts": {"value": prate / 1e6, "unit": UNIT, **{k: pinfo[k] for k in ("cores", "kind", "sample", "isa")}}}
         line["workloads"]["engine_bench"] = engine_bench()
+        line["workloads"]["engine_games"] = engine_games()
     print(json.dumps(line), flush=True)
 
 
@@ -263,6 +264,35 @@ def engine_bench(depth: int = 3):
             m = re.search(r"^(\d+) nodes (\d+) nps", out, re.M)
             return {"config": f"`bench` depth {depth}, 52 positions, 16 MiB hash, 1 thread (BASELINE configs[0]); synthetic tame network seed 7",
                     "nodes": int(m.group(1)), "nps": int(m.group(2)), "unit": "nodes/s", "threads": 1}
+        except Exception as e:  # pragma: no cover
+            return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+def engine_games(games: int = 256, soft_nodes: int = 400, plies: int = 4):
+    """BASELINE configs[4] in miniature on the CPU: self-play games with the reference's own datagen search (runDatagenSearch at a soft
+    node limit, src/datagen/datagen.cpp:113-121, 206-260) on its own CPU evaluation, shared out to every host core
+    (oracle/_ref/sp_engine_cpu `games`).  profiles/r2_engine_on_gpu.md holds the same games played on the GPU evaluator."""
+    import re
+    import subprocess
+    import tempfile
+
+    from stormphrax_b200 import net as N
+
+    engine = os.path.join(ROOT, "oracle", "_ref", "sp_engine_cpu")
+    if not os.path.exists(engine):
+        return {"unavailable": "oracle/_ref/sp_engine_cpu not built"}
+    cores = os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "tame.nnue")
+        N.synthetic(7, tame=True).image.tofile(path)
+        try:
+            out = subprocess.run([engine, path, "games", str(games), str(soft_nodes), str(plies), "42", "1", str(cores)],
+                                 capture_output=True, text=True, timeout=300).stdout
+            m = re.search(r"nodes: (\d+) nodes ([0-9.]+) seconds (\d+) nps checksum ([0-9a-f]+)", out)
+            return {"config": f"{games} self-play games x {plies} moves, datagen search with soft limit {soft_nodes} nodes, seed 42 "
+                              f"(BASELINE configs[4] in miniature); synthetic tame network seed 7",
+                    "nodes": int(m.group(1)), "seconds": float(m.group(2)), "nps": int(m.group(3)), "unit": "nodes/s",
+                    "threads": cores, "checksum": m.group(4)}
         except Exception as e:  # pragma: no cover
             return {"unavailable": f"{type(e).__name__}: {e}"}
 
